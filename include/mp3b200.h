@@ -1,0 +1,171 @@
+/* mp3b200.h — C ABI of the B200-native MP3 encode engine (libmp3b200.so).
+ *
+ * Drop-in boundary for the encode path of mierau/swift-mp3.  Citations are into the reference's
+ * Sources/SwiftMP3/MP3Encoder.swift ("SRC").  No torch / C++ types cross this boundary: plain pointers and
+ * sizes only.  All functions return 0 (MP3B_OK) or a negative mp3b_status; mp3b_last_error() gives the text
+ * of the calling thread's most recent failure.
+ *
+ * Two planes:
+ *   session plane — one handle == one reference `EncoderSession` (SRC:237-350); what a Swift facade binds.
+ *   batch plane   — N independent sessions that share options and advance together; every call is ONE pass
+ *                   of the device pipeline over all streams (this is what the GPU wants; a session is a
+ *                   batch of one).
+ * Handles are not thread-safe; distinct handles may be used from different threads.  There is no CPU
+ * fallback: creation fails with MP3B_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef MP3B200_H
+#define MP3B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MP3B_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  MP3B_OK = 0,
+  MP3B_ERR_BAD_ARG = -1,          /* null pointer, unsupported option value, bad stream index */
+  MP3B_ERR_CUDA = -2,             /* CUDA runtime failure (sticky for the handle) */
+  MP3B_ERR_OOM = -3,              /* host or device allocation failed */
+  MP3B_ERR_BUFFER_TOO_SMALL = -4, /* *written holds the size needed; the data stays pending in the handle */
+  MP3B_ERR_INTERNAL = -5          /* an engine limit was exceeded (e.g. reservoir backlog > 8 KiB) */
+} mp3b_status;
+
+/* MP3EncoderOptions, SRC:57-116.  mode: 0 = .mono, 1 = .stereo, 2 = .jointStereo (SRC:59-63).
+ * quality is clamped to 0...9 like SRC:110.  sample_rate must be > 0; a sample rate / bitrate pair whose
+ * MPEG-1 frame would be smaller than header + side info (the reference traps there) is MP3B_ERR_BAD_ARG. */
+typedef struct mp3b_options {
+  int32_t sample_rate;   /* default 44100 */
+  int32_t bitrate_kbps;  /* default 128; CBR rate or VBR base rate */
+  int32_t vbr;           /* default 0 */
+  int32_t mode;          /* default 1 (.stereo) */
+  int32_t quality;       /* default 5 */
+  int32_t crc_protected; /* default 0 */
+  int32_t original;      /* default 1 */
+  int32_t copyright;     /* default 0 */
+} mp3b_options;
+
+/* ID3Tag, SRC:8-54.  NULL string = nil; negative number = nil. */
+typedef struct mp3b_id3 {
+  const char *title, *artist, *album, *genre, *comment;
+  int32_t track, track_total, year;
+  const uint8_t *album_art;
+  size_t album_art_len;
+  const char *album_art_mime; /* NULL = "image/jpeg" (SRC:41) */
+} mp3b_id3;
+
+typedef struct mp3b_session mp3b_session;
+typedef struct mp3b_batch mp3b_batch;
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+int mp3b_version(void);
+const char *mp3b_last_error(void);
+/* Fills *opts with the reference defaults (MP3EncoderOptions.init, SRC:95-115). */
+void mp3b_options_default(mp3b_options *opts);
+/* Number of usable CUDA devices (compute capability 10.x). */
+int mp3b_device_count(int *count);
+
+/* ---- session plane: EncoderSession ------------------------------------------------------------------ */
+/* MP3Encoder.newSession(), SRC:143-145 / EncoderSession.init, SRC:268-282.  device = CUDA ordinal. */
+int mp3b_session_create(const mp3b_options *opts, int device, mp3b_session **out);
+void mp3b_session_destroy(mp3b_session *s);
+/* EncoderSession.encode(samples:), SRC:297-310.  pcm = interleaved f32 in [-1, 1], any length (0 allowed).
+ * Writes 0...k whole MP3 frames to out; the first full frame of a session yields 0 bytes (one-frame delay,
+ * SRC:546-562).  If cap is too small: MP3B_ERR_BUFFER_TOO_SMALL, *written = bytes needed, and the frames
+ * stay pending — fetch them with mp3b_session_take_output before the next encode/flush. */
+int mp3b_session_encode(mp3b_session *s, const float *pcm, size_t n_floats, uint8_t *out, size_t cap, size_t *written);
+/* EncoderSession.flush(), SRC:318-350.  Idempotent after the first call. */
+int mp3b_session_flush(mp3b_session *s, uint8_t *out, size_t cap, size_t *written);
+int mp3b_session_take_output(mp3b_session *s, uint8_t *out, size_t cap, size_t *written);
+/* Upper bound of the bytes one encode(n_floats) / flush() call can return for this session. */
+size_t mp3b_session_output_bound(const mp3b_session *s, size_t n_floats);
+/* EncoderSession.generateXingHeader(), SRC:367-449 (uses the counters as of now). */
+int mp3b_session_xing_header(const mp3b_session *s, uint8_t *out, size_t cap, size_t *written);
+/* EncoderSession.encodedFrameCount / encodedByteCount, SRC:261-264. */
+uint32_t mp3b_session_frame_count(const mp3b_session *s);
+uint32_t mp3b_session_byte_count(const mp3b_session *s);
+/* EncoderSession.generateID3Tag() / ID3TagWriter.build, SRC:355-358, 1040-1075.  Empty tag -> 0 bytes. */
+int mp3b_id3_build(const mp3b_id3 *tag, uint8_t *out, size_t cap, size_t *written);
+
+/* ---- batch plane ------------------------------------------------------------------------------------ */
+/* n_streams independent EncoderSessions with the same options on one device. */
+int mp3b_batch_create(const mp3b_options *opts, int n_streams, int device, mp3b_batch **out);
+/* Same with an explicit pass size (frames of every stream processed per device pass; 0 = automatic). */
+int mp3b_batch_create_ex(const mp3b_options *opts, int n_streams, int device, int frames_per_pass, mp3b_batch **out);
+int mp3b_batch_frames_per_pass(const mp3b_batch *b);
+void mp3b_batch_destroy(mp3b_batch *b);
+int mp3b_batch_stream_count(const mp3b_batch *b);
+/* One encode(samples:) per stream: pcm[i] = HOST pointer to n_floats[i] interleaved floats (may be 0 / NULL).
+ * flush != 0 additionally performs flush() on every stream afterwards (SRC:318-350).  flush_mask (may be
+ * NULL) restricts the flush to streams with a non-zero byte.  The H2D copies, the device pipeline and the
+ * D2H copy of the produced frames all happen inside the call; results are read with mp3b_batch_output. */
+int mp3b_batch_encode(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, int flush, const uint8_t *flush_mask);
+/* Same, but pcm[i] are DEVICE pointers (same device, 4-byte aligned) and the produced frames stay in device
+ * memory; only the per-stream byte counts come back.  download != 0 also copies the frames to the host. */
+int mp3b_batch_encode_device(mp3b_batch *b, const float *const *d_pcm, const size_t *n_floats, int flush, int download);
+/* Result of the last call for stream i: *data points into batch-owned pinned host memory (valid until the next
+ * encode on this batch), *len = bytes (whole frames). */
+int mp3b_batch_output(const mp3b_batch *b, int stream, const uint8_t **data, size_t *len);
+/* Device-side view of the same result (valid after either encode variant). */
+int mp3b_batch_output_device(const mp3b_batch *b, int stream, const uint8_t **d_data, size_t *len);
+/* Total bytes produced by the last call over all streams. */
+size_t mp3b_batch_output_total(const mp3b_batch *b);
+int mp3b_batch_xing_header(const mp3b_batch *b, int stream, uint8_t *out, size_t cap, size_t *written);
+uint32_t mp3b_batch_frame_count(const mp3b_batch *b, int stream);
+uint32_t mp3b_batch_byte_count(const mp3b_batch *b, int stream);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) so callers can stage PCM for full-speed H2D. */
+int mp3b_host_alloc(size_t bytes, void **out);
+void mp3b_host_free(void *p);
+/* Device memory helpers for the device plane. */
+int mp3b_device_alloc(int device, size_t bytes, void **out);
+void mp3b_device_free(int device, void *p);
+int mp3b_device_copy(int device, void *dst, const void *src, size_t bytes, int kind /* 0 H2D, 1 D2H, 2 D2D */);
+int mp3b_device_sync(int device);
+
+/* ---- measurement / test plane (not part of the reference API) ---------------------------------------- */
+/* Per-stage device time of the last batch call, in milliseconds, summed over the call's passes.
+ * Stage order: see MP3B_STAGE_*.  n = entries available in ms[]. */
+enum {
+  MP3B_STAGE_H2D = 0, MP3B_STAGE_PREPASS, MP3B_STAGE_SPECTRUM, MP3B_STAGE_SCAN, MP3B_STAGE_PACK, MP3B_STAGE_FRAMES,
+  MP3B_STAGE_D2H, MP3B_STAGE_TOTAL, MP3B_STAGE_COUNT
+};
+int mp3b_batch_stage_ms(const mp3b_batch *b, float *ms, int n);
+/* Number of kernel launches issued by the last batch call. */
+int mp3b_batch_launch_count(const mp3b_batch *b);
+/* Enable per-granule-channel traces (costs device memory and bandwidth; off by default).  bit0: keep MDCT
+ * spectra, bit1: keep quantized ix, bit2: also run the (dead, SRC:737) masking-threshold kernel. */
+int mp3b_batch_set_trace(mp3b_batch *b, int flags);
+/* Granule-channel record of the last call, in encode order per stream (frame-major, then gr, then ch). */
+typedef struct mp3b_gc_record {
+  int32_t part23_length, big_values, global_gain, gain_used, block_type, subblock_gain[3];
+  int32_t region0, region1, preflag, g0, max_bits, iterations;
+  float energy;
+} mp3b_gc_record;
+typedef struct mp3b_frame_record {
+  int32_t bitrate_index, padding, frame_size, main_data_size, main_data_begin, reservoir_bits, huff_bytes, ms, is_final;
+  float frame_energy;
+} mp3b_frame_record;
+/* Number of frames the last call encoded for `stream` (its granule-channel count is frames * 2 * channels). */
+int mp3b_batch_trace_frames(const mp3b_batch *b, int stream);
+int mp3b_batch_trace_frame_records(const mp3b_batch *b, int stream, mp3b_frame_record *out, int cap);
+int mp3b_batch_trace_gc_records(const mp3b_batch *b, int stream, mp3b_gc_record *out, int cap);
+/* kind: 0 spectrum f32[576], 1 ix i32[576], 2 thresholds f32[576]; out holds cap_gc * 576 elements. */
+int mp3b_batch_trace_gc_array(const mp3b_batch *b, int stream, int kind, void *out, int cap_gc);
+/* Product tables for cross-checks against the oracle / the reference literals.
+ * which: 0 window[512] f32, 1 analysis[32*64] f32, 2 mdct_long[18*36] f32, 3 mdct_short[6*12] f32,
+ * 4 win_long[36] f32, 5 win_short[12] f32, 6 inv_step[256] f32, 7 len15[256] u8, 8 code15[256] u8,
+ * 9 gain_threshold[256] f64, 10 alias_cs[8] f32, 11 alias_ca[8] f32, 12 sfb_cum[3*21] i32.
+ * Returns the element count, or a negative status. */
+int mp3b_table(int which, void *out, size_t cap_bytes);
+/* Deterministic synthetic PCM written straight into device memory (bench / tests): stream `seed` of the
+ * BASELINE C1/C4 recipe — L = a*sin(2*pi*fL*t) + n*N(0,1), R likewise with fR and phase 0.3, clipped to
+ * [-1, 1]; interleaved when channels == 2. */
+int mp3b_synth_fill(int device, float *d_pcm, size_t n_samples_per_channel, int channels, int sample_rate,
+                    float f_left, float f_right, float amp, float noise, uint64_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MP3B200_H */

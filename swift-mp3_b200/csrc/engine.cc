@@ -1,0 +1,701 @@
+// Host engine + C ABI (include/mp3b200.h) of the B200-native MP3 encode path.
+// SRC = Sources/SwiftMP3/MP3Encoder.swift of the reference.  There is no CPU fallback anywhere in this file: every
+// encode call runs the CUDA pipeline of kernels.cu, and creation fails when no sm_100 device is usable.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/mp3b200.h"
+#include "kernels.h"
+#include "tables.h"
+#include "tables_gen.h"
+
+using namespace mp3b;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? MP3B_ERR_OOM : MP3B_ERR_CUDA, \
+                                       "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <class T> inline T round_up(T v, T a) { return (v + a - 1) / a * a; }
+
+std::mutex g_dev_mu;
+bool g_tables_uploaded[64] = {};
+
+int usable_device(int device) {
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return p.major == 10;
+}
+
+}  // namespace
+
+struct mp3b_batch {
+  Config cfg{};
+  mp3b_options opt{};
+  int device = 0, S = 0, ch = 0, Fc = 0, GC = 0;
+  cudaStream_t st = nullptr;
+  PassBuffers pb{};
+  float *d_head[2] = {nullptr, nullptr};
+  int head_sel = 0;
+  float *d_stage = nullptr; size_t stage_stride = 0;   // floats per stream
+  StreamPlan *h_plan = nullptr;                          // pinned [S]
+  StreamState *h_state = nullptr;                        // pinned [S]
+  uint16_t *h_emit_size = nullptr; uint32_t *h_emit_n = nullptr;
+  uint64_t *d_offsets = nullptr, *h_offsets = nullptr;
+  uint8_t *d_compact = nullptr; size_t compact_cap = 0;
+  uint8_t *h_out = nullptr; size_t h_out_cap = 0;
+  size_t out_cap_bytes = 0;                              // allocation size of pb.out
+  size_t out_total = 0;
+  bool have_host_out = false;
+  std::vector<uint32_t> pending;                         // floats waiting after the carried frame, per stream
+  std::vector<uint32_t> out_len;
+  std::vector<uint32_t> frame_count, byte_count;
+  std::vector<std::vector<uint16_t>> frame_sizes;       // SRC:258
+  int max_frame_bytes = 0;
+  int sticky = 0;
+  // measurement
+  float stage_ms[MP3B_STAGE_COUNT] = {};
+  int launches = 0;
+  cudaEvent_t ev[MP3B_STAGE_COUNT + 1] = {};
+  // trace
+  int trace = 0;
+  std::vector<std::vector<mp3b_frame_record>> tr_frames;
+  std::vector<std::vector<mp3b_gc_record>> tr_gc;
+  std::vector<std::vector<float>> tr_spec, tr_thr;
+  std::vector<std::vector<int32_t>> tr_ix;
+  std::vector<FrameRec> h_rec;
+};
+
+struct mp3b_session {
+  mp3b_batch *b = nullptr;
+  std::vector<uint8_t> pending_out;
+};
+
+namespace {
+
+int fill_config(const mp3b_options &o, int n_streams, Config &c) {
+  if (o.sample_rate <= 0) return fail(MP3B_ERR_BAD_ARG, "sample_rate must be > 0");
+  if (o.mode < 0 || o.mode > 2) return fail(MP3B_ERR_BAD_ARG, "mode must be 0 (mono), 1 (stereo) or 2 (jointStereo)");
+  memset(&c, 0, sizeof c);
+  c.n_streams = n_streams;
+  c.channels = o.mode == 0 ? 1 : 2;                              // SRC:300
+  c.fsc = 1152 * c.channels;
+  c.sample_rate = o.sample_rate; c.base_kbps = o.bitrate_kbps; c.vbr = o.vbr ? 1 : 0; c.mode = o.mode;
+  c.quality = std::min(9, std::max(0, o.quality));               // SRC:110
+  c.crc = o.crc_protected ? 1 : 0; c.original = o.original ? 1 : 0; c.copyright = o.copyright ? 1 : 0;
+  c.sr_index = sample_rate_index(o.sample_rate); c.sfb_index = sfb_table_index(o.sample_rate);
+  c.side_bytes = c.channels == 1 ? 17 : 32;
+  c.header_bytes = 4 + (c.crc ? 2 : 0) + c.side_bytes;
+  if (o.mode == 0) { c.mode_bits = 3; c.mode_ext = 0; } else if (o.mode == 2) { c.mode_bits = 1; c.mode_ext = 2; } else { c.mode_bits = 0; c.mode_ext = 0; }
+  c.cbr_index = bitrate_index(o.bitrate_kbps, o.sample_rate);
+  for (int i = 0; i < 16; ++i) {
+    long long num = 144LL * bitrate_value(i) * 1000;             // SRC:490-495
+    c.frame_base[i] = (int)(num / o.sample_rate); c.frame_rem[i] = (int)(num % o.sample_rate);
+  }
+  for (int k = 0; k <= 320; ++k) c.vbr_idx_of_kbps[k] = (uint8_t)bitrate_index(k, o.sample_rate);
+  // every bitrate index the session can reach must leave room for header + side info (the reference traps otherwise)
+  int lo_idx = c.cbr_index, hi_idx = c.cbr_index;
+  if (c.vbr) {
+    int lo = std::max(32, c.base_kbps - 64 + c.quality * 8), hi = std::min(320, c.base_kbps + 64 - c.quality * 4);
+    lo_idx = 15; hi_idx = 0;
+    for (int k = std::min(lo, hi); k <= std::max(lo, hi); ++k) { lo_idx = std::min<int>(lo_idx, c.vbr_idx_of_kbps[k]); hi_idx = std::max<int>(hi_idx, c.vbr_idx_of_kbps[k]); }
+  }
+  for (int i = lo_idx; i <= hi_idx; ++i)
+    if (c.frame_base[i] - c.header_bytes < 2 * c.channels || c.frame_base[i] + 1 > 65000)
+      return fail(MP3B_ERR_BAD_ARG, "bitrate index %d at %d Hz gives a %d-byte frame: unusable", i, o.sample_rate, c.frame_base[i]);
+  return MP3B_OK;
+}
+
+int max_frame_bytes_of(const Config &c) {
+  int m = 0;
+  if (!c.vbr) return c.frame_base[c.cbr_index] + 1;
+  for (int k = 0; k <= 320; ++k) m = std::max(m, c.frame_base[c.vbr_idx_of_kbps[k]] + 1);
+  return m;
+}
+
+void free_batch(mp3b_batch *b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->st) cudaStreamSynchronize(b->st);
+  PassBuffers &p = b->pb;
+  void *dev[] = {p.plan, p.state, b->d_head[0], b->d_head[1], p.ms, p.frame_energy, p.gc_energy, p.gc_bt, p.frame_br, p.smag,
+                 p.gc_meta, p.gc_bits, p.gc_bv, p.gc_bitoff, p.gc_sel, p.fr_md, p.rec, p.md, p.md_tail, p.md_carry, p.out,
+                 p.emit_size, p.emit_n, p.tr_spectrum, p.tr_ix, p.tr_thr, b->d_stage, b->d_offsets, b->d_compact};
+  for (void *q : dev) if (q) cudaFree(q);
+  void *host[] = {b->h_plan, b->h_state, b->h_emit_size, b->h_emit_n, b->h_offsets, b->h_out};
+  for (void *q : host) if (q) cudaFreeHost(q);
+  for (auto &e : b->ev) if (e) cudaEventDestroy(e);
+  if (b->st) cudaStreamDestroy(b->st);
+  cudaGetLastError();
+  delete b;
+}
+
+template <class T> cudaError_t dalloc(T *&p, size_t n, bool zero = true) {
+  cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T));
+  if (e == cudaSuccess && zero) e = cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T));
+  return e;
+}
+
+int create_batch(const mp3b_options *opts, int n_streams, int device, int frames_per_pass, mp3b_batch **out) {
+  if (!opts || !out || n_streams <= 0) return fail(MP3B_ERR_BAD_ARG, "null options / out or n_streams <= 0");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return fail(MP3B_ERR_CUDA, "no CUDA device: the engine has no CPU fallback"); }
+  if (device < 0 || device >= count) return fail(MP3B_ERR_BAD_ARG, "device %d out of range (%d devices)", device, count);
+  if (!usable_device(device)) return fail(MP3B_ERR_CUDA, "device %d is not compute capability 10.x (sm_100a kernels only)", device);
+  Config cfg;
+  int rc = fill_config(*opts, n_streams, cfg);
+  if (rc) return rc;
+  CU(cudaSetDevice(device));
+  {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (device < 64 && !g_tables_uploaded[device]) { CU(upload_tables()); g_tables_uploaded[device] = true; }
+  }
+  mp3b_batch *b = new mp3b_batch();
+  b->cfg = cfg; b->opt = *opts; b->opt.quality = cfg.quality; b->device = device; b->S = n_streams; b->ch = cfg.channels;
+  int Fc = frames_per_pass > 0 ? frames_per_pass : (int)std::min<long long>(4096, std::max<long long>(8, 262144 / n_streams));
+  b->Fc = Fc; b->GC = Fc * 2 * cfg.channels;
+  b->max_frame_bytes = max_frame_bytes_of(cfg);
+  const size_t S = n_streams, GC = b->GC;
+  PassBuffers &p = b->pb;
+  p.Fc = Fc; p.GC = b->GC;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  A(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
+  A(dalloc(p.plan, S)); A(dalloc(p.state, S));
+  A(dalloc(b->d_head[0], S * 2 * cfg.fsc)); A(dalloc(b->d_head[1], S * 2 * cfg.fsc));
+  A(dalloc(p.ms, S * (Fc + 1))); A(dalloc(p.frame_energy, S * Fc)); A(dalloc(p.gc_energy, S * (10 + GC)));
+  A(dalloc(p.gc_bt, S * GC)); A(dalloc(p.frame_br, S * Fc)); A(dalloc(p.smag, S * GC * 576, false));
+  A(dalloc(p.gc_meta, S * GC)); A(dalloc(p.gc_bits, S * GC * kMaxEntries)); A(dalloc(p.gc_bv, S * GC * kMaxEntries));
+  A(dalloc(p.gc_bitoff, S * GC)); A(dalloc(p.gc_sel, S * GC)); A(dalloc(p.fr_md, S * Fc * 2)); A(dalloc(p.rec, S * (Fc + 1)));
+  p.md_stride = round_up<size_t>(kMdCarryCap + (size_t)Fc * 2 * cfg.channels * 540, 16);
+  A(dalloc(p.md, S * p.md_stride, false)); A(dalloc(p.md_tail, S * 4)); A(dalloc(p.md_carry, S * kMdCarryCap));
+  A(dalloc(p.emit_size, S * (Fc + 1))); A(dalloc(p.emit_n, S));
+  A(dalloc(b->d_offsets, S + 1));
+  A(cudaHostAlloc((void **)&b->h_plan, S * sizeof(StreamPlan), cudaHostAllocDefault));
+  A(cudaHostAlloc((void **)&b->h_state, S * sizeof(StreamState), cudaHostAllocDefault));
+  A(cudaHostAlloc((void **)&b->h_emit_size, S * (Fc + 1) * sizeof(uint16_t), cudaHostAllocDefault));
+  A(cudaHostAlloc((void **)&b->h_emit_n, S * sizeof(uint32_t), cudaHostAllocDefault));
+  A(cudaHostAlloc((void **)&b->h_offsets, (S + 1) * sizeof(uint64_t), cudaHostAllocDefault));
+  for (auto &ev : b->ev) A(cudaEventCreate(&ev));
+  if (e != cudaSuccess) {
+    free_batch(b);
+    return fail(e == cudaErrorMemoryAllocation ? MP3B_ERR_OOM : MP3B_ERR_CUDA, "batch allocation failed: %s", cudaGetErrorString(e));
+  }
+  b->pending.assign(S, 0); b->out_len.assign(S, 0); b->frame_count.assign(S, 0); b->byte_count.assign(S, 0);
+  b->frame_sizes.resize(S);
+  *out = b;
+  return MP3B_OK;
+}
+
+int ensure_out(mp3b_batch *b, size_t stride) {
+  stride = round_up<size_t>(stride, 16);
+  size_t need = stride * b->S;
+  if (need > b->out_cap_bytes) {
+    if (b->pb.out) cudaFree(b->pb.out);
+    b->pb.out = nullptr; b->out_cap_bytes = 0;
+    CU(cudaMalloc((void **)&b->pb.out, need));
+    b->out_cap_bytes = need;
+  }
+  b->pb.out_stride = stride;
+  return MP3B_OK;
+}
+
+int ensure_trace(mp3b_batch *b) {
+  PassBuffers &p = b->pb;
+  const size_t n = (size_t)b->S * b->GC * 576;
+  if ((b->trace & 1) && !p.tr_spectrum) CU(dalloc(p.tr_spectrum, n));
+  if ((b->trace & 2) && !p.tr_ix) CU(dalloc(p.tr_ix, n));
+  if ((b->trace & 4) && !p.tr_thr) { CU(dalloc(p.tr_thr, n)); if (!p.tr_spectrum) CU(dalloc(p.tr_spectrum, n)); }
+  return MP3B_OK;
+}
+
+// One API call = encode(samples:) on every stream (+ optional flush()), split into passes of at most Fc frames.
+int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, bool device_ptrs, int flush,
+             const uint8_t *flush_mask, bool download) {
+  if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");
+  if (b->sticky) return fail(b->sticky, "batch is in a failed state: %s", g_err.c_str());
+  CU(cudaSetDevice(b->device));
+  const Config &cfg = b->cfg;
+  const int S = b->S, fsc = cfg.fsc, Fc = b->Fc;
+  std::vector<size_t> n(S, 0), cursor(S, 0);
+  std::vector<uint8_t> want_flush(S, 0), flushed(S, 0);
+  size_t max_frames = 0;
+  for (int s = 0; s < S; ++s) {
+    n[s] = (n_floats && pcm && pcm[s]) ? n_floats[s] : 0;
+    want_flush[s] = flush && (!flush_mask || flush_mask[s]);
+    size_t avail = b->pending[s] + n[s];
+    max_frames = std::max(max_frames, avail / fsc + 1);
+  }
+  int rc = ensure_out(b, (max_frames + 1) * (size_t)b->max_frame_bytes);
+  if (rc) return rc;
+  if (b->trace) { rc = ensure_trace(b); if (rc) return rc; }
+  if (!device_ptrs && !b->d_stage) {
+    b->stage_stride = (size_t)Fc * fsc;
+    CU(cudaMalloc((void **)&b->d_stage, (size_t)S * b->stage_stride * sizeof(float)));
+  }
+  for (auto &m : b->stage_ms) m = 0.0f;
+  b->launches = 0;
+  b->have_host_out = false;
+  if (b->trace) {
+    b->tr_frames.assign(S, {}); b->tr_gc.assign(S, {}); b->tr_spec.assign(S, {}); b->tr_ix.assign(S, {}); b->tr_thr.assign(S, {});
+  }
+  cudaStream_t st = b->st;
+  bool first = true;
+  for (;;) {
+    bool any = false;
+    // ---- plan
+    for (int s = 0; s < S; ++s) {
+      StreamPlan &pl = b->h_plan[s];
+      size_t remaining = n[s] - cursor[s];
+      size_t room = (size_t)Fc * fsc - b->pending[s];
+      size_t cur_n = std::min(remaining, room);
+      size_t total = b->pending[s] + cur_n;
+      uint32_t nfr = (uint32_t)(total / fsc), flags = first ? 4u : 0u;
+      uint32_t new_pending = (uint32_t)(total % fsc);
+      if (remaining == cur_n && want_flush[s] && !flushed[s]) {
+        if (new_pending > 0) {
+          if ((int)nfr < Fc) { nfr += 1; flags |= 3u; new_pending = 0; flushed[s] = 1; }
+        } else { flags |= 2u; flushed[s] = 1; }
+      }
+      pl.cur = device_ptrs ? (n[s] ? pcm[s] + cursor[s] : nullptr) : b->d_stage + (size_t)s * b->stage_stride;
+      pl.cur_n = (uint32_t)cur_n; pl.n_frames = nfr; pl.flags = flags; pl.head_n = (uint32_t)(fsc + b->pending[s]);
+      if (cur_n || nfr || (flags & 2u)) any = true;
+      // bookkeeping for the next pass
+      cursor[s] += cur_n;
+      b->pending[s] = new_pending;
+    }
+    if (!any && !first) break;
+    // one strided copy when every stream hands over the same amount from equally spaced host buffers
+    bool uniform = !device_ptrs && S > 1 && b->h_plan[0].cur_n > 0;
+    const size_t cur0 = b->h_plan[0].cur_n; ptrdiff_t pitch = 0;
+    for (int s = 0; s < S && uniform; ++s) {
+      if (b->h_plan[s].cur_n != cur0) { uniform = false; break; }
+      if (s >= 1) {
+        ptrdiff_t d = (const char *)(pcm[s] + cursor[s]) - (const char *)(pcm[s - 1] + cursor[s - 1]);
+        if (s == 1) pitch = d; else if (d != pitch) uniform = false;
+      }
+    }
+    // ---- H2D
+    CU(cudaEventRecord(b->ev[0], st));
+    if (!device_ptrs) {
+      if (uniform && pitch >= (ptrdiff_t)(cur0 * sizeof(float))) {
+        CU(cudaMemcpy2DAsync(b->d_stage, b->stage_stride * sizeof(float), pcm[0] + (cursor[0] - cur0), (size_t)pitch,
+                             cur0 * sizeof(float), S, cudaMemcpyHostToDevice, st));
+      } else {
+        for (int s = 0; s < S; ++s) {
+          size_t cur_n = b->h_plan[s].cur_n;
+          if (cur_n) CU(cudaMemcpyAsync(b->d_stage + (size_t)s * b->stage_stride, pcm[s] + (cursor[s] - cur_n), cur_n * sizeof(float),
+                                        cudaMemcpyHostToDevice, st));
+        }
+      }
+    }
+    CU(cudaMemcpyAsync(b->pb.plan, b->h_plan, (size_t)S * sizeof(StreamPlan), cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(b->ev[1], st));
+    // ---- device pipeline
+    PassBuffers pb = b->pb;
+    pb.head_in = b->d_head[b->head_sel]; pb.head_out = b->d_head[b->head_sel ^ 1];
+#define LAUNCH(expr)                                                                                        \
+  do {                                                                                                      \
+    int k = (expr);                                                                                             \
+    if (k < 0) { b->sticky = MP3B_ERR_CUDA; return fail(MP3B_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString((cudaError_t)(-k))); } \
+    b->launches += k;                                                                                       \
+  } while (0)
+    LAUNCH(launch_prepass(cfg, pb, st));
+    CU(cudaEventRecord(b->ev[2], st));
+    LAUNCH(launch_spectrum(cfg, pb, st));
+    LAUNCH(launch_curve(cfg, pb, st));
+    if (b->trace & 4) LAUNCH(launch_thresholds(cfg, pb, st));
+    CU(cudaEventRecord(b->ev[3], st));
+    LAUNCH(launch_scan(cfg, pb, st));
+    CU(cudaEventRecord(b->ev[4], st));
+    LAUNCH(launch_pack(cfg, pb, st));
+    CU(cudaEventRecord(b->ev[5], st));
+    LAUNCH(launch_frames(cfg, pb, st));
+    LAUNCH(launch_carry(cfg, pb, st));
+    CU(cudaEventRecord(b->ev[6], st));
+    b->head_sel ^= 1;
+    CU(cudaMemcpyAsync(b->h_emit_n, pb.emit_n, (size_t)S * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(b->h_emit_size, pb.emit_size, (size_t)S * (Fc + 1) * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    if (b->trace) {
+      b->h_rec.resize((size_t)S * (Fc + 1));
+      CU(cudaMemcpyAsync(b->h_rec.data(), pb.rec, b->h_rec.size() * sizeof(FrameRec), cudaMemcpyDeviceToHost, st));
+    }
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (se != cudaSuccess) { b->sticky = MP3B_ERR_CUDA; return fail(MP3B_ERR_CUDA, "device pipeline failed: %s", cudaGetErrorString(se)); }
+    {
+      static const int stage_of[6] = {MP3B_STAGE_H2D, MP3B_STAGE_PREPASS, MP3B_STAGE_SPECTRUM, MP3B_STAGE_SCAN, MP3B_STAGE_PACK, MP3B_STAGE_FRAMES};
+      for (int i = 0; i < 6; ++i) { float ms = 0; cudaEventElapsedTime(&ms, b->ev[i], b->ev[i + 1]); b->stage_ms[stage_of[i]] += ms; }
+      float ms = 0; cudaEventElapsedTime(&ms, b->ev[0], b->ev[6]); b->stage_ms[MP3B_STAGE_TOTAL] += ms;
+    }
+    for (int s = 0; s < S; ++s) {
+      uint32_t ne = b->h_emit_n[s];
+      const uint16_t *sz = b->h_emit_size + (size_t)s * (Fc + 1);
+      if (ne) b->frame_sizes[s].insert(b->frame_sizes[s].end(), sz, sz + ne);
+    }
+    if (b->trace) {
+      const int ngc = 2 * cfg.channels;
+      std::vector<float> tmpf; std::vector<int32_t> tmpi;
+      for (int s = 0; s < S; ++s) {
+        const uint32_t nf = b->h_plan[s].n_frames;
+        for (uint32_t f = 0; f < nf; ++f) {
+          const FrameRec &r = b->h_rec[(size_t)s * (Fc + 1) + 1 + f];
+          mp3b_frame_record fr{};
+          fr.bitrate_index = r.br_index; fr.padding = r.padding; fr.frame_size = r.slot + cfg.header_bytes; fr.main_data_size = r.slot;
+          fr.main_data_begin = r.mdb; fr.reservoir_bits = r.reservoir_bits; fr.huff_bytes = r.huff_bytes; fr.ms = r.ms; fr.is_final = r.is_final;
+          fr.frame_energy = r.frame_energy;
+          b->tr_frames[s].push_back(fr);
+          for (int j = 0; j < ngc; ++j) {
+            const GcSide &g = r.gc[j];
+            mp3b_gc_record q{};
+            q.part23_length = g.part23; q.big_values = g.big_values; q.global_gain = g.global_gain; q.gain_used = g.gain_used;
+            q.block_type = g.block_type; q.subblock_gain[0] = g.sbg[0]; q.subblock_gain[1] = g.sbg[1]; q.subblock_gain[2] = g.sbg[2];
+            q.region0 = g.region0; q.region1 = g.region1; q.preflag = g.preflag; q.g0 = g.g0; q.max_bits = g.max_bits;
+            q.iterations = g.iterations; q.energy = g.energy;
+            b->tr_gc[s].push_back(q);
+          }
+        }
+        const size_t cnt = (size_t)nf * ngc * 576, off = (size_t)s * b->GC * 576;
+        if (cnt) {
+          if (b->trace & 1) { size_t o = b->tr_spec[s].size(); b->tr_spec[s].resize(o + cnt); CU(cudaMemcpy(b->tr_spec[s].data() + o, pb.tr_spectrum + off, cnt * 4, cudaMemcpyDeviceToHost)); }
+          if (b->trace & 2) { size_t o = b->tr_ix[s].size(); b->tr_ix[s].resize(o + cnt); CU(cudaMemcpy(b->tr_ix[s].data() + o, pb.tr_ix + off, cnt * 4, cudaMemcpyDeviceToHost)); }
+          if (b->trace & 4) { size_t o = b->tr_thr[s].size(); b->tr_thr[s].resize(o + cnt); CU(cudaMemcpy(b->tr_thr[s].data() + o, pb.tr_thr + off, cnt * 4, cudaMemcpyDeviceToHost)); }
+        }
+      }
+    }
+    first = false;
+    bool more = false;
+    for (int s = 0; s < S && !more; ++s) more = cursor[s] < n[s] || (want_flush[s] && !flushed[s]);
+    if (!more) break;
+  }
+  // ---- results: counters, lengths, optional download
+  CU(cudaEventRecord(b->ev[0], st));
+  LAUNCH(launch_compact(cfg, b->pb, b->d_offsets, nullptr, 0, st));
+  CU(cudaMemcpyAsync(b->h_state, b->pb.state, (size_t)S * sizeof(StreamState), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(b->h_offsets, b->d_offsets, (size_t)(S + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  int err = 0;
+  for (int s = 0; s < S; ++s) {
+    const StreamState &hs = b->h_state[s];
+    b->out_len[s] = hs.out_pos; b->frame_count[s] = hs.frame_count; b->byte_count[s] = hs.total_bytes;
+    err |= hs.error;
+  }
+  b->out_total = 0;
+  for (int s = 0; s < S; ++s) b->out_total += b->out_len[s];
+  if (err) { b->sticky = MP3B_ERR_INTERNAL; return fail(MP3B_ERR_INTERNAL, "engine limit exceeded (flags 0x%x: 1 curve, 2 main-data buffer, 4 output buffer, 8 backlog > %d bytes)", err, kMdCarryCap); }
+  if (download) {
+    const size_t total = (size_t)b->h_offsets[S];
+    if (total > b->compact_cap) {
+      if (b->d_compact) cudaFree(b->d_compact);
+      b->d_compact = nullptr; b->compact_cap = 0;
+      size_t cap = round_up<size_t>(total + total / 8 + 4096, 4096);
+      CU(cudaMalloc((void **)&b->d_compact, cap));
+      b->compact_cap = cap;
+    }
+    if (total > b->h_out_cap) {
+      if (b->h_out) cudaFreeHost(b->h_out);
+      b->h_out = nullptr; b->h_out_cap = 0;
+      size_t cap = round_up<size_t>(total + total / 8 + 4096, 4096);
+      CU(cudaHostAlloc((void **)&b->h_out, cap, cudaHostAllocDefault));
+      b->h_out_cap = cap;
+    }
+    if (total) {
+      LAUNCH(launch_compact(cfg, b->pb, b->d_offsets, b->d_compact, 1, st));
+      CU(cudaMemcpyAsync(b->h_out, b->d_compact, total, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+    }
+    b->have_host_out = true;
+  }
+  CU(cudaEventRecord(b->ev[1], st));
+  CU(cudaEventSynchronize(b->ev[1]));
+  { float ms = 0; cudaEventElapsedTime(&ms, b->ev[0], b->ev[1]); b->stage_ms[MP3B_STAGE_D2H] += ms; b->stage_ms[MP3B_STAGE_TOTAL] += ms; }
+  return MP3B_OK;
+#undef LAUNCH
+}
+
+int copy_out(const uint8_t *src, size_t len, uint8_t *out, size_t cap, size_t *written) {
+  if (written) *written = len;
+  if (len > cap) return fail(MP3B_ERR_BUFFER_TOO_SMALL, "output needs %zu bytes, capacity is %zu", len, cap);
+  if (len && !out) return fail(MP3B_ERR_BAD_ARG, "null output buffer");
+  if (len) memcpy(out, src, len);
+  return MP3B_OK;
+}
+
+// generateXingHeader SRC:367-420 + generateTOC SRC:423-449
+int xing_header(const mp3b_batch *b, int stream, uint8_t *out, size_t cap, size_t *written) {
+  const Config &c = b->cfg;
+  const int frame_size = c.frame_base[c.cbr_index];
+  std::vector<uint8_t> v;
+  uint32_t h = 0;                                                 // SRC:379-392: no CRC, no padding, original = 1, copyright = 0
+  h = 0x7FFu; h = h << 2 | 3u; h = h << 2 | 1u; h = h << 1 | 1u; h = h << 4 | (uint32_t)c.cbr_index; h = h << 2 | (uint32_t)c.sr_index;
+  h = h << 1 | 0u; h = h << 1 | 0u; h = h << 2 | (uint32_t)c.mode_bits; h = h << 2 | (uint32_t)c.mode_ext; h = h << 1 | 0u; h = h << 1 | 1u; h = h << 2 | 0u;
+  for (int i = 3; i >= 0; --i) v.push_back((uint8_t)(h >> (8 * i)));
+  v.insert(v.end(), (size_t)c.side_bytes, 0);
+  const char *tag = c.vbr ? "Xing" : "Info";
+  v.insert(v.end(), tag, tag + 4);
+  uint32_t words[3] = {0x07u, b->frame_count[stream] + 1u, b->byte_count[stream] + (uint32_t)frame_size};
+  for (uint32_t w : words) for (int i = 3; i >= 0; --i) v.push_back((uint8_t)(w >> (8 * i)));
+  const std::vector<uint16_t> &fs = b->frame_sizes[stream];
+  long long total = 0;
+  for (uint16_t z : fs) total += z;
+  if (fs.empty() || total <= 0) { for (int p = 0; p < 100; ++p) v.push_back((uint8_t)(p * 255 / 99)); }
+  else {
+    std::vector<long long> cum(fs.size()); long long run = 0;
+    for (size_t i = 0; i < fs.size(); ++i) { run += fs[i]; cum[i] = run; }
+    for (int p = 0; p < 100; ++p) {
+      size_t target = (size_t)p * fs.size() / 100;
+      long long pos = target > 0 ? cum[target - 1] : 0, scaled = pos * 255 / total;
+      v.push_back((uint8_t)std::min<long long>(scaled, 255));
+    }
+  }
+  if ((int)v.size() < frame_size) v.resize((size_t)frame_size, 0);
+  return copy_out(v.data(), v.size(), out, cap, written);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mp3b_version(void) { return MP3B_VERSION; }
+const char *mp3b_last_error(void) { return g_err.c_str(); }
+
+void mp3b_options_default(mp3b_options *o) {                       // SRC:95-115
+  if (!o) return;
+  o->sample_rate = 44100; o->bitrate_kbps = 128; o->vbr = 0; o->mode = 1; o->quality = 5; o->crc_protected = 0; o->original = 1; o->copyright = 0;
+}
+
+int mp3b_device_count(int *count) {
+  if (!count) return fail(MP3B_ERR_BAD_ARG, "null count");
+  int n = 0; *count = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return fail(MP3B_ERR_CUDA, "cudaGetDeviceCount failed"); }
+  for (int i = 0; i < n; ++i) *count += usable_device(i);
+  return MP3B_OK;
+}
+
+int mp3b_batch_create(const mp3b_options *opts, int n_streams, int device, mp3b_batch **out) { return create_batch(opts, n_streams, device, 0, out); }
+int mp3b_batch_create_ex(const mp3b_options *opts, int n_streams, int device, int frames_per_pass, mp3b_batch **out) {
+  if (frames_per_pass < 0 || frames_per_pass > 16384) return fail(MP3B_ERR_BAD_ARG, "frames_per_pass out of range");
+  return create_batch(opts, n_streams, device, frames_per_pass, out);
+}
+void mp3b_batch_destroy(mp3b_batch *b) { free_batch(b); }
+int mp3b_batch_stream_count(const mp3b_batch *b) { return b ? b->S : 0; }
+int mp3b_batch_frames_per_pass(const mp3b_batch *b) { return b ? b->Fc : 0; }
+
+int mp3b_batch_encode(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, int flush, const uint8_t *flush_mask) {
+  return run_call(b, pcm, n_floats, false, flush, flush_mask, true);
+}
+int mp3b_batch_encode_device(mp3b_batch *b, const float *const *d_pcm, const size_t *n_floats, int flush, int download) {
+  return run_call(b, d_pcm, n_floats, true, flush, nullptr, download != 0);
+}
+int mp3b_batch_output(const mp3b_batch *b, int stream, const uint8_t **data, size_t *len) {
+  if (!b || stream < 0 || stream >= b->S || !data || !len) return fail(MP3B_ERR_BAD_ARG, "bad stream index or null pointer");
+  if (!b->have_host_out) return fail(MP3B_ERR_BAD_ARG, "the last call did not download its output");
+  *data = b->h_out ? b->h_out + b->h_offsets[stream] : nullptr; *len = b->out_len[stream];
+  return MP3B_OK;
+}
+int mp3b_batch_output_device(const mp3b_batch *b, int stream, const uint8_t **d_data, size_t *len) {
+  if (!b || stream < 0 || stream >= b->S || !d_data || !len) return fail(MP3B_ERR_BAD_ARG, "bad stream index or null pointer");
+  *d_data = b->pb.out + (size_t)stream * b->pb.out_stride; *len = b->out_len[stream];
+  return MP3B_OK;
+}
+size_t mp3b_batch_output_total(const mp3b_batch *b) { return b ? b->out_total : 0; }
+int mp3b_batch_xing_header(const mp3b_batch *b, int stream, uint8_t *out, size_t cap, size_t *written) {
+  if (!b || stream < 0 || stream >= b->S) return fail(MP3B_ERR_BAD_ARG, "bad stream index");
+  return xing_header(b, stream, out, cap, written);
+}
+uint32_t mp3b_batch_frame_count(const mp3b_batch *b, int stream) { return (b && stream >= 0 && stream < b->S) ? b->frame_count[stream] : 0; }
+uint32_t mp3b_batch_byte_count(const mp3b_batch *b, int stream) { return (b && stream >= 0 && stream < b->S) ? b->byte_count[stream] : 0; }
+
+// ---- session plane: a batch of one ------------------------------------------------------------------------
+int mp3b_session_create(const mp3b_options *opts, int device, mp3b_session **out) {
+  if (!out) return fail(MP3B_ERR_BAD_ARG, "null out");
+  mp3b_batch *b = nullptr;
+  int rc = create_batch(opts, 1, device, 256, &b);
+  if (rc) return rc;
+  mp3b_session *s = new mp3b_session(); s->b = b; *out = s;
+  return MP3B_OK;
+}
+void mp3b_session_destroy(mp3b_session *s) { if (!s) return; free_batch(s->b); delete s; }
+
+static int session_call(mp3b_session *s, const float *pcm, size_t n_floats, int flush, uint8_t *out, size_t cap, size_t *written) {
+  if (!s) return fail(MP3B_ERR_BAD_ARG, "null session");
+  if (!s->pending_out.empty()) return fail(MP3B_ERR_BAD_ARG, "output of the previous call is still pending: call mp3b_session_take_output");
+  const float *ptrs[1] = {pcm}; size_t ns[1] = {pcm ? n_floats : 0};
+  int rc = run_call(s->b, ptrs, ns, false, flush, nullptr, true);
+  if (rc) return rc;
+  const uint8_t *data; size_t len;
+  rc = mp3b_batch_output(s->b, 0, &data, &len);
+  if (rc) return rc;
+  rc = copy_out(data, len, out, cap, written);
+  if (rc == MP3B_ERR_BUFFER_TOO_SMALL) s->pending_out.assign(data, data + len);
+  return rc;
+}
+int mp3b_session_encode(mp3b_session *s, const float *pcm, size_t n_floats, uint8_t *out, size_t cap, size_t *written) {
+  return session_call(s, pcm, n_floats, 0, out, cap, written);
+}
+int mp3b_session_flush(mp3b_session *s, uint8_t *out, size_t cap, size_t *written) { return session_call(s, nullptr, 0, 1, out, cap, written); }
+int mp3b_session_take_output(mp3b_session *s, uint8_t *out, size_t cap, size_t *written) {
+  if (!s) return fail(MP3B_ERR_BAD_ARG, "null session");
+  int rc = copy_out(s->pending_out.data(), s->pending_out.size(), out, cap, written);
+  if (rc == MP3B_OK) s->pending_out.clear();
+  return rc;
+}
+size_t mp3b_session_output_bound(const mp3b_session *s, size_t n_floats) {
+  if (!s) return 0;
+  const mp3b_batch *b = s->b;
+  return ((b->pending[0] + n_floats) / b->cfg.fsc + 2) * (size_t)b->max_frame_bytes;
+}
+int mp3b_session_xing_header(const mp3b_session *s, uint8_t *out, size_t cap, size_t *written) {
+  if (!s) return fail(MP3B_ERR_BAD_ARG, "null session");
+  return xing_header(s->b, 0, out, cap, written);
+}
+uint32_t mp3b_session_frame_count(const mp3b_session *s) { return s ? s->b->frame_count[0] : 0; }
+uint32_t mp3b_session_byte_count(const mp3b_session *s) { return s ? s->b->byte_count[0] : 0; }
+
+// ID3TagWriter.build SRC:1040-1075 (host only, no device involved)
+int mp3b_id3_build(const mp3b_id3 *tag, uint8_t *out, size_t cap, size_t *written) {
+  if (!tag) return fail(MP3B_ERR_BAD_ARG, "null tag");
+  std::vector<uint8_t> f;
+  auto frame_header = [&](const char *id, uint32_t size) {        // SRC:1127-1135
+    f.insert(f.end(), id, id + 4);
+    for (int i = 3; i >= 0; --i) f.push_back((uint8_t)(size >> (8 * i)));
+    f.push_back(0); f.push_back(0);
+  };
+  auto text = [&](const char *id, const std::string &v) {         // SRC:1078-1086
+    frame_header(id, (uint32_t)(1 + v.size())); f.push_back(0x03); f.insert(f.end(), v.begin(), v.end());
+  };
+  if (tag->title) text("TIT2", tag->title);
+  if (tag->artist) text("TPE1", tag->artist);
+  if (tag->album) text("TALB", tag->album);
+  if (tag->genre) text("TCON", tag->genre);
+  if (tag->year >= 0) text("TYER", std::to_string(tag->year));
+  if (tag->track >= 0) text("TRCK", tag->track_total >= 0 ? std::to_string(tag->track) + "/" + std::to_string(tag->track_total) : std::to_string(tag->track));
+  if (tag->comment) {                                              // SRC:1089-1099
+    std::string c = tag->comment;
+    frame_header("COMM", (uint32_t)(1 + 3 + 1 + c.size()));
+    f.push_back(0x03); f.push_back('e'); f.push_back('n'); f.push_back('g'); f.push_back(0); f.insert(f.end(), c.begin(), c.end());
+  }
+  if (tag->album_art) {                                            // SRC:1102-1114
+    std::string mime = tag->album_art_mime ? tag->album_art_mime : "image/jpeg";
+    frame_header("APIC", (uint32_t)(1 + mime.size() + 1 + 1 + 1 + tag->album_art_len));
+    f.push_back(0x03); f.insert(f.end(), mime.begin(), mime.end()); f.push_back(0); f.push_back(0x03); f.push_back(0);
+    f.insert(f.end(), tag->album_art, tag->album_art + tag->album_art_len);
+  }
+  if (f.empty()) { if (written) *written = 0; return MP3B_OK; }   // SRC:1066
+  std::vector<uint8_t> o = {0x49, 0x44, 0x33, 0x03, 0x00, 0x00};
+  uint32_t sz = (uint32_t)f.size();
+  o.push_back((sz >> 21) & 0x7F); o.push_back((sz >> 14) & 0x7F); o.push_back((sz >> 7) & 0x7F); o.push_back(sz & 0x7F);
+  o.insert(o.end(), f.begin(), f.end());
+  return copy_out(o.data(), o.size(), out, cap, written);
+}
+
+// ---- memory helpers ---------------------------------------------------------------------------------------
+int mp3b_host_alloc(size_t bytes, void **out) {
+  if (!out) return fail(MP3B_ERR_BAD_ARG, "null out");
+  CU(cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocDefault));
+  return MP3B_OK;
+}
+void mp3b_host_free(void *p) { if (p) cudaFreeHost(p); }
+int mp3b_device_alloc(int device, size_t bytes, void **out) {
+  if (!out) return fail(MP3B_ERR_BAD_ARG, "null out");
+  CU(cudaSetDevice(device));
+  CU(cudaMalloc(out, std::max<size_t>(bytes, 1)));
+  return MP3B_OK;
+}
+void mp3b_device_free(int device, void *p) { if (p) { cudaSetDevice(device); cudaFree(p); } }
+int mp3b_device_copy(int device, void *dst, const void *src, size_t bytes, int kind) {
+  CU(cudaSetDevice(device));
+  CU(cudaMemcpy(dst, src, bytes, kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice));
+  return MP3B_OK;
+}
+int mp3b_device_sync(int device) { CU(cudaSetDevice(device)); CU(cudaDeviceSynchronize()); return MP3B_OK; }
+
+// ---- measurement / test plane -------------------------------------------------------------------------------
+int mp3b_batch_stage_ms(const mp3b_batch *b, float *ms, int n) {
+  if (!b || !ms) return fail(MP3B_ERR_BAD_ARG, "null pointer");
+  for (int i = 0; i < n && i < MP3B_STAGE_COUNT; ++i) ms[i] = b->stage_ms[i];
+  return MP3B_STAGE_COUNT;
+}
+int mp3b_batch_launch_count(const mp3b_batch *b) { return b ? b->launches : 0; }
+int mp3b_batch_set_trace(mp3b_batch *b, int flags) { if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch"); b->trace = flags ? (flags | 8) : 0; return MP3B_OK; }
+int mp3b_batch_trace_frames(const mp3b_batch *b, int stream) {
+  if (!b || stream < 0 || stream >= b->S || (size_t)stream >= b->tr_frames.size()) return 0;
+  return (int)b->tr_frames[stream].size();
+}
+int mp3b_batch_trace_frame_records(const mp3b_batch *b, int stream, mp3b_frame_record *out, int cap) {
+  int n = mp3b_batch_trace_frames(b, stream);
+  if (n > cap) return fail(MP3B_ERR_BUFFER_TOO_SMALL, "need %d records", n);
+  if (n) memcpy(out, b->tr_frames[stream].data(), (size_t)n * sizeof *out);
+  return n;
+}
+int mp3b_batch_trace_gc_records(const mp3b_batch *b, int stream, mp3b_gc_record *out, int cap) {
+  if (!b || stream < 0 || (size_t)stream >= b->tr_gc.size()) return 0;
+  int n = (int)b->tr_gc[stream].size();
+  if (n > cap) return fail(MP3B_ERR_BUFFER_TOO_SMALL, "need %d records", n);
+  if (n) memcpy(out, b->tr_gc[stream].data(), (size_t)n * sizeof *out);
+  return n;
+}
+int mp3b_batch_trace_gc_array(const mp3b_batch *b, int stream, int kind, void *out, int cap_gc) {
+  if (!b || stream < 0 || (size_t)stream >= b->tr_gc.size() || !out) return fail(MP3B_ERR_BAD_ARG, "bad stream or null out");
+  const void *src; size_t elems;
+  if (kind == 0) { src = b->tr_spec[stream].data(); elems = b->tr_spec[stream].size(); }
+  else if (kind == 1) { src = b->tr_ix[stream].data(); elems = b->tr_ix[stream].size(); }
+  else if (kind == 2) { src = b->tr_thr[stream].data(); elems = b->tr_thr[stream].size(); }
+  else return fail(MP3B_ERR_BAD_ARG, "kind must be 0, 1 or 2");
+  if (elems > (size_t)cap_gc * 576) return fail(MP3B_ERR_BUFFER_TOO_SMALL, "need %zu granule-channels", elems / 576);
+  if (elems) memcpy(out, src, elems * 4);
+  return (int)(elems / 576);
+}
+
+int mp3b_table(int which, void *out, size_t cap_bytes) {
+  const void *src = nullptr; size_t n = 0, es = 4;
+  switch (which) {
+    case 0: src = tab::kWindow; n = 512; break;
+    case 1: src = tab::kAnalysis; n = 2048; break;
+    case 2: src = tab::kMdctLong; n = 648; break;
+    case 3: src = tab::kMdctShort; n = 72; break;
+    case 4: src = tab::kWinLong; n = 36; break;
+    case 5: src = tab::kWinShort; n = 12; break;
+    case 6: src = host_inv_step(); n = 256; break;
+    case 7: src = tab::kHuff15Len; n = 256; es = 1; break;
+    case 8: src = tab::kHuff15Code; n = 256; es = 1; break;
+    case 9: src = host_gain_thr(); n = 256; es = 8; break;
+    case 10: src = tab::kAliasCs; n = 8; break;
+    case 11: src = tab::kAliasCa; n = 8; break;
+    case 12: src = host_sfb_cum(); n = 63; break;
+    default: return fail(MP3B_ERR_BAD_ARG, "unknown table %d", which);
+  }
+  if (n * es > cap_bytes) return fail(MP3B_ERR_BUFFER_TOO_SMALL, "table %d needs %zu bytes", which, n * es);
+  if (out) memcpy(out, src, n * es);
+  return (int)n;
+}
+
+int mp3b_synth_fill(int device, float *d_pcm, size_t n_samples_per_channel, int channels, int sample_rate, float f_left,
+                    float f_right, float amp, float noise, uint64_t seed) {
+  if (!d_pcm || channels < 1 || channels > 2 || sample_rate <= 0) return fail(MP3B_ERR_BAD_ARG, "bad synth arguments");
+  CU(cudaSetDevice(device));
+  int k = launch_synth(d_pcm, n_samples_per_channel, channels, sample_rate, f_left, f_right, amp, noise, seed, nullptr);
+  if (k < 0) return fail(MP3B_ERR_CUDA, "synth launch failed: %s", cudaGetErrorString((cudaError_t)(-k)));
+  CU(cudaDeviceSynchronize());
+  return MP3B_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,846 @@
+// sm_100a kernels of the MP3 encode path.  SRC = Sources/SwiftMP3/MP3Encoder.swift of the reference.
+//
+// Numerical contract (bit-exact against oracle/mp3_oracle.c): every floating-point operation below is an explicit
+// IEEE-754 round-to-nearest intrinsic (__fmul_rn / __fadd_rn / __fmaf_rn / __fdiv_rn) in the order the oracle
+// defines ([OD1]..[OD5] in its header); the file is compiled with -fmad=false so nothing else is contracted.
+// All constant tables are literals (tables_gen.h) so that the fully unrolled loops carry them as instruction
+// immediates: the 32x64 analysis matrix, the 512-tap window and the MDCT matrices cost no memory traffic at all.
+#include "kernels.h"
+
+#include <cstdio>
+
+#include "tables_gen.h"
+
+namespace mp3b {
+
+__constant__ float c_inv_step[256];     // 1 / Float(max(2^((g-210)/4), 1e-4)), SRC:798-800
+__constant__ double c_gain_thr[256];    // 2^((g-210)/4) in double: replaces log2 in computeGlobalGain, SRC:1004
+__constant__ uint8_t c_len15[256];      // SRC:2457-2473
+__constant__ uint8_t c_code15[256];     // SRC:2476-2493
+__constant__ int c_sfb_cum[3][21];      // cumulative long sfb widths, SRC:1814-1820
+
+extern const float *host_inv_step();    // tables.cc
+extern const double *host_gain_thr();
+extern const int *host_sfb_cum();
+extern const uint8_t *host_len15();
+extern const uint8_t *host_code15();
+
+cudaError_t upload_tables() {
+  cudaError_t e;
+  if ((e = cudaMemcpyToSymbol(c_inv_step, host_inv_step(), sizeof(float) * 256))) return e;
+  if ((e = cudaMemcpyToSymbol(c_gain_thr, host_gain_thr(), sizeof(double) * 256))) return e;
+  if ((e = cudaMemcpyToSymbol(c_len15, host_len15(), 256))) return e;
+  if ((e = cudaMemcpyToSymbol(c_code15, host_code15(), 256))) return e;
+  if ((e = cudaMemcpyToSymbol(c_sfb_cum, host_sfb_cum(), sizeof(int) * 63))) return e;
+  return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// helpers
+
+// Logical PCM sequence of a stream in one pass: head[0, head_n) ++ cur[0, cur_n) ++ zeros (flush padding, SRC:322-328).
+struct PcmView {
+  const float *head, *cur;
+  uint32_t head_n, cur_n;
+  __device__ __forceinline__ float at(int64_t q) const {
+    if (q < (int64_t)head_n) return head[q];
+    q -= head_n;
+    return q < (int64_t)cur_n ? __ldg(cur + q) : 0.0f;
+  }
+};
+__device__ __forceinline__ PcmView pcm_view(const Config &cfg, const PassBuffers &pb, int s) {
+  const StreamPlan &p = pb.plan[s];
+  PcmView v;
+  v.head = pb.head_in + (size_t)s * 2 * cfg.fsc;
+  v.cur = p.cur; v.head_n = p.head_n; v.cur_n = p.cur_n;
+  return v;
+}
+
+// [OD1b] butterfly tree over the 32 lane partials; every lane ends with the same bits (a + b == b + a).
+__device__ __forceinline__ float lane_tree(float p) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, m));
+  return p;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+
+// [OD3] |x|^0.75 = (float)(sqrt(d) * sqrt(sqrt(d))) in IEEE double.
+__device__ __forceinline__ float pow34(float a) {
+  double d = (double)a;
+  double r = __dsqrt_rn(d);
+  return __double2float_rn(__dmul_rn(r, __dsqrt_rn(r)));
+}
+
+// quantizeWithGain SRC:816-821: min(Int32(roundf(mag * inv)), 15); roundf = ties away from zero [OD4].
+__device__ __forceinline__ int quant15(float mag, float inv) {
+  float t = fminf(__fmul_rn(mag, inv), 16.0f);
+  float r = truncf(t);
+  int q = (int)r + (__fsub_rn(t, r) >= 0.5f ? 1 : 0);
+  return q > 15 ? 15 : q;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K0: pre-pass.  One warp per frame: frame energy (SRC:477), stereo decision (SRC:2140-2162), granule energies
+// (SRC:673), transient thirds -> block type + subblock_gain (SRC:1944-1968).
+
+__device__ __forceinline__ void transient_decide(const float e3[3], int &bt, int sbg[3]) {
+  float mx = fmaxf(e3[0], fmaxf(e3[1], e3[2])), mn = fminf(e3[0], fminf(e3[1], e3[2]));
+  float ratio = __fdiv_rn(mx, fmaxf(mn, 0.0001f));
+  if (ratio > 6.0f) bt = (e3[0] == mx) ? 1 : 2; else bt = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float normalized = fminf(fmaxf(__fdiv_rn(e3[i], fmaxf(mx, 0.0001f)), 0.0f), 1.0f);
+    sbg[i] = (int)__fmul_rn(__fsub_rn(1.0f, normalized), 7.0f);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_prepass(Config cfg, PassBuffers pb) {
+  const int s = blockIdx.x, lane = threadIdx.x & 31;
+  const int f = blockIdx.y * 4 + (threadIdx.x >> 5);
+  const StreamPlan &plan = pb.plan[s];
+  if (f >= (int)plan.n_frames) return;
+  const int ch = cfg.channels;
+  const PcmView pv = pcm_view(cfg, pb, s);
+  const int64_t q0 = (int64_t)(1 + f) * cfg.fsc;
+  StreamState &stt = pb.state[s];
+
+  if (f == 0 && lane < 10) {  // carried VBR history, right aligned in front of this pass's gc energies
+    int n = stt.vbr_n;
+    pb.gc_energy[(size_t)s * (10 + pb.GC) + lane] = lane >= 10 - n ? stt.vbr_hist[lane - (10 - n)] : 0.0f;
+  }
+
+  // frame energy over the interleaved frame, lane = float index mod 32 [OD1b]
+  float pf = 0.0f;
+  for (int i = lane; i < cfg.fsc; i += 32) { float x = pv.at(q0 + i); pf = __fmaf_rn(x, x, pf); }
+  float frame_energy = __fdiv_rn(lane_tree(pf), (float)cfg.fsc);
+
+  // per-channel signals; variant 0/1 = L/R (or mono), 2/3 = mid/side
+  const bool joint = cfg.mode == 2;
+  float eg[4][2], e3[4][2][3];
+  float pm = 0.0f, ps = 0.0f;
+#pragma unroll
+  for (int gr = 0; gr < 2; ++gr) {
+    float ag[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int th = 0; th < 3; ++th) {
+      float a3[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int jj = 0; jj < 6; ++jj) {
+        int n = gr * 576 + th * 192 + jj * 32 + lane;
+        float v[4];
+        if (ch == 1) { v[0] = pv.at(q0 + n); v[1] = v[2] = v[3] = 0.0f; }
+        else {
+          v[0] = pv.at(q0 + 2 * n); v[1] = pv.at(q0 + 2 * n + 1);
+          v[2] = __fmul_rn(__fadd_rn(v[0], v[1]), 0.5f);       // SRC:2148-2150
+          v[3] = __fmul_rn(__fsub_rn(v[0], v[1]), 0.5f);       // SRC:2153-2154
+          pm = __fmaf_rn(v[2], v[2], pm); ps = __fmaf_rn(v[3], v[3], ps);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a3[k] = __fmaf_rn(v[k], v[k], a3[k]); ag[k] = __fmaf_rn(v[k], v[k], ag[k]); }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) e3[k][gr][th] = __fdiv_rn(lane_tree(a3[k]), 192.0f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) eg[k][gr] = __fdiv_rn(lane_tree(ag[k]), 576.0f);
+  }
+  int ms = 0;
+  if (joint) {
+    float me = __fdiv_rn(lane_tree(pm), 1152.0f), se = __fdiv_rn(lane_tree(ps), 1152.0f);
+    ms = se < __fmul_rn(me, 0.4f) ? 1 : 0;                      // SRC:2156-2158
+  }
+  if (lane == 0) {
+    pb.frame_energy[(size_t)s * pb.Fc + f] = frame_energy;
+    pb.ms[(size_t)s * (pb.Fc + 1) + 1 + f] = (uint8_t)ms;
+    if (!cfg.vbr) pb.frame_br[(size_t)s * pb.Fc + f] = (uint8_t)cfg.cbr_index;
+  }
+  if (lane < 2 * ch) {
+    int gr = lane / ch, c = lane % ch, k = c + (ms ? 2 : 0);
+    float e[3]; float g = 0.0f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int g2 = 0; g2 < 2; ++g2)
+        if (kk == k && g2 == gr) { e[0] = e3[kk][g2][0]; e[1] = e3[kk][g2][1]; e[2] = e3[kk][g2][2]; g = eg[kk][g2]; }
+    int bt, sbg[3];
+    transient_decide(e, bt, sbg);
+    int gci = (2 * f + gr) * ch + c;
+    pb.gc_energy[(size_t)s * (10 + pb.GC) + 10 + gci] = g;
+    pb.gc_bt[(size_t)s * pb.GC + gci] = (uint16_t)(bt | sbg[0] << 2 | sbg[1] << 5 | sbg[2] << 8);
+  }
+}
+
+// VBRState.chooseBitrate SRC:1177-1189 + MP3Tables.bitrateIndex SRC:2509-2523: one thread per frame.
+__global__ void k_bitrate(Config cfg, PassBuffers pb) {
+  const int s = blockIdx.x, f = blockIdx.y * blockDim.x + threadIdx.x;
+  if (f >= (int)pb.plan[s].n_frames) return;
+  const float *hist = pb.gc_energy + (size_t)s * (10 + pb.GC);
+  const int before = f * 2 * cfg.channels;             // gc energies of this pass appended before frame f
+  int count = pb.state[s].vbr_n + before; if (count > 10) count = 10;
+  const float e = pb.frame_energy[(size_t)s * pb.Fc + f];
+  float average;
+  if (count == 0) average = e;
+  else {
+    float sum = 0.0f;
+    for (int i = 10 + before - count; i < 10 + before; ++i) sum = __fadd_rn(sum, hist[i]);
+    average = __fdiv_rn(sum, (float)count);
+  }
+  float ratio = fminf(fmaxf(__fdiv_rn(e, fmaxf(average, 0.0001f)), 0.5f), 2.0f);
+  float quality_factor = __fdiv_rn((float)(9 - cfg.quality), 9.0f);
+  int max_adjustment = (int)__fadd_rn(32.0f, __fmul_rn(32.0f, quality_factor));
+  int adjustment = (int)__fmul_rn(__fsub_rn(ratio, 1.0f), (float)max_adjustment);
+  int lo = max(32, cfg.base_kbps - 64 + cfg.quality * 8), hi = min(320, cfg.base_kbps + 64 - cfg.quality * 4);
+  int kbps = max(lo, min(cfg.base_kbps + adjustment, hi));
+  kbps = min(max(kbps, 0), 320);
+  pb.frame_br[(size_t)s * pb.Fc + f] = cfg.vbr_idx_of_kbps[kbps];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1+K2: polyphase filterbank (SRC:1367-1411) + MDCT / alias reduction (SRC:1512-1662) + |x|^0.75, peak -> g0
+// (SRC:989-1006), preflag (SRC:2042-2066).
+//
+// One CTA = one run of up to 15 consecutive granules of one (stream, channel); the granule in front of the run is
+// recomputed for the MDCT overlap, so 288 filterbank steps = 288 threads.  Phase A: thread = time step; its 32
+// subband accumulators live in registers and every window / matrix coefficient is an instruction immediate; the
+// only memory operands are the 512 PCM samples of the step, read from a 33-float-padded shared tile (conflict
+// free).  Phase B: warp = granule, lane = subband: 18x36 / 6x12 MDCT with immediate coefficients, butterflies through
+// shared memory.  Phase C: same warp, coalesced over the 576 lines.
+constexpr int kSteps = 18 * (kRunGranules + 1);   // 288
+constexpr int kLook = 15;                         // 480 samples of look-back = 15 rows of 32
+constexpr int kRows = kSteps + kLook;             // 303
+constexpr int kRowPad = 33;
+constexpr int kSpecSmemFloats = kRows * kRowPad + kSteps * kRowPad;
+constexpr int kSpecSmemBytes = kSpecSmemFloats * 4;
+
+__device__ __forceinline__ int gain_from_peak(float peak) {      // computeGlobalGain SRC:989-1006
+  if (!(peak > 0.0f)) return 210;
+  float ratio = __fdiv_rn(pow34(peak), 15.0f);
+  if (ratio <= 0.0f) return 210;
+  double r = (double)ratio;
+  // 210 + Int(4*log2(r)): Int() truncates toward zero.  i = largest index with 2^((i-210)/4) <= r.
+  if (r < c_gain_thr[0]) return 0;
+  int lo = 0, hi = 255;
+  while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (c_gain_thr[mid] <= r) lo = mid; else hi = mid - 1; }
+  int gain = lo;                                                   // floor
+  if (r < 1.0 && c_gain_thr[lo] != r) gain = lo + 1;               // negative values truncate upwards
+  return gain > 255 ? 255 : gain;
+}
+
+__global__ void __launch_bounds__(kSteps, 2) k_spectrum(Config cfg, PassBuffers pb) {
+  extern __shared__ float sm[];
+  float *P = sm;                           // [kRows][33] PCM tile, later X[15][576]
+  float *Sb = sm + kRows * kRowPad;        // [kSteps][33] subband samples [step][sb]
+  const int s = blockIdx.x, c = blockIdx.y, run = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const StreamPlan &plan = pb.plan[s];
+  const int ngr = 2 * (int)plan.n_frames;
+  const int g_begin = run * kRunGranules;
+  if (g_begin >= ngr) return;
+  const int g_cnt = min(kRunGranules, ngr - g_begin);
+  const int ch = cfg.channels;
+  const PcmView pv = pcm_view(cfg, pb, s);
+  const uint8_t *msrow = pb.ms + (size_t)s * (pb.Fc + 1);
+  const uint32_t ms_prev = pb.state[s].ms_prev;
+
+  // ---- stage PCM: sample n (per channel, relative to frame 0 of the pass) = n0 + 32*row + col
+  const int n0 = 576 * (g_begin - 1) - 480;
+  const int rows_needed = kLook + 18 * (g_cnt + 1);
+  for (int e = tid; e < rows_needed * 32; e += kSteps) {
+    int n = n0 + e;
+    int64_t q = (int64_t)(n + 1152) * ch;
+    float v;
+    if (ch == 1) v = pv.at(q);
+    else {
+      int fr = n >= 0 ? n / 1152 : -1;
+      bool ms = cfg.mode == 2 && (fr < 0 ? ms_prev != 0 : msrow[1 + fr] != 0);
+      if (!ms) v = pv.at(q + c);
+      else {
+        float l = pv.at(q), r = pv.at(q + 1);
+        v = c == 0 ? __fmul_rn(__fadd_rn(l, r), 0.5f) : __fmul_rn(__fsub_rn(l, r), 0.5f);
+      }
+    }
+    P[(e >> 5) * kRowPad + (e & 31)] = v;
+  }
+  __syncthreads();
+
+  // ---- phase A: filterbank step `tid`
+  if (tid < 18 * (g_cnt + 1)) {
+    float acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.0f;
+    const float *row = P + (tid + kLook) * kRowPad;
+#pragma unroll
+    for (int n = 0; n < 64; ++n) {
+      const int col = (31 - n) & 31, rsh = n >= 32 ? 1 : 0;
+      float y = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float z = __fmul_rn(row[-(2 * i + rsh) * kRowPad + col], tab::kWindow[n + 64 * i]);   // SRC:1386-1389
+        y = i == 0 ? z : __fadd_rn(y, z);                                                      // SRC:1392-1399
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc[k] = __fmaf_rn(y, tab::kAnalysis[k][n], acc[k]);       // SRC:1402-1408
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) Sb[tid * kRowPad + k] = acc[k];
+  }
+  __syncthreads();
+
+  // ---- phase B + C: warp per granule
+  for (int gl = warp; gl < g_cnt; gl += kSteps / 32) {
+    const int gp = g_begin + gl;                    // granule index inside the pass
+    const int gci = gp * ch + c;
+    const size_t gslot = (size_t)s * pb.GC + gci;
+    const int bt = pb.gc_bt[gslot] & 3;
+    float *X = P + gl * 576;
+    {
+      const int sb = lane;
+      const bool flip = sb & 1;
+      const float *prev = Sb + (18 * gl) * kRowPad + sb, *cur = prev + 18 * kRowPad;
+      const bool use_long = bt == 0 || (bt == 1 && sb < 2);      // SRC:1542-1553
+      if (use_long) {                                             // mdctLong SRC:1619-1636
+        float a[18];
+#pragma unroll
+        for (int m = 0; m < 18; ++m) a[m] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 36; ++k) {
+          float v = k < 18 ? prev[k * kRowPad] : cur[(k - 18) * kRowPad];
+          if (flip && (k & 1)) v = -v;                            // SRC:1520-1524
+          float w = __fmul_rn(v, tab::kWinLong[k]);
+#pragma unroll
+          for (int m = 0; m < 18; ++m) a[m] = __fmaf_rn(w, tab::kMdctLong[m][k], a[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < 18; ++m) X[sb * 18 + m] = __fdiv_rn(a[m], 9.0f);
+      }
+      if (!use_long) {                                            // mdctShort SRC:1639-1662
+#pragma unroll
+        for (int w3 = 0; w3 < 3; ++w3) {
+          float seg[12];
+#pragma unroll
+          for (int i = 0; i < 12; ++i) {
+            int k = w3 * 6 + 6 + i;
+            float v = k < 18 ? prev[k * kRowPad] : cur[(k - 18) * kRowPad];
+            if (flip && (k & 1)) v = -v;
+            seg[i] = __fmul_rn(v, tab::kWinShort[i]);
+          }
+#pragma unroll
+          for (int m = 0; m < 6; ++m) {
+            float r = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) r = __fmaf_rn(seg[k], tab::kMdctShort[m][k], r);
+            X[sb * 18 + w3 + 3 * m] = __fdiv_rn(r, 3.0f);
+          }
+        }
+      }
+      __syncwarp();
+      if (bt == 0 && sb < 31) {                                   // applyAliasingReduction SRC:1581-1616 [OD5]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int iu = sb * 18 + 17 - i, il = (sb + 1) * 18 + i;
+          float upper = X[iu], lower = X[il];
+          X[iu] = __fadd_rn(__fmul_rn(lower, tab::kAliasCa[i]), __fmul_rn(upper, tab::kAliasCs[i]));
+          X[il] = __fsub_rn(__fmul_rn(lower, tab::kAliasCs[i]), __fmul_rn(upper, tab::kAliasCa[i]));
+        }
+      }
+      __syncwarp();
+    }
+    // phase C: line i = lane + 32 j
+    float peak = 0.0f, plo = 0.0f, phi = 0.0f;
+    float *smag = pb.smag + gslot * 576;
+    float *trs = pb.tr_spectrum ? pb.tr_spectrum + gslot * 576 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 18; ++j) {
+      int i = lane + 32 * j;
+      float x = X[i];
+      float ax = fabsf(x);
+      peak = fmaxf(peak, ax);
+      // PreEmphasis SRC:2050-2056 [OD1b]: partial index = (i - segment start) mod 32; 432 mod 32 = 16 is an xor
+      // permutation of the lanes, which the butterfly tree is invariant under.
+      if (i < 432) plo = __fmaf_rn(x, x, plo); else phi = __fmaf_rn(x, x, phi);
+      float mag = pow34(fmaxf(ax, 1e-10f));                       // SRC:805-813 [OD3]
+      smag[i] = x < 0.0f ? -mag : mag;
+      if (trs) trs[i] = x;
+    }
+    peak = warp_max(peak);
+    float low = lane_tree(plo), high = lane_tree(phi);
+    if (lane == 0) {
+      int g0 = gain_from_peak(peak);
+      int pre = high > __fmul_rn(low, 1.5f) ? 1 : 0;
+      pb.gc_meta[gslot] = (uint32_t)g0 | (uint32_t)pre << 17;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K4: bits-vs-gain curve of quantizeToFitBudget (SRC:734-794).  One warp per gc.  The loop's gain sequence does not
+// depend on maxBits (only where it stops does), so the warp evaluates it until the bit count fits the smallest
+// budget the frame can have (no reservoir, no padding) or the loop's own exits fire; the serial scan (K_scan) then
+// only looks entries up.
+__device__ __forceinline__ int lo_bits_of(const Config &cfg, int bri) {
+  return ((cfg.frame_base[bri] - cfg.header_bytes) * 8) / (2 * cfg.channels);
+}
+
+__global__ void __launch_bounds__(256) k_curve(Config cfg, PassBuffers pb) {
+  __shared__ uint8_t len15[256];
+  len15[threadIdx.x] = c_len15[threadIdx.x];
+  __syncthreads();
+  const int s = blockIdx.x, lane = threadIdx.x & 31;
+  const int gci = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int ch = cfg.channels;
+  if (gci >= (int)pb.plan[s].n_frames * 2 * ch) return;
+  const size_t gslot = (size_t)s * pb.GC + gci;
+  const int f = gci / (2 * ch);
+  const int lo_bits = lo_bits_of(cfg, pb.frame_br[(size_t)s * pb.Fc + f]);
+  const float2 *sm2 = reinterpret_cast<const float2 *>(pb.smag + gslot * 576);
+  float mx[9], my[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) { float2 v = sm2[lane + 32 * j]; mx[j] = fabsf(v.x); my[j] = fabsf(v.y); }
+  uint32_t meta = pb.gc_meta[gslot];
+  const int g0 = meta & 255;
+  int gain = g0, n = 0, restart = 0;
+  uint16_t *bits_out = pb.gc_bits + gslot * kMaxEntries, *bv_out = pb.gc_bv + gslot * kMaxEntries;
+  for (int it = 0; it < kMaxEntries; ++it) {
+    const float inv = c_inv_step[gain];
+    int total = 0, last = 0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      int qx = quant15(mx[j], inv), qy = quant15(my[j], inv);
+      total += len15[qx * 16 + qy] + (qx != 0) + (qy != 0);
+      if (qx | qy) last = lane + 32 * j + 1;
+    }
+    const int bv = warp_max_i(last);                 // pairs up to and including the last non-zero one, SRC:750-763
+    const int bits = warp_sum_i(total) - 3 * (288 - bv);   // all-zero pairs beyond big_values are not coded (len15[0][0] = 3)
+    if (lane == 0) { bits_out[it] = (uint16_t)bits; bv_out[it] = (uint16_t)bv; }
+    n = it + 1;
+    if (bv == 0 && it == 0) { restart = 1; gain = max(gain - 40, 0); continue; }   // SRC:758-761
+    if (bits <= lo_bits) break;                      // fits every possible budget of this frame
+    int next = min(gain + 4, 255);                   // SRC:772-775
+    if (next >= 255) break;
+    gain = next;
+  }
+  if (lane == 0) pb.gc_meta[gslot] = (meta & 0xFFFE00FFu) | (uint32_t)n << 8 | (uint32_t)restart << 16;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K_scan: the serial part of a stream (SRC:475-568): padding, reservoir, per-gc gain choice, main_data_begin,
+// slot filling bookkeeping.  One thread per stream.
+__device__ __forceinline__ void region_counts(const Config &cfg, int big_values, int &r0, int &r1) {  // SRC:856-887
+  const int region = big_values * 2;
+  const int *b = c_sfb_cum[cfg.sfb_index];
+  int region0 = 0;
+  for (int i = 0; i < 15; ++i) { if (b[i] <= region) region0 = i; else break; }
+  int region1 = 0, start = region0 + 1, lim = min(start + 7, 21);
+  for (int i = start; i < lim; ++i) { if (b[i] <= region) region1 = i - region0 - 1; else break; }
+  r0 = min(region0, 15); r1 = min(region1, 7);
+}
+
+__global__ void k_scan(Config cfg, PassBuffers pb) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cfg.n_streams) return;
+  const StreamPlan plan = pb.plan[s];
+  StreamState &st = pb.state[s];
+  const int ch = cfg.channels, nf = (int)plan.n_frames, ngc = 2 * ch;
+  if (plan.flags & 4) st.out_pos = 0;
+  FrameRec *rec = pb.rec + (size_t)s * (pb.Fc + 1);
+  uint16_t *emit_size = pb.emit_size + (size_t)s * (pb.Fc + 1);
+  uint32_t n_emit = 0;
+  const uint32_t B0 = (uint32_t)st.backlog;
+  uint32_t R = 0, W = B0;
+  rec[0] = st.buffered;
+  rec[0].emit = 0;
+  int prev = rec[0].valid ? 0 : -1;
+  for (int f = 0; f < nf; ++f) {
+    const bool is_final = (plan.flags & 1) && f == nf - 1;
+    const int bri = pb.frame_br[(size_t)s * pb.Fc + f];
+    int padding = 0;                                             // shouldPad SRC:456-463
+    st.pad_rem += cfg.frame_rem[bri];
+    if (st.pad_rem >= cfg.sample_rate) { st.pad_rem -= cfg.sample_rate; padding = 1; }
+    const int frame_size = cfg.frame_base[bri] + padding;
+    const int mds = frame_size - cfg.header_bytes;               // SRC:497
+    const int mdb = is_final ? 0 : (int)min(W - R, 511u);        // SRC:499, 2099-2101
+    const int res_bits = is_final ? 0 : st.avail_bytes * 8;      // SRC:500
+    const int bpg = (mds * 8 + (res_bits * 9) / 10) / (2 * ch);  // SRC:647-650
+    FrameRec fr;
+    fr.valid = 1; fr.br_index = (uint8_t)bri; fr.padding = (uint8_t)padding;
+    fr.ms = pb.ms[(size_t)s * (pb.Fc + 1) + 1 + f];
+    fr.mdb = (uint16_t)mdb; fr.slot = (uint16_t)mds; fr.is_final = is_final; fr.emit = 0; fr.pad0[0] = fr.pad0[1] = 0;
+    fr.reservoir_bits = res_bits; fr.frame_energy = pb.frame_energy[(size_t)s * pb.Fc + f];
+    fr.src_off = fr.take = fr.out_off = 0;
+    int total = 0;
+    for (int j = 0; j < ngc; ++j) {
+      const int gci = f * ngc + j;
+      const size_t gslot = (size_t)s * pb.GC + gci;
+      const uint32_t meta = pb.gc_meta[gslot];
+      const int g0 = meta & 255, n = (meta >> 8) & 255, restart = (meta >> 16) & 1, pre = (meta >> 17) & 1;
+      const uint16_t *cb = pb.gc_bits + gslot * kMaxEntries, *cv = pb.gc_bv + gslot * kMaxEntries;
+      int gain = g0, chosen = n - 1, gain_out = g0, gain_used = g0, iters = n;
+      for (int e = 0; e < n; ++e) {                               // quantizeToFitBudget SRC:745-776
+        gain_used = gain;
+        if (e == 0 && restart) { gain = max(gain - 40, 0); continue; }
+        if ((int)cb[e] <= bpg) { chosen = e; gain_out = gain; iters = e + 1; break; }
+        int next = min(gain + 4, 255);
+        if (next >= 255 || e == kMaxEntries - 1) { chosen = e; gain_out = next; iters = e + 1; break; }
+        if (e == n - 1) { chosen = e; gain_out = next; st.error |= 1; break; }   // curve ended early: engine bug
+        gain = next;
+      }
+      if (n == 1 && restart) { chosen = 0; gain_out = gain; gain_used = g0; }    // unreachable: restart implies n >= 2
+      const int bits = cb[chosen], bv = min((int)cv[chosen], 288);
+      GcSide &g = fr.gc[j];
+      g.part23 = (uint16_t)bits; g.big_values = (uint16_t)bv; g.global_gain = (uint8_t)gain_out; g.gain_used = (uint8_t)gain_used;
+      const uint16_t btw = pb.gc_bt[gslot];
+      g.block_type = btw & 3; g.sbg[0] = (btw >> 2) & 7; g.sbg[1] = (btw >> 5) & 7; g.sbg[2] = (btw >> 8) & 7;
+      int r0, r1; region_counts(cfg, bv, r0, r1);
+      g.region0 = (uint8_t)r0; g.region1 = (uint8_t)r1; g.preflag = (uint8_t)pre; g.g0 = (uint8_t)g0;
+      g.iterations = (uint8_t)iters; g.pad = 0; g.max_bits = (uint16_t)bpg;
+      g.energy = pb.gc_energy[(size_t)s * (10 + pb.GC) + 10 + gci];
+      pb.gc_sel[gslot] = (uint32_t)gain_used | (uint32_t)bv << 8;
+      pb.gc_bitoff[gslot] = (uint32_t)total;
+      total += bits;
+    }
+    for (int j = ngc; j < 4; ++j) fr.gc[j] = GcSide{};
+    const int huff = (total + 7) >> 3;                            // padToByte SRC:729
+    fr.huff_bytes = huff;
+    pb.fr_md[((size_t)s * pb.Fc + f) * 2] = W;
+    pb.fr_md[((size_t)s * pb.Fc + f) * 2 + 1] = (uint32_t)huff;
+    W += (uint32_t)huff;                                          // appendHuffmanData SRC:511
+    if (W > pb.md_stride) { st.error |= 2; W = (uint32_t)pb.md_stride; }
+    rec[1 + f] = fr;
+    if (prev >= 0) {                                              // emit the buffered frame, SRC:548-556 + fillSlot 2110-2121
+      FrameRec &p = rec[prev];
+      uint32_t take = min((uint32_t)p.slot, W - R);
+      p.emit = 1; p.src_off = R; p.take = take; p.out_off = st.out_pos;
+      R += take;
+      uint32_t sz = (uint32_t)cfg.header_bytes + p.slot;
+      st.out_pos += sz; st.frame_count += 1; st.total_bytes += sz;
+      emit_size[n_emit++] = (uint16_t)sz;
+    }
+    prev = 1 + f;
+    int a = st.avail_bytes + mds - huff;                          // updateReservoir SRC:565, 2125-2128
+    st.avail_bytes = a < 0 ? 0 : a > 511 ? 511 : a;
+  }
+  if ((plan.flags & 2) && prev >= 0) {                            // flush SRC:335-347
+    FrameRec &p = rec[prev];
+    uint32_t take = min((uint32_t)p.slot, W - R);
+    p.emit = 1; p.src_off = R; p.take = take; p.out_off = st.out_pos;
+    R += take;
+    uint32_t sz = (uint32_t)cfg.header_bytes + p.slot;
+    st.out_pos += sz; st.frame_count += 1; st.total_bytes += sz;
+    emit_size[n_emit++] = (uint16_t)sz;
+    prev = -1;
+  }
+  if (prev >= 0) { st.buffered = rec[prev]; st.buffered.emit = 0; } else st.buffered.valid = 0;
+  if (st.out_pos > pb.out_stride) st.error |= 4;
+  if (W - R > (uint32_t)kMdCarryCap) st.error |= 8;
+  st.backlog = (int32_t)min(W - R, (uint32_t)kMdCarryCap);
+  st.frames_total += (uint32_t)nf;
+  pb.md_tail[(size_t)s * 4] = R; pb.md_tail[(size_t)s * 4 + 1] = (uint32_t)st.backlog; pb.md_tail[(size_t)s * 4 + 2] = B0;
+  pb.emit_n[s] = n_emit;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5: Huffman table-15 bit packing (SRC:1705-1737, writer semantics SRC:2230-2252).  One CTA per frame, one warp
+// per gc.  Lane L codes pairs 9L...9L+8, so a warp prefix sum of the lane bit counts gives every lane its bit
+// position; codes are OR-ed MSB-first into a shared bit buffer and the frame's bytes are written once.
+__global__ void __launch_bounds__(128) k_pack(Config cfg, PassBuffers pb) {
+  __shared__ uint32_t buf[548];
+  __shared__ uint8_t len15[256], code15[256];
+  const int s = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (f >= (int)pb.plan[s].n_frames) return;
+  for (int i = tid; i < 256; i += 128) { len15[i] = c_len15[i]; code15[i] = c_code15[i]; }
+  for (int i = tid; i < 548; i += 128) buf[i] = 0;
+  __syncthreads();
+  const int ch = cfg.channels, ngc = 2 * ch;
+  if (warp < ngc) {
+    const int gci = f * ngc + warp;
+    const size_t gslot = (size_t)s * pb.GC + gci;
+    const uint32_t sel = pb.gc_sel[gslot];
+    const int gain = sel & 255, bv = sel >> 8;
+    const float inv = c_inv_step[gain];
+    const float2 *sm2 = reinterpret_cast<const float2 *>(pb.smag + gslot * 576);
+    int32_t *trix = pb.tr_ix ? pb.tr_ix + gslot * 576 : nullptr;
+    uint32_t val[9]; int len[9]; int mine = 0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int p = 9 * lane + j;
+      float2 v = sm2[p];
+      int qx = quant15(fabsf(v.x), inv), qy = quant15(fabsf(v.y), inv);
+      if (trix) { trix[2 * p] = v.x < 0.0f ? -qx : qx; trix[2 * p + 1] = v.y < 0.0f ? -qy : qy; }
+      uint32_t code = code15[qx * 16 + qy]; int l = len15[qx * 16 + qy];
+      if (qx) { code = code << 1 | (v.x < 0.0f ? 1u : 0u); ++l; }   // SRC:1729-1736
+      if (qy) { code = code << 1 | (v.y < 0.0f ? 1u : 0u); ++l; }
+      if (p >= bv) l = 0;
+      val[j] = code; len[j] = l; mine += l;
+    }
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    uint32_t pos = pb.gc_bitoff[gslot] + (uint32_t)(incl - mine);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      if (len[j]) {
+        uint32_t w = pos >> 5, off = pos & 31;
+        unsigned long long v64 = (unsigned long long)val[j] << (64 - len[j] - off);
+        atomicOr(&buf[w], (uint32_t)(v64 >> 32));
+        uint32_t lo = (uint32_t)v64;
+        if (lo) atomicOr(&buf[w + 1], lo);
+        pos += len[j];
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t off = pb.fr_md[((size_t)s * pb.Fc + f) * 2], nbytes = pb.fr_md[((size_t)s * pb.Fc + f) * 2 + 1];
+  uint8_t *dst = pb.md + (size_t)s * pb.md_stride + off;
+  if (off + nbytes <= pb.md_stride)
+    for (uint32_t i = tid; i < nbytes; i += 128) dst[i] = (uint8_t)(buf[i >> 2] >> (24 - 8 * (i & 3)));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K_frames: header (SRC:522-544) + side info (SRC:571-625) + slot fill (SRC:2110-2121).  One warp per frame slot.
+struct BitW {   // MSB-first writer into a byte array (BitstreamWriter SRC:2230-2252), single thread
+  uint8_t *p; int n; uint32_t acc; int nb;
+  __device__ void put(uint32_t bits, int count) {
+    acc = (acc << count) | (bits & ((1u << count) - 1u)); nb += count;
+    while (nb >= 8) { nb -= 8; p[n++] = (uint8_t)(acc >> nb); }
+  }
+  __device__ void pad() { if (nb > 0) { p[n++] = (uint8_t)(acc << (8 - nb)); nb = 0; } acc = 0; }
+};
+
+__device__ inline uint16_t crc16_mpeg(const uint8_t *p, int n) {  // SRC:2190-2215 (poly 0x8005, init 0xFFFF)
+  uint32_t crc = 0xFFFF;
+  for (int i = 0; i < n; ++i) {
+    crc ^= (uint32_t)p[i] << 8;
+    for (int b = 0; b < 8; ++b) crc = (crc & 0x8000) ? ((crc << 1) ^ 0x8005) & 0xFFFF : (crc << 1) & 0xFFFF;
+  }
+  return (uint16_t)crc;
+}
+
+__global__ void __launch_bounds__(128) k_frames(Config cfg, PassBuffers pb) {
+  __shared__ uint8_t hdr[4][40];
+  const int s = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.y * 4 + warp;
+  if (r > (int)pb.plan[s].n_frames) return;
+  const FrameRec &fr = pb.rec[(size_t)s * (pb.Fc + 1) + r];
+  if (!fr.valid || !fr.emit) return;
+  const int ch = cfg.channels;
+  if (lane == 0) {
+    BitW w{hdr[warp], 0, 0, 0};
+    w.put(0x7FF, 11); w.put(3, 2); w.put(1, 2); w.put(cfg.crc ? 0 : 1, 1);
+    w.put(fr.br_index, 4); w.put(cfg.sr_index, 2); w.put(fr.padding, 1); w.put(0, 1);
+    w.put(cfg.mode_bits, 2); w.put(cfg.mode_ext, 2); w.put(cfg.copyright ? 1 : 0, 1); w.put(cfg.original ? 1 : 0, 1); w.put(0, 2);
+    if (cfg.crc) { uint16_t crc = crc16_mpeg(hdr[warp], 4); w.put(crc >> 8, 8); w.put(crc & 0xFF, 8); }   // SRC:538-543
+    w.put(min((int)fr.mdb, 511), 9); w.put(0, ch == 1 ? 5 : 3);
+    for (int c = 0; c < ch; ++c) w.put(0, 4);                                        // scfsi SRC:644
+    for (int j = 0; j < 2 * ch; ++j) {
+      const GcSide &g = fr.gc[j];
+      w.put(g.part23, 12); w.put(g.big_values, 9); w.put(g.global_gain, 8); w.put(0, 4);
+      const int ws = g.block_type != 0;
+      w.put(ws, 1);
+      if (ws) {
+        w.put(g.block_type, 2); w.put(g.block_type == 1, 1); w.put(15, 5); w.put(15, 5);
+        w.put(g.sbg[0], 3); w.put(g.sbg[1], 3); w.put(g.sbg[2], 3);
+      } else {
+        w.put(15, 5); w.put(15, 5); w.put(15, 5); w.put(g.region0, 4); w.put(g.region1, 3);
+      }
+      w.put(g.preflag, 1); w.put(0, 1); w.put(0, 1);
+    }
+    w.pad();
+    while (w.n < cfg.header_bytes) w.p[w.n++] = 0;
+  }
+  __syncwarp();
+  uint8_t *dst = pb.out + (size_t)s * pb.out_stride + fr.out_off;
+  if ((size_t)fr.out_off + cfg.header_bytes + fr.slot > pb.out_stride) return;
+  for (int i = lane; i < cfg.header_bytes; i += 32) dst[i] = hdr[warp][i];
+  dst += cfg.header_bytes;
+  const uint32_t B0 = pb.md_tail[(size_t)s * 4 + 2];
+  const uint8_t *carry = pb.md_carry + (size_t)s * kMdCarryCap, *md = pb.md + (size_t)s * pb.md_stride;
+  for (uint32_t i = lane; i < fr.slot; i += 32) {
+    uint8_t b = 0;
+    if (i < fr.take) { uint32_t o = fr.src_off + i; b = o < B0 ? carry[o] : md[o]; }
+    dst[i] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K_carry: state that crosses the pass boundary: last frame + pending partial PCM, reservoir backlog bytes, VBR
+// history, stereo decision of the carried frame.  One CTA per stream.
+__global__ void __launch_bounds__(256) k_carry(Config cfg, PassBuffers pb) {
+  __shared__ uint8_t tail[kMdCarryCap];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const StreamPlan plan = pb.plan[s];
+  const PcmView pv = pcm_view(cfg, pb, s);
+  const int64_t total = (int64_t)plan.head_n + plan.cur_n;
+  const int64_t start = (int64_t)plan.n_frames * cfg.fsc;
+  int64_t left = total - start - cfg.fsc; if (left < 0) left = 0;      // pending partial after the carried frame
+  const int keep = cfg.fsc + (int)left;
+  float *dst = pb.head_out + (size_t)s * 2 * cfg.fsc;
+  for (int i = tid; i < keep && i < 2 * cfg.fsc; i += 256) dst[i] = pv.at(start + i);
+  const uint32_t R = pb.md_tail[(size_t)s * 4], len = pb.md_tail[(size_t)s * 4 + 1], B0 = pb.md_tail[(size_t)s * 4 + 2];
+  uint8_t *carry = pb.md_carry + (size_t)s * kMdCarryCap;
+  const uint8_t *md = pb.md + (size_t)s * pb.md_stride;
+  for (uint32_t i = tid; i < len; i += 256) { uint32_t o = R + i; tail[i] = o < B0 ? carry[o] : md[o]; }
+  __syncthreads();
+  for (uint32_t i = tid; i < len; i += 256) carry[i] = tail[i];
+  StreamState &st = pb.state[s];
+  const int ngc = (int)plan.n_frames * 2 * cfg.channels;
+  if (tid == 0 && plan.n_frames) {
+    const float *hist = pb.gc_energy + (size_t)s * (10 + pb.GC);
+    int count = min(10, st.vbr_n + ngc);
+    float h[10];
+    for (int i = 0; i < count; ++i) h[i] = hist[10 + ngc - count + i];
+    for (int i = 0; i < count; ++i) st.vbr_hist[i] = h[i];
+    st.vbr_n = count;
+    st.ms_prev = pb.ms[(size_t)s * (pb.Fc + 1) + plan.n_frames];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PsychoacousticModel.maskingThresholds SRC:1983-2013 — dead output in the reference (SRC:737); trace only.
+__global__ void __launch_bounds__(256) k_thresholds(Config cfg, PassBuffers pb) {
+  const int s = blockIdx.x, lane = threadIdx.x & 31;
+  const int gci = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (gci >= (int)pb.plan[s].n_frames * 2 * cfg.channels || !pb.tr_thr || !pb.tr_spectrum) return;
+  const size_t gslot = (size_t)s * pb.GC + gci;
+  const float *x = pb.tr_spectrum + gslot * 576;
+  float *thr = pb.tr_thr + gslot * 576;
+  double qd = (double)(10 - cfg.quality) / 10.0;
+  const float quality_scale = (float)(qd > 0.1 ? qd : 0.1);
+  for (int i = lane; i < 576; i += 32) thr[i] = 0.0001f;
+  __syncwarp();
+  int cursor = 0;
+  for (int b = 0; b < 21; ++b) {
+    int end = min(c_sfb_cum[cfg.sfb_index][b], 576), size = end - cursor;
+    if (size > 0) {
+      float p = 0.0f;
+      for (int i = lane; i < size; i += 32) { float v = x[cursor + i]; p = __fmaf_rn(v, v, p); }
+      float t = fmaxf(__fmul_rn(__fdiv_rn(lane_tree(p), (float)size), quality_scale), 0.0001f);
+      for (int i = lane; i < size; i += 32) thr[cursor + i] = t;
+    }
+    cursor = end;
+    if (cursor >= 576) break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Output compaction: offsets[s] = 16-byte aligned exclusive prefix sum of the streams' output lengths.
+__global__ void __launch_bounds__(1024) k_offsets(Config cfg, PassBuffers pb, uint64_t *offsets) {
+  __shared__ uint64_t part[1024];
+  const int tid = threadIdx.x, S = cfg.n_streams;
+  const int per = (S + 1023) / 1024, b = tid * per, e = min(b + per, S);
+  uint64_t sum = 0;
+  for (int i = b; i < e; ++i) sum += ((uint64_t)pb.state[i].out_pos + 15) & ~15ull;
+  part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) { uint64_t run = 0; for (int i = 0; i < 1024; ++i) { uint64_t t = part[i]; part[i] = run; run += t; } offsets[S] = run; }
+  __syncthreads();
+  uint64_t run = part[tid];
+  for (int i = b; i < e; ++i) { offsets[i] = run; run += ((uint64_t)pb.state[i].out_pos + 15) & ~15ull; }
+}
+__global__ void __launch_bounds__(256) k_gather(Config cfg, PassBuffers pb, const uint64_t *offsets, uint8_t *compact) {
+  const int s = blockIdx.x;
+  const uint32_t len = pb.state[s].out_pos, n16 = (len + 15) >> 4;
+  const uint4 *src = reinterpret_cast<const uint4 *>(pb.out + (size_t)s * pb.out_stride);
+  uint4 *dst = reinterpret_cast<uint4 *>(compact + offsets[s]);
+  for (uint32_t i = blockIdx.y * 256 + threadIdx.x; i < n16; i += gridDim.y * 256) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Synthetic PCM (bench / tests), BASELINE C1/C4 recipe: a*sin(2 pi f t) + noise*N(0,1), clipped to [-1, 1].
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void k_synth(float *pcm, size_t n, int channels, int sample_rate, float f_left, float f_right, float amp,
+                        float noise, uint64_t seed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t h = splitmix64(seed * 0x100000001B3ull + i);
+  float u1 = ((uint32_t)(h >> 40) + 1u) * (1.0f / 16777217.0f), u2 = ((uint32_t)h >> 8) * (1.0f / 16777216.0f);
+  float rad = sqrtf(-2.0f * __logf(u1)), sn, cs;
+  __sincosf(6.28318530718f * u2, &sn, &cs);
+  for (int c = 0; c < channels; ++c) {
+    double cyc = (double)(c == 0 ? f_left : f_right) * (double)i / (double)sample_rate;
+    float ph = (float)(cyc - floor(cyc));
+    float v = amp * sinpif(2.0f * ph + (c == 1 ? 0.3f / 3.14159265f : 0.0f)) + noise * rad * (c == 0 ? cs : sn);
+    pcm[i * channels + c] = fminf(fmaxf(v, -1.0f), 1.0f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launchers
+static inline int check(int launched) { cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? launched : -(int)e; }
+
+int launch_prepass(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  dim3 grid(cfg.n_streams, (pb.Fc + 3) / 4);
+  k_prepass<<<grid, 128, 0, st>>>(cfg, pb);
+  int n = 1;
+  if (cfg.vbr) { dim3 g2(cfg.n_streams, (pb.Fc + 63) / 64); k_bitrate<<<g2, 64, 0, st>>>(cfg, pb); ++n; }
+  return check(n);
+}
+int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  static bool attr_set[64] = {};
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpecSmemBytes);
+    attr_set[dev] = true;
+  }
+  dim3 grid(cfg.n_streams, cfg.channels, (2 * pb.Fc + kRunGranules - 1) / kRunGranules);
+  k_spectrum<<<grid, kSteps, kSpecSmemBytes, st>>>(cfg, pb);
+  return check(1);
+}
+int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  dim3 grid(cfg.n_streams, (pb.GC + 7) / 8);
+  k_curve<<<grid, 256, 0, st>>>(cfg, pb);
+  return check(1);
+}
+int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  k_scan<<<(cfg.n_streams + 63) / 64, 64, 0, st>>>(cfg, pb);
+  return check(1);
+}
+int launch_pack(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  dim3 grid(cfg.n_streams, pb.Fc);
+  k_pack<<<grid, 128, 0, st>>>(cfg, pb);
+  return check(1);
+}
+int launch_frames(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  dim3 grid(cfg.n_streams, (pb.Fc + 1 + 3) / 4);
+  k_frames<<<grid, 128, 0, st>>>(cfg, pb);
+  return check(1);
+}
+int launch_carry(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  k_carry<<<cfg.n_streams, 256, 0, st>>>(cfg, pb);
+  return check(1);
+}
+int launch_thresholds(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  dim3 grid(cfg.n_streams, (pb.GC + 7) / 8);
+  k_thresholds<<<grid, 256, 0, st>>>(cfg, pb);
+  return check(1);
+}
+int launch_compact(const Config &cfg, const PassBuffers &pb, uint64_t *offsets, uint8_t *compact, int gather, cudaStream_t st) {
+  if (!gather) { k_offsets<<<1, 1024, 0, st>>>(cfg, pb, offsets); return check(1); }
+  dim3 grid(cfg.n_streams, 8);
+  k_gather<<<grid, 256, 0, st>>>(cfg, pb, offsets, compact);
+  return check(1);
+}
+int launch_synth(float *d_pcm, size_t n_per_channel, int channels, int sample_rate, float f_left, float f_right, float amp,
+                 float noise, uint64_t seed, cudaStream_t st) {
+  if (!n_per_channel) return 0;
+  k_synth<<<(unsigned)((n_per_channel + 255) / 256), 256, 0, st>>>(d_pcm, n_per_channel, channels, sample_rate, f_left, f_right,
+                                                                   amp, noise, seed);
+  return check(1);
+}
+
+}  // namespace mp3b

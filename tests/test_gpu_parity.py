@@ -1,0 +1,117 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs — bytes, side-info
+records, MDCT spectra and quantized ix must all be bit-identical."""
+import numpy as np
+import pytest
+
+import signals
+
+pytestmark = pytest.mark.gpu
+
+MODE = {"mono": 0, "stereo": 1, "jointStereo": 2}
+
+
+def _opts(mp3, **o):
+    return mp3.MP3EncoderOptions(sampleRate=o.get("sample_rate", 44100), bitrateKbps=o.get("bitrate_kbps", 128),
+                                 vbr=o.get("vbr", False), mode=MODE[o.get("mode", "stereo")], quality=o.get("quality", 5),
+                                 crcProtected=o.get("crc_protected", False), original=o.get("original", True),
+                                 copyright=o.get("copyright", False))
+
+
+def _compare(mp3, orc, pcm, frames_per_pass=0, arrays=True, **o):
+    ref_bytes, rs = orc.encode_all(pcm, trace=True, **o)
+    b = mp3.EncoderBatch(_opts(mp3, **o), 1, 0, frames_per_pass)
+    b.set_trace(spectrum=arrays, ix=arrays, thresholds=arrays)
+    out = b.encode([pcm], flush=True)[0]
+    gt, ft = rs.gc_trace(), rs.frame_trace()
+    gg, gf = b.trace_gc(0), b.trace_frames(0)
+    assert len(gf) == len(ft) and len(gg) == len(gt)
+    for a, r in (("bitrate_index", "bitrate_index"), ("padding", "padding"), ("frame_size", "frame_size"),
+                 ("main_data_size", "main_data_size"), ("ms", "ms"), ("is_final", "is_final"),
+                 ("reservoir_bits", "reservoir_bits"), ("huff_bytes", "huff_bytes"), ("main_data_begin", "main_data_begin")):
+        bad = np.nonzero(gf[a] != ft[r])[0]
+        assert bad.size == 0, "frame field %s differs first at frame %d: gpu %s oracle %s" % (a, bad[0], gf[a][bad[0]], ft[r][bad[0]])
+    assert np.array_equal(gf["frame_energy"].view("<u4"), ft["frame_energy"].view("<u4"))
+    for a, r in (("block_type", "block_type"), ("g0", "g0"), ("max_bits", "max_bits"), ("gain_used", "gain_used"),
+                 ("global_gain", "gain_out"), ("iterations", "iterations"), ("part23_length", "bits"),
+                 ("big_values", "big_values"), ("region0", "region0"), ("region1", "region1"), ("preflag", "preflag")):
+        bad = np.nonzero(gg[a] != gt[r])[0]
+        assert bad.size == 0, "gc field %s differs first at gc %d: gpu %s oracle %s" % (a, bad[0], gg[a][bad[0]], gt[r][bad[0]])
+    assert np.array_equal(gg["subblock_gain"], gt["subblock_gain"])
+    assert np.array_equal(gg["energy"].view("<u4"), gt["energy"].view("<u4"))
+    if arrays:
+        spec = b.trace_array(0, "spectrum")
+        bad = np.nonzero((spec.view("<u4") != gt["spectrum"].view("<u4")) & ~((spec == 0) & (gt["spectrum"] == 0)))
+        assert bad[0].size == 0, "spectrum differs first at gc %d line %d" % (bad[0][0], bad[1][0])
+        assert np.array_equal(b.trace_array(0, "ix"), gt["ix"])
+        assert np.array_equal(b.trace_array(0, "thresholds").view("<u4"), gt["thresholds"].view("<u4"))
+    assert b.frame_count(0) == rs.frame_count and b.byte_count(0) == rs.byte_count
+    assert out == ref_bytes
+    assert b.xing_header(0) == rs.xing_header()
+    b.close()
+    return out
+
+
+def test_c1_sine_noise_stereo_cbr128(mp3, orc):
+    _compare(mp3, orc, signals.sine_noise(2.0))
+
+
+def test_c1_multi_pass(mp3, orc):
+    """Same stream cut into passes of 7 frames: the carried state (PCM look-back, reservoir, backlog) is exact."""
+    _compare(mp3, orc, signals.sine_noise(1.5, seed=7), frames_per_pass=7)
+
+
+def test_c2_mono_48k_320(mp3, orc):
+    _compare(mp3, orc, signals.white(2.0), sample_rate=48000, bitrate_kbps=320, mode="mono")
+
+
+def test_c3_joint_vbr_transients(mp3, orc):
+    pcm = signals.castanets(3.0)
+    _compare(mp3, orc, pcm, sample_rate=44100, bitrate_kbps=128, mode="jointStereo", vbr=True, quality=2)
+    _compare(mp3, orc, pcm, frames_per_pass=5, arrays=False, sample_rate=44100, bitrate_kbps=128, mode="jointStereo", vbr=True, quality=2)
+
+
+def test_silence_and_ragged_tail(mp3, orc):
+    _compare(mp3, orc, np.zeros(2304 * 3 + 777, np.float32))
+    _compare(mp3, orc, signals.sine440(3)[: 2304 * 2 + 10], crc_protected=True, copyright=True, original=False)
+
+
+@pytest.mark.parametrize("cfg", [dict(sample_rate=32000, bitrate_kbps=64), dict(sample_rate=48000, bitrate_kbps=192),
+                                 dict(sample_rate=44100, bitrate_kbps=128, mode="mono"),
+                                 dict(sample_rate=44100, bitrate_kbps=128, mode="jointStereo"),
+                                 dict(sample_rate=44100, bitrate_kbps=100, vbr=True, quality=0)])
+def test_reference_configurations(mp3, orc, cfg):
+    """The configurations of the reference's multipleConfigurationsDecodeSuccessfully (TST:727-755) + off-table VBR."""
+    ch = 1 if cfg.get("mode") == "mono" else 2
+    pcm = signals.sine_noise(0.7, sr=cfg["sample_rate"], channels=ch, seed=11)
+    _compare(mp3, orc, pcm, **cfg)
+
+
+def test_streaming_chunks_match_one_shot(mp3, orc):
+    """encode(samples:) fed in ragged chunks gives the same bytes as one call, and as the oracle fed the same chunks."""
+    pcm = signals.sine_noise(1.0, seed=5)
+    s = mp3.MP3Encoder(_opts(mp3)).newSession()
+    rs = orc.Session()
+    cuts = [0, 100, 2304, 2305, 9000, 9000, 20000, 41234, pcm.size]
+    got, ref = b"", b""
+    for a, z in zip(cuts[:-1], cuts[1:]):
+        g, r = s.encode(pcm[a:z]), rs.encode(pcm[a:z])
+        assert g == r
+        got += g; ref += r
+    g, r = s.flush(), rs.flush()
+    assert g == r and s.flush() == b"" and rs.flush() == b""
+    assert s.encodedFrameCount == rs.frame_count and s.encodedByteCount == rs.byte_count
+    one, _ = orc.encode_all(pcm)
+    assert got + g == one
+
+
+def test_batch_of_independent_streams(mp3, orc):
+    """Ragged batch: streams of different lengths (one empty) in one call; each equals its own oracle session."""
+    lens = [0.0, 0.31, 0.5, 0.77, 0.5, 1.01]
+    pcms = [signals.sine_noise(t, seed=100 + i, f_left=110.0 * 2 ** (i / 12.0), f_right=138.6 * 2 ** (i / 12.0)) for i, t in enumerate(lens)]
+    b = mp3.EncoderBatch(_opts(mp3), len(pcms), 0, 6)
+    outs = b.encode(pcms, flush=True)
+    for i, p in enumerate(pcms):
+        ref, rs = orc.encode_all(p)
+        assert outs[i] == ref, "stream %d" % i
+        assert b.frame_count(i) == rs.frame_count
+    b.close()
