@@ -1,0 +1,292 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the B200-native MP3 encode path.
+
+Metric (BASELINE.json): encoded audio seconds per second (x realtime), whole job over all GPUs.
+Workload (BASELINE config 4, weak scaling): every GPU encodes its shard of the batch of independent 30 s 44.1 kHz
+stereo CBR 128 kbps streams — 512 streams per GPU, i.e. the named 4096-stream batch at N = 8.  One "step" = every
+stream of the shard through fresh EncoderSessions: encode(samples:) of the whole stream + flush().
+
+  value : PCM already resident in HBM, MP3 frames left in HBM (device plane of the C ABI), timed with CUDA events on
+          the engine's own stream, max over ranks.
+  e2e   : the same step through the reference-facing call with HOST buffers (pinned): H2D of the PCM and D2H of the
+          MP3 bytes inside the timed region, wall clock bracketed by synchronize + barrier, max over ranks.
+  --impl reference : the CPU restatement of the reference (oracle/, the Swift original cannot be built here) on all
+          host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SR, CH, KBPS = 44100, 2, 128
+ALGO_BYTES_PER_GC_SPECTRUM = 2304 + 2304 + 4      # PCM in + sign*|x|^0.75 out + meta word
+FLOP_PER_GC_SPECTRUM = 18 * (512 + 448 + 2 * 2048) + 32 * (36 + 2 * 648 + 18)   # direct form as executed, long blocks
+
+
+def stream_params(i):
+    """BASELINE C4 recipe: seed 1000+i, f_L = 110 * 2^((i mod 48)/12), f_R = 1.26 f_L."""
+    fl = 110.0 * 2.0 ** ((i % 48) / 12.0)
+    return fl, fl * 1.26, 1000 + i
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(seconds_per_stream, min_wall=10.0, max_wall=40.0):
+    """The CPU restatement of the reference on every host core: bounded sample of the C4 workload."""
+    import numpy as np
+    import oracle_binding as orc
+    import signals
+    cores = os.cpu_count() or 1
+    n = max(2 * cores, 8)
+    pcms = [signals.sine_noise(seconds_per_stream, sr=SR, f_left=stream_params(i)[0], f_right=stream_params(i)[1],
+                               seed=stream_params(i)[2]) for i in range(min(n, 16))]
+    pcms = [pcms[i % len(pcms)] for i in range(n)]
+    opts = dict(sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")
+    orc.encode_streams(pcms[:cores], cores, **opts)            # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        orc.encode_streams(pcms, cores, **opts)
+        done += n
+        el = time.perf_counter() - t0
+        if el >= min_wall or el >= max_wall:
+            break
+    audio = done * seconds_per_stream
+    return {"value": audio / el, "unit": "x realtime (audio s / s)", "cores": cores, "kind": "port",
+            "sample": "%d streams x %.0f s of the C4 recipe (44.1 kHz stereo CBR128), one oracle session per stream, "
+                      "%d threads, %.1f s wall" % (done, seconds_per_stream, cores, el)}, el, audio
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native")
+    ap.add_argument("--streams", type=int, default=512, help="streams per GPU")
+    ap.add_argument("--seconds", type=float, default=30.0)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "encoded audio sec/sec (x realtime)"
+    workload = ("C4 shard: %d independent %.0f s 44.1 kHz stereo CBR 128 kbps streams per GPU (4096 x 30 s at 8 GPUs); "
+                "inputs %.1f GB per GPU > L2" % (a.streams, a.seconds, a.streams * a.seconds * SR * CH * 4 / 1e9))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        res, el, audio = cpu_reference(a.seconds, min_wall=max(5.0, 2.0 * a.steps), max_wall=120.0)
+        line = {"impl": "reference", "metric": metric, "value": res["value"], "unit": "x realtime", "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * el / max(a.steps, 1), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "reference": "C restatement of SwiftMP3 (oracle/); the Swift + Accelerate "
+                           "original cannot be built on Linux"},
+                "cpu_baseline": res,
+                "e2e": {"value": res["value"], "unit": "x realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    mp3 = importlib.import_module("swift-mp3_b200")
+    L = mp3.lib()
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    S = a.streams
+    n_per = int(round(a.seconds * SR))
+    n_floats = n_per * CH
+    pcm = torch.empty((S, n_floats), dtype=torch.float32, device="cuda")
+    for i in range(S):
+        fl, fr, seed = stream_params(rank * S + i)
+        rc = L.mp3b_synth_fill(local, pcm[i].data_ptr(), n_per, CH, SR, fl, fr, 0.5, 0.05, seed)
+        assert rc == 0, L.mp3b_last_error()
+    torch.cuda.synchronize()
+    dptrs = (C.c_void_p * S)(*[pcm[i].data_ptr() for i in range(S)])
+    ns = (C.c_size_t * S)(*([n_floats] * S))
+    opts = mp3.MP3EncoderOptions(sampleRate=SR, bitrateKbps=KBPS, mode=mp3.Mode.stereo)
+    b = mp3.EncoderBatch(opts, S, local)
+    ext = torch.cuda.ExternalStream(b.cuda_stream, device=torch.device("cuda", local))
+    audio_per_step = S * a.seconds
+
+    # ---- parity spot check (untimed): two streams of this shard against the CPU oracle
+    parity = None
+    if rank == 0:
+        import oracle_binding as orc
+        b.reset()
+        b.encode_device(dptrs, ns, flush=True, download=True)
+        checked = 0
+        for i in (0, S - 1):
+            ref, _ = orc.encode_all(pcm[i].cpu().numpy(), sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")
+            assert b.output(i) == ref, "stream %d differs from the oracle" % i
+            checked += 1
+        parity = "%d streams bit-identical to the oracle" % checked
+
+    # ---- value: device plane, K steps
+    def step_device():
+        b.reset()
+        b.encode_device(dptrs, ns, flush=True, download=False)
+
+    for _ in range(a.warmup):
+        step_device()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    stages = {k: 0.0 for k in mp3.STAGES}
+    launches = passes = 0
+    for _ in range(a.steps):
+        step_device()
+        for k, v in b.stage_ms().items():
+            stages[k] += v
+        launches += b.launch_count; passes += b.pass_count
+    e1.record(ext)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    ms_per_step = ms_total / a.steps
+    value = world * audio_per_step / (ms_per_step / 1000.0)
+    out_bytes = b.output_total
+
+    # ---- roofline of the dominant kernel (k_spectrum: filterbank + MDCT), from the engine's CUDA events
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, which = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    frames = (n_per + 1151) // 1152
+    gc_per_step = S * frames * 2 * CH
+    spectrum_ms_per_launch = stages["spectrum"] / max(passes, 1)
+    gc_per_launch = gc_per_step * a.steps / max(passes, 1)
+    achieved = gc_per_launch * ALGO_BYTES_PER_GC_SPECTRUM / (spectrum_ms_per_launch / 1000.0) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "spectrum_traffic.json")))["dram_bytes_per_gc"] * gc_per_launch
+    except Exception:
+        pass
+    fp32_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) / 1000.0) / 1000.0   # nominal TFLOP/s, non-tensor FP32
+    fp32_ach = gc_per_launch * FLOP_PER_GC_SPECTRUM * (16.0 / 15.0) / (spectrum_ms_per_launch / 1000.0) / 1e12
+    roofline = {"kernel": "k_spectrum (polyphase filterbank + MDCT + |x|^0.75)", "bound": "hbm", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": which,
+                "ms_per_launch": spectrum_ms_per_launch, "gc_per_launch": gc_per_launch,
+                "limiter": "fp32 (direct-form 32x64 matrixing kept for bit-exact parity); see fp32",
+                "fp32": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
+                         "peak_source": "nominal 148 SM x 128 lanes x 2 x sm_max_mhz"},
+                "stage_ms_per_step": {k: v / a.steps for k, v in stages.items()}}
+
+    # ---- e2e: host plane (pinned PCM in, MP3 bytes out), wall clock
+    e2e_steps = a.e2e_steps or min(a.steps, 5)
+    hp = C.c_void_p()
+    assert L.mp3b_host_alloc(S * n_floats * 4, C.byref(hp)) == 0, L.mp3b_last_error()
+    assert L.mp3b_device_copy(local, hp, pcm.data_ptr(), S * n_floats * 4, 1) == 0
+    hptrs = (C.c_void_p * S)(*[hp.value + i * n_floats * 4 for i in range(S)])
+
+    def step_host():
+        b.reset()
+        b.encode_ptrs(hptrs, ns, flush=True)
+
+    for _ in range(max(1, min(a.warmup, 2))):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    e2e_stage = b.stage_ms()
+    e2e = {"value": world * audio_per_step / e2e_s, "unit": "x realtime", "h2d_bytes_per_step": S * n_floats * 4,
+           "d2h_bytes_per_step": int(b.output_total), "ms_per_step": 1000.0 * e2e_s, "steps": e2e_steps,
+           "stage_ms_last_step": e2e_stage}
+    if rank == 0:
+        import oracle_binding as orc
+        ref, _ = orc.encode_all(pcm[1].cpu().numpy(), sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")
+        assert b.output(1) == ref, "e2e output differs from the oracle"
+    L.mp3b_host_free(hp)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cpu, _, _ = cpu_reference(a.seconds, min_wall=10.0, max_wall=30.0)
+    total_launches = int(sum_over_ranks(launches))
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": "x realtime", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": workload, "streams_per_gpu": S, "seconds_per_stream": a.seconds,
+                                                "frames_per_pass": b.frames_per_pass, "l2": "inputs larger than L2",
+                                                "parity": parity, "output_bytes_per_step_per_gpu": int(out_bytes)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -96,6 +96,8 @@ int mp3b_batch_create_ex(const mp3b_options *opts, int n_streams, int device, in
 int mp3b_batch_frames_per_pass(const mp3b_batch *b);
 void mp3b_batch_destroy(mp3b_batch *b);
 int mp3b_batch_stream_count(const mp3b_batch *b);
+/* Every stream back to a fresh EncoderSession (SRC:268-282) without reallocating anything. */
+int mp3b_batch_reset(mp3b_batch *b);
 /* One encode(samples:) per stream: pcm[i] = HOST pointer to n_floats[i] interleaved floats (may be 0 / NULL).
  * flush != 0 additionally performs flush() on every stream afterwards (SRC:318-350).  flush_mask (may be
  * NULL) restricts the flush to streams with a non-zero byte.  The H2D copies, the device pipeline and the
@@ -128,10 +130,14 @@ int mp3b_device_sync(int device);
 /* Per-stage device time of the last batch call, in milliseconds, summed over the call's passes.
  * Stage order: see MP3B_STAGE_*.  n = entries available in ms[]. */
 enum {
-  MP3B_STAGE_H2D = 0, MP3B_STAGE_PREPASS, MP3B_STAGE_SPECTRUM, MP3B_STAGE_SCAN, MP3B_STAGE_PACK, MP3B_STAGE_FRAMES,
-  MP3B_STAGE_D2H, MP3B_STAGE_TOTAL, MP3B_STAGE_COUNT
+  MP3B_STAGE_H2D = 0, MP3B_STAGE_PREPASS, MP3B_STAGE_SPECTRUM, MP3B_STAGE_CURVE, MP3B_STAGE_SCAN, MP3B_STAGE_PACK,
+  MP3B_STAGE_FRAMES, MP3B_STAGE_D2H, MP3B_STAGE_TOTAL, MP3B_STAGE_COUNT
 };
 int mp3b_batch_stage_ms(const mp3b_batch *b, float *ms, int n);
+/* Number of device passes of the last batch call (each stage kernel is launched once per pass). */
+int mp3b_batch_pass_count(const mp3b_batch *b);
+/* The CUDA stream (cudaStream_t) all work of this batch is issued on, so that callers can record their own events. */
+void *mp3b_batch_stream(const mp3b_batch *b);
 /* Number of kernel launches issued by the last batch call. */
 int mp3b_batch_launch_count(const mp3b_batch *b);
 /* Enable per-granule-channel traces (costs device memory and bandwidth; off by default).  bit0: keep MDCT

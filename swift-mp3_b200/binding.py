@@ -37,7 +37,7 @@ GC_RECORD = np.dtype([("part23_length", "<i4"), ("big_values", "<i4"), ("global_
 FRAME_RECORD = np.dtype([("bitrate_index", "<i4"), ("padding", "<i4"), ("frame_size", "<i4"), ("main_data_size", "<i4"),
                          ("main_data_begin", "<i4"), ("reservoir_bits", "<i4"), ("huff_bytes", "<i4"), ("ms", "<i4"),
                          ("is_final", "<i4"), ("frame_energy", "<f4")])
-STAGES = ("h2d", "prepass", "spectrum", "scan", "pack", "frames", "d2h", "total")
+STAGES = ("h2d", "prepass", "spectrum", "curve", "scan", "pack", "frames", "d2h", "total")
 
 _lib = None
 
@@ -86,6 +86,7 @@ def lib():
         "mp3b_device_alloc": (i32, [i32, sz, C.POINTER(vp)]), "mp3b_device_free": (None, [i32, vp]),
         "mp3b_device_copy": (i32, [i32, vp, vp, sz, i32]), "mp3b_device_sync": (i32, [i32]),
         "mp3b_batch_stage_ms": (i32, [vp, C.POINTER(C.c_float), i32]), "mp3b_batch_launch_count": (i32, [vp]),
+        "mp3b_batch_pass_count": (i32, [vp]), "mp3b_batch_stream": (vp, [vp]), "mp3b_batch_reset": (i32, [vp]),
         "mp3b_batch_set_trace": (i32, [vp, i32]), "mp3b_batch_trace_frames": (i32, [vp, i32]),
         "mp3b_batch_trace_frame_records": (i32, [vp, i32, vp, i32]),
         "mp3b_batch_trace_gc_records": (i32, [vp, i32, vp, i32]),
@@ -308,6 +309,18 @@ class EncoderBatch:
     @property
     def launch_count(self):
         return lib().mp3b_batch_launch_count(self._h)
+
+    @property
+    def pass_count(self):
+        return lib().mp3b_batch_pass_count(self._h)
+
+    @property
+    def cuda_stream(self):
+        """cudaStream_t (as an int) all work of this batch is issued on."""
+        return lib().mp3b_batch_stream(self._h)
+
+    def reset(self):
+        _check(lib().mp3b_batch_reset(self._h))
 
     # ---- traces (tests) ----
     def set_trace(self, spectrum=False, ix=False, thresholds=False, records=True):

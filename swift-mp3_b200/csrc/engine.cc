@@ -74,7 +74,7 @@ struct mp3b_batch {
   int sticky = 0;
   // measurement
   float stage_ms[MP3B_STAGE_COUNT] = {};
-  int launches = 0;
+  int launches = 0, passes = 0;
   cudaEvent_t ev[MP3B_STAGE_COUNT + 1] = {};
   // trace
   int trace = 0;
@@ -138,7 +138,7 @@ void free_batch(mp3b_batch *b) {
   if (b->st) cudaStreamSynchronize(b->st);
   PassBuffers &p = b->pb;
   void *dev[] = {p.plan, p.state, b->d_head[0], b->d_head[1], p.ms, p.frame_energy, p.gc_energy, p.gc_bt, p.frame_br, p.smag,
-                 p.gc_meta, p.gc_bits, p.gc_bv, p.gc_bitoff, p.gc_sel, p.fr_md, p.rec, p.md, p.md_tail, p.md_carry, p.out,
+                 p.gc_meta, p.gc_bits, p.gc_bv, p.gc_bitoff, p.gc_sel, p.fr_md, p.rec, p.emit, p.md, p.md_tail, p.md_carry, p.out,
                  p.emit_size, p.emit_n, p.tr_spectrum, p.tr_ix, p.tr_thr, b->d_stage, b->d_offsets, b->d_compact};
   for (void *q : dev) if (q) cudaFree(q);
   void *host[] = {b->h_plan, b->h_state, b->h_emit_size, b->h_emit_n, b->h_offsets, b->h_out};
@@ -185,7 +185,7 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   A(dalloc(p.ms, S * (Fc + 1))); A(dalloc(p.frame_energy, S * Fc)); A(dalloc(p.gc_energy, S * (10 + GC)));
   A(dalloc(p.gc_bt, S * GC)); A(dalloc(p.frame_br, S * Fc)); A(dalloc(p.smag, S * GC * 576, false));
   A(dalloc(p.gc_meta, S * GC)); A(dalloc(p.gc_bits, S * GC * kMaxEntries)); A(dalloc(p.gc_bv, S * GC * kMaxEntries));
-  A(dalloc(p.gc_bitoff, S * GC)); A(dalloc(p.gc_sel, S * GC)); A(dalloc(p.fr_md, S * Fc * 2)); A(dalloc(p.rec, S * (Fc + 1)));
+  A(dalloc(p.gc_bitoff, S * GC)); A(dalloc(p.gc_sel, S * GC)); A(dalloc(p.fr_md, S * Fc * 2)); A(dalloc(p.rec, S * (Fc + 1))); A(dalloc(p.emit, S * (Fc + 1)));
   p.md_stride = round_up<size_t>(kMdCarryCap + (size_t)Fc * 2 * cfg.channels * 540, 16);
   A(dalloc(p.md, S * p.md_stride, false)); A(dalloc(p.md_tail, S * 4)); A(dalloc(p.md_carry, S * kMdCarryCap));
   A(dalloc(p.emit_size, S * (Fc + 1))); A(dalloc(p.emit_n, S));
@@ -253,7 +253,7 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
     CU(cudaMalloc((void **)&b->d_stage, (size_t)S * b->stage_stride * sizeof(float)));
   }
   for (auto &m : b->stage_ms) m = 0.0f;
-  b->launches = 0;
+  b->launches = 0; b->passes = 0;
   b->have_host_out = false;
   if (b->trace) {
     b->tr_frames.assign(S, {}); b->tr_gc.assign(S, {}); b->tr_spec.assign(S, {}); b->tr_ix.assign(S, {}); b->tr_thr.assign(S, {});
@@ -322,16 +322,18 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
     LAUNCH(launch_prepass(cfg, pb, st));
     CU(cudaEventRecord(b->ev[2], st));
     LAUNCH(launch_spectrum(cfg, pb, st));
+    CU(cudaEventRecord(b->ev[3], st));
     LAUNCH(launch_curve(cfg, pb, st));
     if (b->trace & 4) LAUNCH(launch_thresholds(cfg, pb, st));
-    CU(cudaEventRecord(b->ev[3], st));
-    LAUNCH(launch_scan(cfg, pb, st));
     CU(cudaEventRecord(b->ev[4], st));
-    LAUNCH(launch_pack(cfg, pb, st));
+    LAUNCH(launch_scan(cfg, pb, st));
     CU(cudaEventRecord(b->ev[5], st));
+    LAUNCH(launch_pack(cfg, pb, st));
+    CU(cudaEventRecord(b->ev[6], st));
     LAUNCH(launch_frames(cfg, pb, st));
     LAUNCH(launch_carry(cfg, pb, st));
-    CU(cudaEventRecord(b->ev[6], st));
+    CU(cudaEventRecord(b->ev[7], st));
+    b->passes += 1;
     b->head_sel ^= 1;
     CU(cudaMemcpyAsync(b->h_emit_n, pb.emit_n, (size_t)S * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(b->h_emit_size, pb.emit_size, (size_t)S * (Fc + 1) * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
@@ -342,9 +344,9 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
     cudaError_t se = cudaStreamSynchronize(st);
     if (se != cudaSuccess) { b->sticky = MP3B_ERR_CUDA; return fail(MP3B_ERR_CUDA, "device pipeline failed: %s", cudaGetErrorString(se)); }
     {
-      static const int stage_of[6] = {MP3B_STAGE_H2D, MP3B_STAGE_PREPASS, MP3B_STAGE_SPECTRUM, MP3B_STAGE_SCAN, MP3B_STAGE_PACK, MP3B_STAGE_FRAMES};
-      for (int i = 0; i < 6; ++i) { float ms = 0; cudaEventElapsedTime(&ms, b->ev[i], b->ev[i + 1]); b->stage_ms[stage_of[i]] += ms; }
-      float ms = 0; cudaEventElapsedTime(&ms, b->ev[0], b->ev[6]); b->stage_ms[MP3B_STAGE_TOTAL] += ms;
+      static const int stage_of[7] = {MP3B_STAGE_H2D, MP3B_STAGE_PREPASS, MP3B_STAGE_SPECTRUM, MP3B_STAGE_CURVE, MP3B_STAGE_SCAN, MP3B_STAGE_PACK, MP3B_STAGE_FRAMES};
+      for (int i = 0; i < 7; ++i) { float ms = 0; cudaEventElapsedTime(&ms, b->ev[i], b->ev[i + 1]); b->stage_ms[stage_of[i]] += ms; }
+      float ms = 0; cudaEventElapsedTime(&ms, b->ev[0], b->ev[7]); b->stage_ms[MP3B_STAGE_TOTAL] += ms;
     }
     for (int s = 0; s < S; ++s) {
       uint32_t ne = b->h_emit_n[s];
@@ -635,6 +637,24 @@ int mp3b_batch_stage_ms(const mp3b_batch *b, float *ms, int n) {
   return MP3B_STAGE_COUNT;
 }
 int mp3b_batch_launch_count(const mp3b_batch *b) { return b ? b->launches : 0; }
+int mp3b_batch_pass_count(const mp3b_batch *b) { return b ? b->passes : 0; }
+void *mp3b_batch_stream(const mp3b_batch *b) { return b ? (void *)b->st : nullptr; }
+int mp3b_batch_reset(mp3b_batch *b) {
+  if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");
+  CU(cudaSetDevice(b->device));
+  const size_t S = b->S;
+  CU(cudaMemsetAsync(b->pb.state, 0, S * sizeof(StreamState), b->st));
+  CU(cudaMemsetAsync(b->d_head[0], 0, S * 2 * b->cfg.fsc * sizeof(float), b->st));
+  CU(cudaMemsetAsync(b->d_head[1], 0, S * 2 * b->cfg.fsc * sizeof(float), b->st));
+  CU(cudaStreamSynchronize(b->st));
+  std::fill(b->pending.begin(), b->pending.end(), 0u);
+  std::fill(b->out_len.begin(), b->out_len.end(), 0u);
+  std::fill(b->frame_count.begin(), b->frame_count.end(), 0u);
+  std::fill(b->byte_count.begin(), b->byte_count.end(), 0u);
+  for (auto &v : b->frame_sizes) v.clear();
+  b->out_total = 0; b->have_host_out = false; b->sticky = 0;
+  return MP3B_OK;
+}
 int mp3b_batch_set_trace(mp3b_batch *b, int flags) { if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch"); b->trace = flags ? (flags | 8) : 0; return MP3B_OK; }
 int mp3b_batch_trace_frames(const mp3b_batch *b, int stream) {
   if (!b || stream < 0 || stream >= b->S || (size_t)stream >= b->tr_frames.size()) return 0;

@@ -108,25 +108,25 @@ __device__ __forceinline__ void transient_decide(const float e3[3], int &bt, int
   }
 }
 
-__global__ void __launch_bounds__(128) k_prepass(Config cfg, PassBuffers pb) {
-  const int s = blockIdx.x, lane = threadIdx.x & 31;
-  const int f = blockIdx.y * 4 + (threadIdx.x >> 5);
-  const StreamPlan &plan = pb.plan[s];
-  if (f >= (int)plan.n_frames) return;
-  const int ch = cfg.channels;
-  const PcmView pv = pcm_view(cfg, pb, s);
-  const int64_t q0 = (int64_t)(1 + f) * cfg.fsc;
-  StreamState &stt = pb.state[s];
-
-  if (f == 0 && lane < 10) {  // carried VBR history, right aligned in front of this pass's gc energies
-    int n = stt.vbr_n;
-    pb.gc_energy[(size_t)s * (10 + pb.GC) + lane] = lane >= 10 - n ? stt.vbr_hist[lane - (10 - n)] : 0.0f;
+// Frame access for the pre-pass: MODE 0 = generic (frame straddles head / cur / zero padding), 1 = contiguous in cur,
+// 2 = contiguous and 8-byte aligned (stereo pairs as one 64-bit load).
+template <int MODE> struct FrameLoad {
+  PcmView pv; int64_t q0; const float *p;
+  __device__ __forceinline__ float one(int i) const { return MODE ? __ldg(p + i) : pv.at(q0 + i); }
+  __device__ __forceinline__ float2 pair(int n) const {
+    if (MODE == 2) return __ldg(reinterpret_cast<const float2 *>(p) + n);
+    return make_float2(one(2 * n), one(2 * n + 1));
   }
+};
 
-  // frame energy over the interleaved frame, lane = float index mod 32 [OD1b]
+template <int MODE> __device__ __forceinline__ void prepass_frame(const Config &cfg, const PassBuffers &pb, const FrameLoad<MODE> &ld,
+                                                                  int s, int f, int lane) {
+  const int ch = cfg.channels;
+  // frame energy over the interleaved frame (SRC:477), lane = float index mod 32 [OD1b]
   float pf = 0.0f;
-  for (int i = lane; i < cfg.fsc; i += 32) { float x = pv.at(q0 + i); pf = __fmaf_rn(x, x, pf); }
-  float frame_energy = __fdiv_rn(lane_tree(pf), (float)cfg.fsc);
+#pragma unroll 8
+  for (int i = lane; i < cfg.fsc; i += 32) { float x = ld.one(i); pf = __fmaf_rn(x, x, pf); }
+  const float frame_energy = __fdiv_rn(lane_tree(pf), (float)cfg.fsc);
 
   // per-channel signals; variant 0/1 = L/R (or mono), 2/3 = mid/side
   const bool joint = cfg.mode == 2;
@@ -138,12 +138,16 @@ __global__ void __launch_bounds__(128) k_prepass(Config cfg, PassBuffers pb) {
 #pragma unroll
     for (int th = 0; th < 3; ++th) {
       float a3[4] = {0.f, 0.f, 0.f, 0.f};
+      float2 lr[6];
+#pragma unroll
       for (int jj = 0; jj < 6; ++jj) {
         int n = gr * 576 + th * 192 + jj * 32 + lane;
-        float v[4];
-        if (ch == 1) { v[0] = pv.at(q0 + n); v[1] = v[2] = v[3] = 0.0f; }
-        else {
-          v[0] = pv.at(q0 + 2 * n); v[1] = pv.at(q0 + 2 * n + 1);
+        lr[jj] = ch == 1 ? make_float2(ld.one(n), 0.0f) : ld.pair(n);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 6; ++jj) {
+        float v[4] = {lr[jj].x, lr[jj].y, 0.0f, 0.0f};
+        if (joint) {
           v[2] = __fmul_rn(__fadd_rn(v[0], v[1]), 0.5f);       // SRC:2148-2150
           v[3] = __fmul_rn(__fsub_rn(v[0], v[1]), 0.5f);       // SRC:2153-2154
           pm = __fmaf_rn(v[2], v[2], pm); ps = __fmaf_rn(v[3], v[3], ps);
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(128) k_prepass(Config cfg, PassBuffers pb) {
   }
   if (lane < 2 * ch) {
     int gr = lane / ch, c = lane % ch, k = c + (ms ? 2 : 0);
-    float e[3]; float g = 0.0f;
+    float e[3] = {0.f, 0.f, 0.f}; float g = 0.0f;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
@@ -181,6 +185,26 @@ __global__ void __launch_bounds__(128) k_prepass(Config cfg, PassBuffers pb) {
     pb.gc_energy[(size_t)s * (10 + pb.GC) + 10 + gci] = g;
     pb.gc_bt[(size_t)s * pb.GC + gci] = (uint16_t)(bt | sbg[0] << 2 | sbg[1] << 5 | sbg[2] << 8);
   }
+}
+
+__global__ void __launch_bounds__(128) k_prepass(Config cfg, PassBuffers pb) {
+  const int s = blockIdx.x, lane = threadIdx.x & 31;
+  const int f = blockIdx.y * 4 + (threadIdx.x >> 5);
+  const StreamPlan &plan = pb.plan[s];
+  if (f >= (int)plan.n_frames) return;
+  const PcmView pv = pcm_view(cfg, pb, s);
+  const int64_t q0 = (int64_t)(1 + f) * cfg.fsc;
+  if (f == 0 && lane < 10) {  // carried VBR history, right aligned in front of this pass's gc energies
+    const StreamState &stt = pb.state[s];
+    int n = stt.vbr_n;
+    pb.gc_energy[(size_t)s * (10 + pb.GC) + lane] = lane >= 10 - n ? stt.vbr_hist[lane - (10 - n)] : 0.0f;
+  }
+  const int64_t rel = q0 - (int64_t)pv.head_n;
+  if (rel >= 0 && rel + cfg.fsc <= (int64_t)pv.cur_n) {
+    const float *p = pv.cur + rel;
+    if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) { FrameLoad<2> ld{pv, q0, p}; prepass_frame<2>(cfg, pb, ld, s, f, lane); }
+    else { FrameLoad<1> ld{pv, q0, p}; prepass_frame<1>(cfg, pb, ld, s, f, lane); }
+  } else { FrameLoad<0> ld{pv, q0, nullptr}; prepass_frame<0>(cfg, pb, ld, s, f, lane); }
 }
 
 // VBRState.chooseBitrate SRC:1177-1189 + MP3Tables.bitrateIndex SRC:2509-2523: one thread per frame.
@@ -448,107 +472,178 @@ __device__ __forceinline__ void region_counts(const Config &cfg, int big_values,
   r0 = min(region0, 15); r1 = min(region1, 7);
 }
 
-__global__ void k_scan(Config cfg, PassBuffers pb) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= cfg.n_streams) return;
+// One warp per stream.  Frames are taken 32 at a time: (1) the warp stages the chunk's curve tables in shared memory
+// with coalesced loads, (2) lane 0 walks the 32 frames serially out of shared memory — this is the only truly
+// sequential work of the whole encoder —, (3) lane l writes the records of frame l.
+struct ScanFrame { int padding, mdb, res_bits, bpg, huff, is_final; uint32_t w_off, e_src, e_take, e_out; };
+
+__global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
+  __shared__ __align__(16) uint16_t sh_bits[32 * 4 * kMaxEntries];
+  __shared__ uint32_t sh_meta[32 * 4];
+  __shared__ uint8_t sh_bri[32];
+  __shared__ uint8_t sh_sel[32 * 4][4];       // chosen entry, gain_out, gain_used, iterations
+  __shared__ ScanFrame sh_fr[32];
+  __shared__ int sh_state[8];
+  const int s = blockIdx.x, lane = threadIdx.x;
   const StreamPlan plan = pb.plan[s];
   StreamState &st = pb.state[s];
   const int ch = cfg.channels, nf = (int)plan.n_frames, ngc = 2 * ch;
-  if (plan.flags & 4) st.out_pos = 0;
   FrameRec *rec = pb.rec + (size_t)s * (pb.Fc + 1);
+  FrameEmit *emit = pb.emit + (size_t)s * (pb.Fc + 1);
   uint16_t *emit_size = pb.emit_size + (size_t)s * (pb.Fc + 1);
-  uint32_t n_emit = 0;
+  // rec[0] = bufferedFrame of the previous pass
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&st.buffered);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&rec[0]);
+    for (int i = lane; i < (int)(sizeof(FrameRec) / 4); i += 32) dst[i] = src[i];
+  }
+  // serial state lives in lane 0's registers
+  uint32_t out_pos = (plan.flags & 4) ? 0u : st.out_pos;
   const uint32_t B0 = (uint32_t)st.backlog;
-  uint32_t R = 0, W = B0;
-  rec[0] = st.buffered;
-  rec[0].emit = 0;
-  int prev = rec[0].valid ? 0 : -1;
-  for (int f = 0; f < nf; ++f) {
-    const bool is_final = (plan.flags & 1) && f == nf - 1;
-    const int bri = pb.frame_br[(size_t)s * pb.Fc + f];
-    int padding = 0;                                             // shouldPad SRC:456-463
-    st.pad_rem += cfg.frame_rem[bri];
-    if (st.pad_rem >= cfg.sample_rate) { st.pad_rem -= cfg.sample_rate; padding = 1; }
-    const int frame_size = cfg.frame_base[bri] + padding;
-    const int mds = frame_size - cfg.header_bytes;               // SRC:497
-    const int mdb = is_final ? 0 : (int)min(W - R, 511u);        // SRC:499, 2099-2101
-    const int res_bits = is_final ? 0 : st.avail_bytes * 8;      // SRC:500
-    const int bpg = (mds * 8 + (res_bits * 9) / 10) / (2 * ch);  // SRC:647-650
-    FrameRec fr;
-    fr.valid = 1; fr.br_index = (uint8_t)bri; fr.padding = (uint8_t)padding;
-    fr.ms = pb.ms[(size_t)s * (pb.Fc + 1) + 1 + f];
-    fr.mdb = (uint16_t)mdb; fr.slot = (uint16_t)mds; fr.is_final = is_final; fr.emit = 0; fr.pad0[0] = fr.pad0[1] = 0;
-    fr.reservoir_bits = res_bits; fr.frame_energy = pb.frame_energy[(size_t)s * pb.Fc + f];
-    fr.src_off = fr.take = fr.out_off = 0;
-    int total = 0;
-    for (int j = 0; j < ngc; ++j) {
-      const int gci = f * ngc + j;
-      const size_t gslot = (size_t)s * pb.GC + gci;
-      const uint32_t meta = pb.gc_meta[gslot];
-      const int g0 = meta & 255, n = (meta >> 8) & 255, restart = (meta >> 16) & 1, pre = (meta >> 17) & 1;
-      const uint16_t *cb = pb.gc_bits + gslot * kMaxEntries, *cv = pb.gc_bv + gslot * kMaxEntries;
-      int gain = g0, chosen = n - 1, gain_out = g0, gain_used = g0, iters = n;
-      for (int e = 0; e < n; ++e) {                               // quantizeToFitBudget SRC:745-776
-        gain_used = gain;
-        if (e == 0 && restart) { gain = max(gain - 40, 0); continue; }
-        if ((int)cb[e] <= bpg) { chosen = e; gain_out = gain; iters = e + 1; break; }
-        int next = min(gain + 4, 255);
-        if (next >= 255 || e == kMaxEntries - 1) { chosen = e; gain_out = next; iters = e + 1; break; }
-        if (e == n - 1) { chosen = e; gain_out = next; st.error |= 1; break; }   // curve ended early: engine bug
-        gain = next;
+  uint32_t R = 0, W = B0, n_emit = 0, frame_count = st.frame_count, total_bytes = st.total_bytes;
+  int avail = st.avail_bytes, pad_rem = st.pad_rem, err = 0;
+  int prev_slot = st.buffered.valid ? (int)st.buffered.slot : -1;     // slot of the buffered frame, -1 = none
+  const int first_emit = prev_slot >= 0 ? 0 : 1;                      // rec index of the first frame this pass can emit
+  __syncwarp();
+  for (int base = 0; base < nf; base += 32) {
+    const int cnt = min(32, nf - base);
+    {  // (1) stage
+      const size_t g0s = (size_t)s * pb.GC + (size_t)base * ngc;
+      const uint4 *src = reinterpret_cast<const uint4 *>(pb.gc_bits + g0s * kMaxEntries);   // 40-byte rows, 16-byte aligned chunk start
+      uint4 *dst = reinterpret_cast<uint4 *>(sh_bits);
+      const int n16 = cnt * ngc * kMaxEntries * 2 / 16;
+      for (int i = lane; i < n16; i += 32) dst[i] = src[i];
+      for (int i = n16 * 8 + lane; i < cnt * ngc * kMaxEntries; i += 32) sh_bits[i] = pb.gc_bits[g0s * kMaxEntries + i];
+      for (int i = lane; i < cnt * ngc; i += 32) sh_meta[i] = pb.gc_meta[g0s + i];
+      if (lane < cnt) sh_bri[lane] = pb.frame_br[(size_t)s * pb.Fc + base + lane];
+    }
+    __syncwarp();
+    if (lane == 0) {  // (2) the serial chain, SRC:475-568
+      for (int l = 0; l < cnt; ++l) {
+        const int f = base + l;
+        const bool is_final = (plan.flags & 1) && f == nf - 1;
+        const int bri = sh_bri[l];
+        int padding = 0;                                             // shouldPad SRC:456-463
+        pad_rem += cfg.frame_rem[bri];
+        if (pad_rem >= cfg.sample_rate) { pad_rem -= cfg.sample_rate; padding = 1; }
+        const int mds = cfg.frame_base[bri] + padding - cfg.header_bytes;   // SRC:497
+        const int mdb = is_final ? 0 : (int)min(W - R, 511u);        // SRC:499, 2099-2101
+        const int res_bits = is_final ? 0 : avail * 8;               // SRC:500
+        const int bpg = (mds * 8 + (res_bits * 9) / 10) / (2 * ch);  // SRC:647-650
+        int total = 0;
+        for (int j = 0; j < ngc; ++j) {
+          const uint32_t meta = sh_meta[l * ngc + j];
+          const int g0 = meta & 255, n = (meta >> 8) & 255, restart = (meta >> 16) & 1;
+          const uint16_t *cb = sh_bits + (l * ngc + j) * kMaxEntries;
+          int gain = g0, chosen = n - 1, gain_out = g0, gain_used = g0, iters = n;
+          for (int e = 0; e < n; ++e) {                              // quantizeToFitBudget SRC:745-776
+            gain_used = gain;
+            if (e == 0 && restart) { gain = max(gain - 40, 0); continue; }
+            if ((int)cb[e] <= bpg) { chosen = e; gain_out = gain; iters = e + 1; break; }
+            int next = min(gain + 4, 255);
+            if (next >= 255 || e == kMaxEntries - 1) { chosen = e; gain_out = next; iters = e + 1; break; }
+            if (e == n - 1) { chosen = e; gain_out = next; err |= 1; break; }   // curve ended early: engine bug
+            gain = next;
+          }
+          sh_sel[l * ngc + j][0] = (uint8_t)chosen; sh_sel[l * ngc + j][1] = (uint8_t)gain_out;
+          sh_sel[l * ngc + j][2] = (uint8_t)gain_used; sh_sel[l * ngc + j][3] = (uint8_t)iters;
+          total += cb[chosen];
+        }
+        const int huff = (total + 7) >> 3;                           // padToByte SRC:729
+        ScanFrame &o = sh_fr[l];
+        o.padding = padding; o.mdb = mdb; o.res_bits = res_bits; o.bpg = bpg; o.huff = huff; o.is_final = is_final;
+        o.w_off = W;
+        W += (uint32_t)huff;                                         // appendHuffmanData SRC:511
+        if (W > pb.md_stride) { err |= 2; W = (uint32_t)pb.md_stride; }
+        o.e_take = 0xFFFFFFFFu;
+        if (prev_slot >= 0) {                                        // emit the buffered frame, SRC:548-556 + fillSlot 2110-2121
+          uint32_t take = min((uint32_t)prev_slot, W - R);
+          o.e_src = R; o.e_take = take; o.e_out = out_pos;
+          R += take;
+          uint32_t sz = (uint32_t)cfg.header_bytes + (uint32_t)prev_slot;
+          out_pos += sz; frame_count += 1; total_bytes += sz; n_emit += 1;
+        }
+        prev_slot = mds;
+        int a = avail + mds - huff;                                  // updateReservoir SRC:565, 2125-2128
+        avail = a < 0 ? 0 : a > 511 ? 511 : a;
       }
-      if (n == 1 && restart) { chosen = 0; gain_out = gain; gain_used = g0; }    // unreachable: restart implies n >= 2
-      const int bits = cb[chosen], bv = min((int)cv[chosen], 288);
-      GcSide &g = fr.gc[j];
-      g.part23 = (uint16_t)bits; g.big_values = (uint16_t)bv; g.global_gain = (uint8_t)gain_out; g.gain_used = (uint8_t)gain_used;
-      const uint16_t btw = pb.gc_bt[gslot];
-      g.block_type = btw & 3; g.sbg[0] = (btw >> 2) & 7; g.sbg[1] = (btw >> 5) & 7; g.sbg[2] = (btw >> 8) & 7;
-      int r0, r1; region_counts(cfg, bv, r0, r1);
-      g.region0 = (uint8_t)r0; g.region1 = (uint8_t)r1; g.preflag = (uint8_t)pre; g.g0 = (uint8_t)g0;
-      g.iterations = (uint8_t)iters; g.pad = 0; g.max_bits = (uint16_t)bpg;
-      g.energy = pb.gc_energy[(size_t)s * (10 + pb.GC) + 10 + gci];
-      pb.gc_sel[gslot] = (uint32_t)gain_used | (uint32_t)bv << 8;
-      pb.gc_bitoff[gslot] = (uint32_t)total;
-      total += bits;
     }
-    for (int j = ngc; j < 4; ++j) fr.gc[j] = GcSide{};
-    const int huff = (total + 7) >> 3;                            // padToByte SRC:729
-    fr.huff_bytes = huff;
-    pb.fr_md[((size_t)s * pb.Fc + f) * 2] = W;
-    pb.fr_md[((size_t)s * pb.Fc + f) * 2 + 1] = (uint32_t)huff;
-    W += (uint32_t)huff;                                          // appendHuffmanData SRC:511
-    if (W > pb.md_stride) { st.error |= 2; W = (uint32_t)pb.md_stride; }
-    rec[1 + f] = fr;
-    if (prev >= 0) {                                              // emit the buffered frame, SRC:548-556 + fillSlot 2110-2121
-      FrameRec &p = rec[prev];
-      uint32_t take = min((uint32_t)p.slot, W - R);
-      p.emit = 1; p.src_off = R; p.take = take; p.out_off = st.out_pos;
+    __syncwarp();
+    if (lane < cnt) {  // (3) records of frame f = base + lane
+      const int f = base + lane;
+      const ScanFrame o = sh_fr[lane];
+      const int bri = sh_bri[lane];
+      FrameRec fr;
+      fr.valid = 1; fr.br_index = (uint8_t)bri; fr.padding = (uint8_t)o.padding;
+      fr.ms = pb.ms[(size_t)s * (pb.Fc + 1) + 1 + f];
+      const int mds = cfg.frame_base[bri] + o.padding - cfg.header_bytes;
+      fr.mdb = (uint16_t)o.mdb; fr.slot = (uint16_t)mds; fr.is_final = (uint8_t)o.is_final; fr.pad0[0] = fr.pad0[1] = fr.pad0[2] = 0;
+      fr.reservoir_bits = o.res_bits; fr.huff_bytes = o.huff; fr.frame_energy = pb.frame_energy[(size_t)s * pb.Fc + f];
+      int total = 0;
+      for (int j = 0; j < ngc; ++j) {
+        const int gci = f * ngc + j;
+        const size_t gslot = (size_t)s * pb.GC + gci;
+        const uint32_t meta = sh_meta[lane * ngc + j];
+        const int chosen = sh_sel[lane * ngc + j][0];
+        const int bits = sh_bits[(lane * ngc + j) * kMaxEntries + chosen];
+        const int bv = min((int)pb.gc_bv[gslot * kMaxEntries + chosen], 288);
+        GcSide &g = fr.gc[j];
+        g.part23 = (uint16_t)bits; g.big_values = (uint16_t)bv;
+        g.global_gain = sh_sel[lane * ngc + j][1]; g.gain_used = sh_sel[lane * ngc + j][2];
+        const uint16_t btw = pb.gc_bt[gslot];
+        g.block_type = btw & 3; g.sbg[0] = (btw >> 2) & 7; g.sbg[1] = (btw >> 5) & 7; g.sbg[2] = (btw >> 8) & 7;
+        int r0, r1; region_counts(cfg, bv, r0, r1);
+        g.region0 = (uint8_t)r0; g.region1 = (uint8_t)r1; g.preflag = (uint8_t)((meta >> 17) & 1); g.g0 = (uint8_t)(meta & 255);
+        g.iterations = sh_sel[lane * ngc + j][3]; g.pad = 0; g.max_bits = (uint16_t)o.bpg;
+        g.energy = pb.gc_energy[(size_t)s * (10 + pb.GC) + 10 + gci];
+        pb.gc_sel[gslot] = (uint32_t)g.gain_used | (uint32_t)bv << 8;
+        pb.gc_bitoff[gslot] = (uint32_t)total;
+        total += bits;
+      }
+      for (int j = ngc; j < 4; ++j) fr.gc[j] = GcSide{};
+      pb.fr_md[((size_t)s * pb.Fc + f) * 2] = o.w_off;
+      pb.fr_md[((size_t)s * pb.Fc + f) * 2 + 1] = (uint32_t)o.huff;
+      rec[1 + f] = fr;
+      FrameEmit em;                                                  // emission of rec[f], decided while frame f was encoded
+      em.emit = o.e_take != 0xFFFFFFFFu; em.src_off = em.emit ? o.e_src : 0; em.take = em.emit ? o.e_take : 0; em.out_off = em.emit ? o.e_out : 0;
+      emit[f] = em;
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+  // tail: flush emission, state write-back
+  if (lane == 0) {
+    FrameEmit em; em.emit = 0; em.src_off = em.take = em.out_off = 0;
+    if ((plan.flags & 2) && prev_slot >= 0) {                        // flush SRC:335-347
+      uint32_t take = min((uint32_t)prev_slot, W - R);
+      em.emit = 1; em.src_off = R; em.take = take; em.out_off = out_pos;
       R += take;
-      uint32_t sz = (uint32_t)cfg.header_bytes + p.slot;
-      st.out_pos += sz; st.frame_count += 1; st.total_bytes += sz;
-      emit_size[n_emit++] = (uint16_t)sz;
+      uint32_t sz = (uint32_t)cfg.header_bytes + (uint32_t)prev_slot;
+      out_pos += sz; frame_count += 1; total_bytes += sz; n_emit += 1;
+      prev_slot = -1;
     }
-    prev = 1 + f;
-    int a = st.avail_bytes + mds - huff;                          // updateReservoir SRC:565, 2125-2128
-    st.avail_bytes = a < 0 ? 0 : a > 511 ? 511 : a;
+    emit[nf] = em;
+    if (out_pos > pb.out_stride) err |= 4;
+    if (W - R > (uint32_t)kMdCarryCap) err |= 8;
+    st.out_pos = out_pos; st.frame_count = frame_count; st.total_bytes = total_bytes;
+    st.avail_bytes = avail; st.pad_rem = pad_rem; st.error |= err;
+    st.backlog = (int32_t)min(W - R, (uint32_t)kMdCarryCap);
+    st.frames_total += (uint32_t)nf;
+    pb.md_tail[(size_t)s * 4] = R; pb.md_tail[(size_t)s * 4 + 1] = (uint32_t)st.backlog; pb.md_tail[(size_t)s * 4 + 2] = B0;
+    pb.emit_n[s] = n_emit;
+    sh_state[0] = prev_slot;
   }
-  if ((plan.flags & 2) && prev >= 0) {                            // flush SRC:335-347
-    FrameRec &p = rec[prev];
-    uint32_t take = min((uint32_t)p.slot, W - R);
-    p.emit = 1; p.src_off = R; p.take = take; p.out_off = st.out_pos;
-    R += take;
-    uint32_t sz = (uint32_t)cfg.header_bytes + p.slot;
-    st.out_pos += sz; st.frame_count += 1; st.total_bytes += sz;
-    emit_size[n_emit++] = (uint16_t)sz;
-    prev = -1;
+  __syncwarp();
+  // sizes of the emitted frames, in order: rec[first_emit ...]
+  const uint32_t ne = pb.emit_n[s];
+  for (uint32_t k = lane; k < ne; k += 32) emit_size[k] = (uint16_t)(cfg.header_bytes + rec[first_emit + k].slot);
+  // bufferedFrame for the next pass = last frame of this one (unless flushed)
+  {
+    const bool keep = sh_state[0] >= 0;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&rec[nf]);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&st.buffered);
+    for (int i = lane; i < (int)(sizeof(FrameRec) / 4); i += 32) dst[i] = keep ? src[i] : 0u;
   }
-  if (prev >= 0) { st.buffered = rec[prev]; st.buffered.emit = 0; } else st.buffered.valid = 0;
-  if (st.out_pos > pb.out_stride) st.error |= 4;
-  if (W - R > (uint32_t)kMdCarryCap) st.error |= 8;
-  st.backlog = (int32_t)min(W - R, (uint32_t)kMdCarryCap);
-  st.frames_total += (uint32_t)nf;
-  pb.md_tail[(size_t)s * 4] = R; pb.md_tail[(size_t)s * 4 + 1] = (uint32_t)st.backlog; pb.md_tail[(size_t)s * 4 + 2] = B0;
-  pb.emit_n[s] = n_emit;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -634,7 +729,8 @@ __global__ void __launch_bounds__(128) k_frames(Config cfg, PassBuffers pb) {
   const int r = blockIdx.y * 4 + warp;
   if (r > (int)pb.plan[s].n_frames) return;
   const FrameRec &fr = pb.rec[(size_t)s * (pb.Fc + 1) + r];
-  if (!fr.valid || !fr.emit) return;
+  const FrameEmit em = pb.emit[(size_t)s * (pb.Fc + 1) + r];
+  if (!fr.valid || !em.emit) return;
   const int ch = cfg.channels;
   if (lane == 0) {
     BitW w{hdr[warp], 0, 0, 0};
@@ -661,15 +757,15 @@ __global__ void __launch_bounds__(128) k_frames(Config cfg, PassBuffers pb) {
     while (w.n < cfg.header_bytes) w.p[w.n++] = 0;
   }
   __syncwarp();
-  uint8_t *dst = pb.out + (size_t)s * pb.out_stride + fr.out_off;
-  if ((size_t)fr.out_off + cfg.header_bytes + fr.slot > pb.out_stride) return;
+  uint8_t *dst = pb.out + (size_t)s * pb.out_stride + em.out_off;
+  if ((size_t)em.out_off + cfg.header_bytes + fr.slot > pb.out_stride) return;
   for (int i = lane; i < cfg.header_bytes; i += 32) dst[i] = hdr[warp][i];
   dst += cfg.header_bytes;
   const uint32_t B0 = pb.md_tail[(size_t)s * 4 + 2];
   const uint8_t *carry = pb.md_carry + (size_t)s * kMdCarryCap, *md = pb.md + (size_t)s * pb.md_stride;
   for (uint32_t i = lane; i < fr.slot; i += 32) {
     uint8_t b = 0;
-    if (i < fr.take) { uint32_t o = fr.src_off + i; b = o < B0 ? carry[o] : md[o]; }
+    if (i < em.take) { uint32_t o = em.src_off + i; b = o < B0 ? carry[o] : md[o]; }
     dst[i] = b;
   }
 }
@@ -807,7 +903,7 @@ int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   return check(1);
 }
 int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
-  k_scan<<<(cfg.n_streams + 63) / 64, 64, 0, st>>>(cfg, pb);
+  k_scan<<<cfg.n_streams, 32, 0, st>>>(cfg, pb);
   return check(1);
 }
 int launch_pack(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {

@@ -48,11 +48,13 @@ struct GcSide {              // side-info fields of one gc (GranuleInfo, SRC:207
 struct FrameRec {            // everything needed to emit a frame later (one-frame delay, SRC:546-562)
   uint8_t valid, br_index, padding, ms;
   uint16_t mdb, slot;        // main_data_begin as written; slot = main-data bytes of the frame
-  uint8_t is_final, emit, pad0[2];
+  uint8_t is_final, pad0[3];
   int32_t reservoir_bits, huff_bytes;
   float frame_energy;
-  uint32_t src_off, take, out_off;   // emission: copy `take` bytes from md + src_off, zero-fill up to slot
   GcSide gc[4];
+};
+struct FrameEmit {           // emission of a frame slot in this pass: copy `take` bytes from md + src_off, zero-fill up to slot
+  uint32_t emit, src_off, take, out_off;
 };
 
 struct StreamState {         // persistent per stream
@@ -87,6 +89,7 @@ struct PassBuffers {         // device arrays for one pass; Fc = frame capacity 
   uint32_t *gc_sel;          // [S][GC] gain_used | big_values<<8
   uint32_t *fr_md;           // [S][Fc][2] byte offset of the frame's main data in md, huff bytes
   FrameRec *rec;             // [S][Fc+1]
+  FrameEmit *emit;           // [S][Fc+1]
   uint8_t *md;               // [S][md_stride] main-data byte stream of the pass (starts with the carried backlog)
   size_t md_stride;
   uint32_t *md_tail;         // [S][2] offset / length of the unconsumed tail after the scan
