@@ -107,6 +107,7 @@ int fill_config(const mp3b_options &o, int n_streams, Config &c) {
   c.header_bytes = 4 + (c.crc ? 2 : 0) + c.side_bytes;
   if (o.mode == 0) { c.mode_bits = 3; c.mode_ext = 0; } else if (o.mode == 2) { c.mode_bits = 1; c.mode_ext = 2; } else { c.mode_bits = 0; c.mode_ext = 0; }
   c.cbr_index = bitrate_index(o.bitrate_kbps, o.sample_rate);
+  c.f_one = 1.0f; c.f_neg0 = -0.0f;
   for (int i = 0; i < 16; ++i) {
     long long num = 144LL * bitrate_value(i) * 1000;             // SRC:490-495
     c.frame_base[i] = (int)(num / o.sample_rate); c.frame_rem[i] = (int)(num % o.sample_rate);
@@ -137,9 +138,9 @@ void free_batch(mp3b_batch *b) {
   cudaSetDevice(b->device);
   if (b->st) cudaStreamSynchronize(b->st);
   PassBuffers &p = b->pb;
-  void *dev[] = {p.plan, p.state, b->d_head[0], b->d_head[1], p.ms, p.frame_energy, p.gc_energy, p.gc_bt, p.frame_br, p.smag,
+  void *dev[] = {p.plan, p.state, b->d_head[0], b->d_head[1], p.ms, p.frame_energy, p.gc_energy, p.gc_bt, p.frame_br, p.spec, p.smag,
                  p.gc_meta, p.gc_bits, p.gc_bv, p.gc_bitoff, p.gc_sel, p.fr_md, p.rec, p.emit, p.md, p.md_tail, p.md_carry, p.out,
-                 p.emit_size, p.emit_n, p.tr_spectrum, p.tr_ix, p.tr_thr, b->d_stage, b->d_offsets, b->d_compact};
+                 p.emit_size, p.emit_n, p.tr_ix, p.tr_thr, b->d_stage, b->d_offsets, b->d_compact};
   for (void *q : dev) if (q) cudaFree(q);
   void *host[] = {b->h_plan, b->h_state, b->h_emit_size, b->h_emit_n, b->h_offsets, b->h_out};
   for (void *q : host) if (q) cudaFreeHost(q);
@@ -183,7 +184,7 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   A(dalloc(p.plan, S)); A(dalloc(p.state, S));
   A(dalloc(b->d_head[0], S * 2 * cfg.fsc)); A(dalloc(b->d_head[1], S * 2 * cfg.fsc));
   A(dalloc(p.ms, S * (Fc + 1))); A(dalloc(p.frame_energy, S * Fc)); A(dalloc(p.gc_energy, S * (10 + GC)));
-  A(dalloc(p.gc_bt, S * GC)); A(dalloc(p.frame_br, S * Fc)); A(dalloc(p.smag, S * GC * 576, false));
+  A(dalloc(p.gc_bt, S * GC)); A(dalloc(p.frame_br, S * Fc)); A(dalloc(p.spec, S * GC * 576, false)); A(dalloc(p.smag, S * GC * 576, false));
   A(dalloc(p.gc_meta, S * GC)); A(dalloc(p.gc_bits, S * GC * kMaxEntries)); A(dalloc(p.gc_bv, S * GC * kMaxEntries));
   A(dalloc(p.gc_bitoff, S * GC)); A(dalloc(p.gc_sel, S * GC)); A(dalloc(p.fr_md, S * Fc * 2)); A(dalloc(p.rec, S * (Fc + 1))); A(dalloc(p.emit, S * (Fc + 1)));
   p.md_stride = round_up<size_t>(kMdCarryCap + (size_t)Fc * 2 * cfg.channels * 540, 16);
@@ -222,9 +223,8 @@ int ensure_out(mp3b_batch *b, size_t stride) {
 int ensure_trace(mp3b_batch *b) {
   PassBuffers &p = b->pb;
   const size_t n = (size_t)b->S * b->GC * 576;
-  if ((b->trace & 1) && !p.tr_spectrum) CU(dalloc(p.tr_spectrum, n));
   if ((b->trace & 2) && !p.tr_ix) CU(dalloc(p.tr_ix, n));
-  if ((b->trace & 4) && !p.tr_thr) { CU(dalloc(p.tr_thr, n)); if (!p.tr_spectrum) CU(dalloc(p.tr_spectrum, n)); }
+  if ((b->trace & 4) && !p.tr_thr) CU(dalloc(p.tr_thr, n));
   return MP3B_OK;
 }
 
@@ -312,6 +312,8 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
     CU(cudaEventRecord(b->ev[1], st));
     // ---- device pipeline
     PassBuffers pb = b->pb;
+    pb.max_frames = 0;
+    for (int s = 0; s < S; ++s) pb.max_frames = std::max<int>(pb.max_frames, (int)b->h_plan[s].n_frames);
     pb.head_in = b->d_head[b->head_sel]; pb.head_out = b->d_head[b->head_sel ^ 1];
 #define LAUNCH(expr)                                                                                        \
   do {                                                                                                      \
@@ -377,7 +379,7 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
         }
         const size_t cnt = (size_t)nf * ngc * 576, off = (size_t)s * b->GC * 576;
         if (cnt) {
-          if (b->trace & 1) { size_t o = b->tr_spec[s].size(); b->tr_spec[s].resize(o + cnt); CU(cudaMemcpy(b->tr_spec[s].data() + o, pb.tr_spectrum + off, cnt * 4, cudaMemcpyDeviceToHost)); }
+          if (b->trace & 1) { size_t o = b->tr_spec[s].size(); b->tr_spec[s].resize(o + cnt); CU(cudaMemcpy(b->tr_spec[s].data() + o, pb.spec + off, cnt * 4, cudaMemcpyDeviceToHost)); }
           if (b->trace & 2) { size_t o = b->tr_ix[s].size(); b->tr_ix[s].resize(o + cnt); CU(cudaMemcpy(b->tr_ix[s].data() + o, pb.tr_ix + off, cnt * 4, cudaMemcpyDeviceToHost)); }
           if (b->trace & 4) { size_t o = b->tr_thr[s].size(); b->tr_thr[s].resize(o + cnt); CU(cudaMemcpy(b->tr_thr[s].data() + o, pb.tr_thr + off, cnt * 4, cudaMemcpyDeviceToHost)); }
         }

@@ -245,8 +245,10 @@ __global__ void k_bitrate(Config cfg, PassBuffers pb) {
 constexpr int kSteps = 18 * (kRunGranules + 1);   // 288
 constexpr int kLook = 15;                         // 480 samples of look-back = 15 rows of 32
 constexpr int kRows = kSteps + kLook;             // 303
-constexpr int kRowPad = 33;
-constexpr int kSpecSmemFloats = kRows * kRowPad + kSteps * kRowPad;
+constexpr int kPcmPad = 34;                       // PCM tile row stride: even, so that two adjacent columns are one aligned LDS.64
+constexpr int kRowPad = 33;                       // subband tile row stride
+constexpr int kPcmFloats = (kRows * kPcmPad + 3) & ~3;   // keeps everything behind it 16-byte aligned
+constexpr int kSpecSmemFloats = 64 * 32 + 32 * 8 * 2 + kPcmFloats + kSteps * kRowPad;
 constexpr int kSpecSmemBytes = kSpecSmemFloats * 4;
 
 __device__ __forceinline__ int gain_from_peak(float peak) {      // computeGlobalGain SRC:989-1006
@@ -264,9 +266,11 @@ __device__ __forceinline__ int gain_from_peak(float peak) {      // computeGloba
 }
 
 __global__ void __launch_bounds__(kSteps, 2) k_spectrum(Config cfg, PassBuffers pb) {
-  extern __shared__ float sm[];
-  float *P = sm;                           // [kRows][33] PCM tile, later X[15][576]
-  float *Sb = sm + kRows * kRowPad;        // [kSteps][33] subband samples [step][sb]
+  extern __shared__ __align__(16) float sm[];
+  float *sM = sm;                                  // [64][32] analysis matrix, transposed: M[k][n] at n*32 + k
+  float2 *sW = reinterpret_cast<float2 *>(sM + 64 * 32);   // [32][8] window pairs (C[2p+1+64i], C[2p+64i])
+  float *P = sM + 64 * 32 + 32 * 8 * 2;            // [kRows][34] PCM tile, later X[15][576]
+  float *Sb = P + kPcmFloats;                      // [kSteps][33] subband samples [step][sb]
   const int s = blockIdx.x, c = blockIdx.y, run = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const StreamPlan &plan = pb.plan[s];
@@ -279,47 +283,93 @@ __global__ void __launch_bounds__(kSteps, 2) k_spectrum(Config cfg, PassBuffers 
   const uint8_t *msrow = pb.ms + (size_t)s * (pb.Fc + 1);
   const uint32_t ms_prev = pb.state[s].ms_prev;
 
-  // ---- stage PCM: sample n (per channel, relative to frame 0 of the pass) = n0 + 32*row + col
+  // ---- coefficient tables -> shared memory (tiny loop body in phase A instead of 56 KB of immediates)
+  {
+    const float4 *srcm = reinterpret_cast<const float4 *>(tab::kAnalysisT), *srcw = reinterpret_cast<const float4 *>(tab::kWindowPairs);
+    float4 *dstm = reinterpret_cast<float4 *>(sM), *dstw = reinterpret_cast<float4 *>(sW);
+    for (int e = tid; e < 64 * 32 / 4; e += kSteps) dstm[e] = __ldg(srcm + e);
+    for (int e = tid; e < 32 * 8 * 2 / 4; e += kSteps) dstw[e] = __ldg(srcw + e);
+  }
+
+  // ---- stage PCM: sample n (per channel, relative to frame 0 of the pass) = n0 + 32*row + col; warp = row, lane = col.
+  // 1152 = 36 * 32 and n0 is a multiple of 32, so a row never straddles a frame: one stereo decision per row.
   const int n0 = 576 * (g_begin - 1) - 480;
   const int rows_needed = kLook + 18 * (g_cnt + 1);
-  for (int e = tid; e < rows_needed * 32; e += kSteps) {
-    int n = n0 + e;
-    int64_t q = (int64_t)(n + 1152) * ch;
-    float v;
-    if (ch == 1) v = pv.at(q);
-    else {
-      int fr = n >= 0 ? n / 1152 : -1;
-      bool ms = cfg.mode == 2 && (fr < 0 ? ms_prev != 0 : msrow[1 + fr] != 0);
-      if (!ms) v = pv.at(q + c);
+  const bool joint = cfg.mode == 2;
+  const int64_t rel0 = (int64_t)(n0 + 1152) * ch - (int64_t)pv.head_n;      // offset of the tile inside `cur`
+  const bool tile_in_cur = rel0 >= 0 && rel0 + (int64_t)rows_needed * 32 * ch <= (int64_t)pv.cur_n &&
+                           (ch == 1 || (reinterpret_cast<uintptr_t>(pv.cur + rel0) & 7) == 0);
+  if (tile_in_cur && !joint) {
+    // common case: the whole tile is contiguous in this pass's PCM and needs no mid/side transform: every element is
+    // one 4-byte cp.async (LDGSTS) straight into the padded tile — all rows of a warp are in flight at once, no
+    // registers, one exposed memory latency per CTA.
+    const float *src = pv.cur + rel0 + (ch == 1 ? lane : 2 * lane + c);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(P + lane);
+    for (int r = warp; r < rows_needed; r += 9)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + r * kPcmPad * 4), "l"(src + (size_t)r * 32 * ch));
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
+    // general case: rows may come from the carried head, straddle head / cur, be zero padding, or need mid/side
+    for (int r = warp; r < rows_needed; r += 9) {
+      const int nrow = n0 + 32 * r;
+      const int64_t q = (int64_t)(nrow + 1152) * ch;
+      float v;
+      if (ch == 1) v = pv.at(q + lane);
       else {
-        float l = pv.at(q), r = pv.at(q + 1);
-        v = c == 0 ? __fmul_rn(__fadd_rn(l, r), 0.5f) : __fmul_rn(__fsub_rn(l, r), 0.5f);
+        const float l = pv.at(q + 2 * lane), rr = pv.at(q + 2 * lane + 1);
+        const int fr = nrow >= 0 ? nrow / 1152 : -1;
+        const bool ms = joint && (fr < 0 ? ms_prev != 0 : msrow[1 + fr] != 0);
+        if (!ms) v = c == 0 ? l : rr;
+        else v = c == 0 ? __fmul_rn(__fadd_rn(l, rr), 0.5f) : __fmul_rn(__fsub_rn(l, rr), 0.5f);   // SRC:2148-2154
       }
+      P[r * kPcmPad + lane] = v;
     }
-    P[(e >> 5) * kRowPad + (e & 31)] = v;
   }
   __syncthreads();
 
-  // ---- phase A: filterbank step `tid`
+  // ---- phase A: filterbank step `tid` (SRC:1367-1411).  Packed FP32x2 math (FMUL2 / FADD2 / FFMA2, sm_100): two window
+  // taps n = 2p, 2p+1 share every PCM load (adjacent columns), and two subbands share every FMA instruction.  Each lane
+  // of a packed operation is an independent IEEE round-to-nearest operation, so the results are those of the scalar code.
   if (tid < 18 * (g_cnt + 1)) {
-    float acc[32];
+    float2 acc[16];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) acc[k] = 0.0f;
-    const float *row = P + (tid + kLook) * kRowPad;
-#pragma unroll
-    for (int n = 0; n < 64; ++n) {
-      const int col = (31 - n) & 31, rsh = n >= 32 ? 1 : 0;
-      float y = 0.0f;
+    for (int k = 0; k < 16; ++k) acc[k] = make_float2(0.0f, 0.0f);
+    const float *rowp = P + (tid + kLook) * kPcmPad;
+    const float2 neg0 = make_float2(cfg.f_neg0, cfg.f_neg0), one = make_float2(cfg.f_one, cfg.f_one);
+#pragma unroll 2
+    for (int p = 0; p < 32; ++p) {
+      // X[n + 64 i] = pcm[32 s + 31 - n - 64 i]: row s - 2i (- 1 when n >= 32), column (31 - n) & 31.  Lower column <-> n + 1.
+      const float *src = rowp - (p >= 16 ? kPcmPad : 0) + ((30 - 2 * p) & 31);
+      const float2 *w = sW + p * 8;
+      float2 y;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float z = __fmul_rn(row[-(2 * i + rsh) * kRowPad + col], tab::kWindow[n + 64 * i]);   // SRC:1386-1389
-        y = i == 0 ? z : __fadd_rn(y, z);                                                      // SRC:1392-1399
+        const float2 x = *reinterpret_cast<const float2 *>(src - 2 * i * kPcmPad);
+        // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under --fmad=false (and folds fma(x, w, -0) /
+        // fma(y, 1, z) with literal constants back into that), which would skip the rounding of the product.  Spelling
+        // both as FMAs whose constant operand is a run-time value (cfg.f_neg0 = -0.0f, cfg.f_one = 1.0f) keeps the two
+        // roundings: fma(x, w, -0) == RN(x * w) and fma(y, 1, z) == RN(y + z), bit for bit (signs of zero included).
+        const float2 z = __ffma2_rn(x, w[i], neg0);                        // SRC:1386-1389
+        y = i == 0 ? z : __ffma2_rn(y, one, z);                            // SRC:1392-1399
+      }
+      const float2 ya = make_float2(y.y, y.y), yb = make_float2(y.x, y.x);  // n = 2p, then n = 2p + 1 (ascending n)
+      const float4 *m0 = reinterpret_cast<const float4 *>(sM + (2 * p) * 32), *m1 = m0 + 8;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {                                         // SRC:1402-1408
+        const float4 m = m0[q];
+        acc[2 * q] = __ffma2_rn(ya, make_float2(m.x, m.y), acc[2 * q]);
+        acc[2 * q + 1] = __ffma2_rn(ya, make_float2(m.z, m.w), acc[2 * q + 1]);
       }
 #pragma unroll
-      for (int k = 0; k < 32; ++k) acc[k] = __fmaf_rn(y, tab::kAnalysis[k][n], acc[k]);       // SRC:1402-1408
+      for (int q = 0; q < 8; ++q) {
+        const float4 m = m1[q];
+        acc[2 * q] = __ffma2_rn(yb, make_float2(m.x, m.y), acc[2 * q]);
+        acc[2 * q + 1] = __ffma2_rn(yb, make_float2(m.z, m.w), acc[2 * q + 1]);
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 32; ++k) Sb[tid * kRowPad + k] = acc[k];
+    for (int k = 0; k < 16; ++k) { Sb[tid * kRowPad + 2 * k] = acc[k].x; Sb[tid * kRowPad + 2 * k + 1] = acc[k].y; }
   }
   __syncthreads();
 
@@ -382,30 +432,10 @@ __global__ void __launch_bounds__(kSteps, 2) k_spectrum(Config cfg, PassBuffers 
       }
       __syncwarp();
     }
-    // phase C: line i = lane + 32 j
-    float peak = 0.0f, plo = 0.0f, phi = 0.0f;
-    float *smag = pb.smag + gslot * 576;
-    float *trs = pb.tr_spectrum ? pb.tr_spectrum + gslot * 576 : nullptr;
+    // spectrum -> HBM, coalesced (line i = lane + 32 j); |x|^0.75, peak and preflag belong to k_curve
+    float *spec = pb.spec + gslot * 576;
 #pragma unroll
-    for (int j = 0; j < 18; ++j) {
-      int i = lane + 32 * j;
-      float x = X[i];
-      float ax = fabsf(x);
-      peak = fmaxf(peak, ax);
-      // PreEmphasis SRC:2050-2056 [OD1b]: partial index = (i - segment start) mod 32; 432 mod 32 = 16 is an xor
-      // permutation of the lanes, which the butterfly tree is invariant under.
-      if (i < 432) plo = __fmaf_rn(x, x, plo); else phi = __fmaf_rn(x, x, phi);
-      float mag = pow34(fmaxf(ax, 1e-10f));                       // SRC:805-813 [OD3]
-      smag[i] = x < 0.0f ? -mag : mag;
-      if (trs) trs[i] = x;
-    }
-    peak = warp_max(peak);
-    float low = lane_tree(plo), high = lane_tree(phi);
-    if (lane == 0) {
-      int g0 = gain_from_peak(peak);
-      int pre = high > __fmul_rn(low, 1.5f) ? 1 : 0;
-      pb.gc_meta[gslot] = (uint32_t)g0 | (uint32_t)pre << 17;
-    }
+    for (int j = 0; j < 18; ++j) spec[lane + 32 * j] = X[lane + 32 * j];
   }
 }
 
@@ -420,20 +450,49 @@ __device__ __forceinline__ int lo_bits_of(const Config &cfg, int bri) {
 
 __global__ void __launch_bounds__(256) k_curve(Config cfg, PassBuffers pb) {
   __shared__ uint8_t len15[256];
+  __shared__ __align__(8) float smg[8][576];
   len15[threadIdx.x] = c_len15[threadIdx.x];
   __syncthreads();
-  const int s = blockIdx.x, lane = threadIdx.x & 31;
-  const int gci = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gci = blockIdx.y * 8 + warp;
   const int ch = cfg.channels;
   if (gci >= (int)pb.plan[s].n_frames * 2 * ch) return;
   const size_t gslot = (size_t)s * pb.GC + gci;
   const int f = gci / (2 * ch);
   const int lo_bits = lo_bits_of(cfg, pb.frame_br[(size_t)s * pb.Fc + f]);
-  const float2 *sm2 = reinterpret_cast<const float2 *>(pb.smag + gslot * 576);
+  // |x|^0.75 (SRC:805-813 [OD3]), peak -> g0 (SRC:989-1006), preflag (SRC:2042-2066); line i = lane + 32 j
+  {
+    const float *spec = pb.spec + gslot * 576;
+    float *smag = pb.smag + gslot * 576;
+    float x[18];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) x[j] = __ldg(spec + lane + 32 * j);
+    float peak = 0.0f, plo = 0.0f, phi = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 18; ++j) {
+      const int i = lane + 32 * j;
+      const float ax = fabsf(x[j]);
+      peak = fmaxf(peak, ax);
+      // [OD1b]: partial index = (i - segment start) mod 32; 432 mod 32 = 16 is an xor permutation of the lanes, which
+      // the butterfly tree is invariant under.
+      if (i < 432) plo = __fmaf_rn(x[j], x[j], plo); else phi = __fmaf_rn(x[j], x[j], phi);
+      const float mag = pow34(fmaxf(ax, 1e-10f));
+      smag[i] = x[j] < 0.0f ? -mag : mag;
+      smg[warp][i] = mag;
+    }
+    peak = warp_max(peak);
+    const float low = lane_tree(plo), high = lane_tree(phi);
+    if (lane == 0) {
+      const int g0 = gain_from_peak(peak);
+      const int pre = high > __fmul_rn(low, 1.5f) ? 1 : 0;
+      pb.gc_meta[gslot] = (uint32_t)g0 | (uint32_t)pre << 17;
+    }
+    __syncwarp();
+  }
   float mx[9], my[9];
 #pragma unroll
-  for (int j = 0; j < 9; ++j) { float2 v = sm2[lane + 32 * j]; mx[j] = fabsf(v.x); my[j] = fabsf(v.y); }
-  uint32_t meta = pb.gc_meta[gslot];
+  for (int j = 0; j < 9; ++j) { float2 v = reinterpret_cast<const float2 *>(smg[warp])[lane + 32 * j]; mx[j] = v.x; my[j] = v.y; }
+  const uint32_t meta = __shfl_sync(0xffffffffu, lane == 0 ? pb.gc_meta[gslot] : 0u, 0);
   const int g0 = meta & 255;
   int gain = g0, n = 0, restart = 0;
   uint16_t *bits_out = pb.gc_bits + gslot * kMaxEntries, *bv_out = pb.gc_bv + gslot * kMaxEntries;
@@ -808,9 +867,9 @@ __global__ void __launch_bounds__(256) k_carry(Config cfg, PassBuffers pb) {
 __global__ void __launch_bounds__(256) k_thresholds(Config cfg, PassBuffers pb) {
   const int s = blockIdx.x, lane = threadIdx.x & 31;
   const int gci = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (gci >= (int)pb.plan[s].n_frames * 2 * cfg.channels || !pb.tr_thr || !pb.tr_spectrum) return;
+  if (gci >= (int)pb.plan[s].n_frames * 2 * cfg.channels || !pb.tr_thr) return;
   const size_t gslot = (size_t)s * pb.GC + gci;
-  const float *x = pb.tr_spectrum + gslot * 576;
+  const float *x = pb.spec + gslot * 576;
   float *thr = pb.tr_thr + gslot * 576;
   double qd = (double)(10 - cfg.quality) / 10.0;
   const float quality_scale = (float)(qd > 0.1 ? qd : 0.1);
@@ -880,25 +939,29 @@ __global__ void k_synth(float *pcm, size_t n, int channels, int sample_rate, flo
 static inline int check(int launched) { cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? launched : -(int)e; }
 
 int launch_prepass(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
-  dim3 grid(cfg.n_streams, (pb.Fc + 3) / 4);
+  if (pb.max_frames <= 0) return 0;
+  dim3 grid(cfg.n_streams, (pb.max_frames + 3) / 4);
   k_prepass<<<grid, 128, 0, st>>>(cfg, pb);
   int n = 1;
-  if (cfg.vbr) { dim3 g2(cfg.n_streams, (pb.Fc + 63) / 64); k_bitrate<<<g2, 64, 0, st>>>(cfg, pb); ++n; }
+  if (cfg.vbr) { dim3 g2(cfg.n_streams, (pb.max_frames + 63) / 64); k_bitrate<<<g2, 64, 0, st>>>(cfg, pb); ++n; }
   return check(n);
 }
 int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  if (pb.max_frames <= 0) return 0;
   static bool attr_set[64] = {};
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 64 && !attr_set[dev]) {
     cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpecSmemBytes);
+    cudaFuncSetAttribute(k_spectrum, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set[dev] = true;
   }
-  dim3 grid(cfg.n_streams, cfg.channels, (2 * pb.Fc + kRunGranules - 1) / kRunGranules);
+  dim3 grid(cfg.n_streams, cfg.channels, (2 * pb.max_frames + kRunGranules - 1) / kRunGranules);
   k_spectrum<<<grid, kSteps, kSpecSmemBytes, st>>>(cfg, pb);
   return check(1);
 }
 int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
-  dim3 grid(cfg.n_streams, (pb.GC + 7) / 8);
+  if (pb.max_frames <= 0) return 0;
+  dim3 grid(cfg.n_streams, (pb.max_frames * 2 * cfg.channels + 7) / 8);
   k_curve<<<grid, 256, 0, st>>>(cfg, pb);
   return check(1);
 }
@@ -907,12 +970,13 @@ int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   return check(1);
 }
 int launch_pack(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
-  dim3 grid(cfg.n_streams, pb.Fc);
+  if (pb.max_frames <= 0) return 0;
+  dim3 grid(cfg.n_streams, pb.max_frames);
   k_pack<<<grid, 128, 0, st>>>(cfg, pb);
   return check(1);
 }
 int launch_frames(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
-  dim3 grid(cfg.n_streams, (pb.Fc + 1 + 3) / 4);
+  dim3 grid(cfg.n_streams, (pb.max_frames + 1 + 3) / 4);
   k_frames<<<grid, 128, 0, st>>>(cfg, pb);
   return check(1);
 }
@@ -921,7 +985,8 @@ int launch_carry(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   return check(1);
 }
 int launch_thresholds(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
-  dim3 grid(cfg.n_streams, (pb.GC + 7) / 8);
+  if (pb.max_frames <= 0) return 0;
+  dim3 grid(cfg.n_streams, (pb.max_frames * 2 * cfg.channels + 7) / 8);
   k_thresholds<<<grid, 256, 0, st>>>(cfg, pb);
   return check(1);
 }

@@ -21,6 +21,7 @@ struct Config {              // constant for the lifetime of a batch; passed to 
   int sample_rate, base_kbps, vbr, mode, quality, crc, original, copyright;
   int sr_index, sfb_index, side_bytes, header_bytes /* 4 + crc + side */;
   int mode_bits, mode_ext, cbr_index;
+  float f_one, f_neg0;                // 1.0f and -0.0f as run-time values (see k_spectrum phase A)
   int frame_base[16], frame_rem[16];  // 144*kbps*1000 / sr and % sr per bitrate index
   uint8_t vbr_idx_of_kbps[324];       // bitrateIndex(kbps) for every VBR target 0...320
 };
@@ -73,6 +74,7 @@ struct StreamState {         // persistent per stream
 
 struct PassBuffers {         // device arrays for one pass; Fc = frame capacity per stream, GC = Fc*2*ch
   int Fc, GC;
+  int max_frames;            // largest n_frames of any stream in this pass (grid sizing)
   StreamPlan *plan;          // [S]
   StreamState *state;        // [S]
   float *head_in, *head_out; // [S][2*fsc] carried frame + pending partial (double buffered, swapped per pass)
@@ -81,7 +83,8 @@ struct PassBuffers {         // device arrays for one pass; Fc = frame capacity 
   float *gc_energy;          // [S][10 + GC]  (first 10 = carried history, right aligned)
   uint16_t *gc_bt;           // [S][GC] block_type | sbg0<<2 | sbg1<<5 | sbg2<<8
   uint8_t *frame_br;         // [S][Fc] bitrate index
-  float *smag;               // [S][GC][576] sign(x) * |x|^0.75
+  float *spec;               // [S][GC][576] MDCT spectrum (K1+K2 output)
+  float *smag;               // [S][GC][576] sign(x) * |x|^0.75 (K4 output, K5 input)
   uint32_t *gc_meta;         // [S][GC] g0 | n_entries<<8 | restart<<16 | preflag<<17
   uint16_t *gc_bits;         // [S][GC][20]
   uint16_t *gc_bv;           // [S][GC][20]
@@ -99,7 +102,6 @@ struct PassBuffers {         // device arrays for one pass; Fc = frame capacity 
   uint16_t *emit_size;       // [S][Fc+1] sizes of the frames emitted by this pass, in order
   uint32_t *emit_n;          // [S]
   // optional traces
-  float *tr_spectrum;        // [S][GC][576] or null
   int32_t *tr_ix;            // same
   float *tr_thr;             // same
 };
