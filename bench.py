@@ -32,10 +32,8 @@ ALGO_BYTES_PER_GC_SPECTRUM = 2304 + 2304 + 4      # PCM in + sign*|x|^0.75 out +
 FLOP_PER_GC_SPECTRUM = 18 * (512 + 448 + 2 * 2048) + 32 * (36 + 2 * 648 + 18)   # direct form as executed, long blocks
 
 
-def stream_params(i):
-    """BASELINE C4 recipe: seed 1000+i, f_L = 110 * 2^((i mod 48)/12), f_R = 1.26 f_L."""
-    fl = 110.0 * 2.0 ** ((i % 48) / 12.0)
-    return fl, fl * 1.26, 1000 + i
+sharding = importlib.import_module("swift-mp3_b200.sharding")
+stream_params = sharding.stream_params      # BASELINE C4 recipe: seed 1000+i, f_L = 110 * 2^((i mod 48)/12), f_R = 1.26 f_L
 
 
 class ClockSampler(threading.Thread):
@@ -144,25 +142,19 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(v, dist, "cuda")
 
     def sum_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return sharding.sum_over_ranks(v, dist, "cuda")
 
-    S = a.streams
+    S = a.streams                                                  # weak scaling: a.streams per GPU
+    shard_lo, shard_hi = sharding.shard_range(S * world, rank, world)
+    assert shard_hi - shard_lo == S
     n_per = int(round(a.seconds * SR))
     n_floats = n_per * CH
     pcm = torch.empty((S, n_floats), dtype=torch.float32, device="cuda")
     for i in range(S):
-        fl, fr, seed = stream_params(rank * S + i)
+        fl, fr, seed = stream_params(shard_lo + i)
         rc = L.mp3b_synth_fill(local, pcm[i].data_ptr(), n_per, CH, SR, fl, fr, 0.5, 0.05, seed)
         assert rc == 0, L.mp3b_last_error()
     torch.cuda.synchronize()

@@ -56,8 +56,11 @@ struct mp3b_batch {
   PassBuffers pb{};
   float *d_head[2] = {nullptr, nullptr};
   int head_sel = 0;
-  float *d_stage = nullptr; size_t stage_stride = 0;   // floats per stream
-  StreamPlan *h_plan = nullptr;                          // pinned [S]
+  float *d_stage[2] = {nullptr, nullptr}; size_t stage_stride = 0;   // double-buffered PCM staging, floats per stream
+  StreamPlan *h_plan = nullptr;                          // pinned [2][S]
+  StreamPlan *d_plan[2] = {nullptr, nullptr};
+  cudaStream_t st_copy = nullptr;
+  cudaEvent_t ev_h2d[2][2] = {}, ev_consumed[2] = {};
   StreamState *h_state = nullptr;                        // pinned [S]
   uint16_t *h_emit_size = nullptr; uint32_t *h_emit_n = nullptr;
   uint64_t *d_offsets = nullptr, *h_offsets = nullptr;
@@ -140,12 +143,15 @@ void free_batch(mp3b_batch *b) {
   PassBuffers &p = b->pb;
   void *dev[] = {p.plan, p.state, b->d_head[0], b->d_head[1], p.ms, p.frame_energy, p.gc_energy, p.gc_bt, p.frame_br, p.spec, p.smag,
                  p.gc_meta, p.gc_bits, p.gc_bv, p.gc_bitoff, p.gc_sel, p.fr_md, p.rec, p.emit, p.md, p.md_tail, p.md_carry, p.out,
-                 p.emit_size, p.emit_n, p.tr_ix, p.tr_thr, b->d_stage, b->d_offsets, b->d_compact};
+                 p.emit_size, p.emit_n, p.tr_ix, p.tr_thr, b->d_stage[0], b->d_stage[1], b->d_plan[1], b->d_offsets, b->d_compact};
   for (void *q : dev) if (q) cudaFree(q);
   void *host[] = {b->h_plan, b->h_state, b->h_emit_size, b->h_emit_n, b->h_offsets, b->h_out};
   for (void *q : host) if (q) cudaFreeHost(q);
   for (auto &e : b->ev) if (e) cudaEventDestroy(e);
+  for (auto &e : b->ev_consumed) if (e) cudaEventDestroy(e);
+  for (auto &r : b->ev_h2d) for (auto &e : r) if (e) cudaEventDestroy(e);
   if (b->st) cudaStreamDestroy(b->st);
+  if (b->st_copy) cudaStreamDestroy(b->st_copy);
   cudaGetLastError();
   delete b;
 }
@@ -181,7 +187,8 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   cudaError_t e = cudaSuccess;
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   A(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
-  A(dalloc(p.plan, S)); A(dalloc(p.state, S));
+  A(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
+  A(dalloc(p.plan, S)); A(dalloc(b->d_plan[1], S)); A(dalloc(p.state, S));
   A(dalloc(b->d_head[0], S * 2 * cfg.fsc)); A(dalloc(b->d_head[1], S * 2 * cfg.fsc));
   A(dalloc(p.ms, S * (Fc + 1))); A(dalloc(p.frame_energy, S * Fc)); A(dalloc(p.gc_energy, S * (10 + GC)));
   A(dalloc(p.gc_bt, S * GC)); A(dalloc(p.frame_br, S * Fc)); A(dalloc(p.spec, S * GC * 576, false)); A(dalloc(p.smag, S * GC * 576, false));
@@ -191,18 +198,21 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   A(dalloc(p.md, S * p.md_stride, false)); A(dalloc(p.md_tail, S * 4)); A(dalloc(p.md_carry, S * kMdCarryCap));
   A(dalloc(p.emit_size, S * (Fc + 1))); A(dalloc(p.emit_n, S));
   A(dalloc(b->d_offsets, S + 1));
-  A(cudaHostAlloc((void **)&b->h_plan, S * sizeof(StreamPlan), cudaHostAllocDefault));
+  A(cudaHostAlloc((void **)&b->h_plan, 2 * S * sizeof(StreamPlan), cudaHostAllocDefault));
   A(cudaHostAlloc((void **)&b->h_state, S * sizeof(StreamState), cudaHostAllocDefault));
   A(cudaHostAlloc((void **)&b->h_emit_size, S * (Fc + 1) * sizeof(uint16_t), cudaHostAllocDefault));
   A(cudaHostAlloc((void **)&b->h_emit_n, S * sizeof(uint32_t), cudaHostAllocDefault));
   A(cudaHostAlloc((void **)&b->h_offsets, (S + 1) * sizeof(uint64_t), cudaHostAllocDefault));
   for (auto &ev : b->ev) A(cudaEventCreate(&ev));
+  for (auto &ev : b->ev_consumed) A(cudaEventCreate(&ev));
+  for (auto &r : b->ev_h2d) for (auto &ev : r) A(cudaEventCreate(&ev));
   if (e != cudaSuccess) {
     free_batch(b);
     return fail(e == cudaErrorMemoryAllocation ? MP3B_ERR_OOM : MP3B_ERR_CUDA, "batch allocation failed: %s", cudaGetErrorString(e));
   }
   b->pending.assign(S, 0); b->out_len.assign(S, 0); b->frame_count.assign(S, 0); b->byte_count.assign(S, 0);
   b->frame_sizes.resize(S);
+  b->d_plan[0] = p.plan;
   *out = b;
   return MP3B_OK;
 }
@@ -248,9 +258,10 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
   int rc = ensure_out(b, (max_frames + 1) * (size_t)b->max_frame_bytes);
   if (rc) return rc;
   if (b->trace) { rc = ensure_trace(b); if (rc) return rc; }
-  if (!device_ptrs && !b->d_stage) {
+  if (!device_ptrs && !b->d_stage[0]) {
     b->stage_stride = (size_t)Fc * fsc;
-    CU(cudaMalloc((void **)&b->d_stage, (size_t)S * b->stage_stride * sizeof(float)));
+    CU(cudaMalloc((void **)&b->d_stage[0], (size_t)S * b->stage_stride * sizeof(float)));
+    CU(cudaMalloc((void **)&b->d_stage[1], (size_t)S * b->stage_stride * sizeof(float)));
   }
   for (auto &m : b->stage_ms) m = 0.0f;
   b->launches = 0; b->passes = 0;
@@ -258,62 +269,84 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
   if (b->trace) {
     b->tr_frames.assign(S, {}); b->tr_gc.assign(S, {}); b->tr_spec.assign(S, {}); b->tr_ix.assign(S, {}); b->tr_thr.assign(S, {});
   }
-  cudaStream_t st = b->st;
-  bool first = true;
-  for (;;) {
+  cudaStream_t st = b->st, stc = b->st_copy;
+  // Pass pipeline: while the kernels of pass p run on `st`, the PCM of pass p + 1 crosses PCIe on `st_copy` into the
+  // other staging buffer.  Planning is pure host arithmetic (it never needs device results), so it runs one pass ahead.
+  std::vector<const float *> src[2] = {std::vector<const float *>(S), std::vector<const float *>(S)};
+  bool first_plan = true;
+  auto plan_pass = [&](int slot) -> bool {
     bool any = false;
-    // ---- plan
+    StreamPlan *hp = b->h_plan + (size_t)slot * S;
     for (int s = 0; s < S; ++s) {
-      StreamPlan &pl = b->h_plan[s];
+      StreamPlan &pl = hp[s];
       size_t remaining = n[s] - cursor[s];
       size_t room = (size_t)Fc * fsc - b->pending[s];
       size_t cur_n = std::min(remaining, room);
       size_t total = b->pending[s] + cur_n;
-      uint32_t nfr = (uint32_t)(total / fsc), flags = first ? 4u : 0u;
+      uint32_t nfr = (uint32_t)(total / fsc), flags = first_plan ? 4u : 0u;
       uint32_t new_pending = (uint32_t)(total % fsc);
       if (remaining == cur_n && want_flush[s] && !flushed[s]) {
         if (new_pending > 0) {
           if ((int)nfr < Fc) { nfr += 1; flags |= 3u; new_pending = 0; flushed[s] = 1; }
         } else { flags |= 2u; flushed[s] = 1; }
       }
-      pl.cur = device_ptrs ? (n[s] ? pcm[s] + cursor[s] : nullptr) : b->d_stage + (size_t)s * b->stage_stride;
+      src[slot][s] = n[s] ? pcm[s] + cursor[s] : nullptr;
+      pl.cur = device_ptrs ? src[slot][s] : b->d_stage[slot] + (size_t)s * b->stage_stride;
       pl.cur_n = (uint32_t)cur_n; pl.n_frames = nfr; pl.flags = flags; pl.head_n = (uint32_t)(fsc + b->pending[s]);
       if (cur_n || nfr || (flags & 2u)) any = true;
-      // bookkeeping for the next pass
       cursor[s] += cur_n;
       b->pending[s] = new_pending;
     }
-    if (!any && !first) break;
-    // one strided copy when every stream hands over the same amount from equally spaced host buffers
-    bool uniform = !device_ptrs && S > 1 && b->h_plan[0].cur_n > 0;
-    const size_t cur0 = b->h_plan[0].cur_n; ptrdiff_t pitch = 0;
-    for (int s = 0; s < S && uniform; ++s) {
-      if (b->h_plan[s].cur_n != cur0) { uniform = false; break; }
-      if (s >= 1) {
-        ptrdiff_t d = (const char *)(pcm[s] + cursor[s]) - (const char *)(pcm[s - 1] + cursor[s - 1]);
-        if (s == 1) pitch = d; else if (d != pitch) uniform = false;
-      }
-    }
-    // ---- H2D
-    CU(cudaEventRecord(b->ev[0], st));
+    const bool run = any || first_plan;
+    first_plan = false;
+    return run;
+  };
+  auto issue_h2d = [&](int slot) -> int {
+    const StreamPlan *hp = b->h_plan + (size_t)slot * S;
+    CU(cudaEventRecord(b->ev_h2d[slot][0], stc));
     if (!device_ptrs) {
-      if (uniform && pitch >= (ptrdiff_t)(cur0 * sizeof(float))) {
-        CU(cudaMemcpy2DAsync(b->d_stage, b->stage_stride * sizeof(float), pcm[0] + (cursor[0] - cur0), (size_t)pitch,
-                             cur0 * sizeof(float), S, cudaMemcpyHostToDevice, st));
-      } else {
-        for (int s = 0; s < S; ++s) {
-          size_t cur_n = b->h_plan[s].cur_n;
-          if (cur_n) CU(cudaMemcpyAsync(b->d_stage + (size_t)s * b->stage_stride, pcm[s] + (cursor[s] - cur_n), cur_n * sizeof(float),
-                                        cudaMemcpyHostToDevice, st));
+      CU(cudaStreamWaitEvent(stc, b->ev_consumed[slot], 0));       // the kernels that last read this staging buffer
+      // one strided copy when every stream hands over the same amount from equally spaced host buffers
+      bool uniform = S > 1 && hp[0].cur_n > 0;
+      const size_t cur0 = hp[0].cur_n; ptrdiff_t pitch = 0;
+      for (int s = 0; s < S && uniform; ++s) {
+        if (hp[s].cur_n != cur0) { uniform = false; break; }
+        if (s >= 1) {
+          ptrdiff_t d = (const char *)src[slot][s] - (const char *)src[slot][s - 1];
+          if (s == 1) pitch = d; else if (d != pitch) uniform = false;
         }
       }
+      if (uniform && pitch >= (ptrdiff_t)(cur0 * sizeof(float))) {
+        CU(cudaMemcpy2DAsync(b->d_stage[slot], b->stage_stride * sizeof(float), src[slot][0], (size_t)pitch, cur0 * sizeof(float), S,
+                             cudaMemcpyHostToDevice, stc));
+      } else {
+        for (int s = 0; s < S; ++s)
+          if (hp[s].cur_n) CU(cudaMemcpyAsync(b->d_stage[slot] + (size_t)s * b->stage_stride, src[slot][s], hp[s].cur_n * sizeof(float),
+                                              cudaMemcpyHostToDevice, stc));
+      }
     }
-    CU(cudaMemcpyAsync(b->pb.plan, b->h_plan, (size_t)S * sizeof(StreamPlan), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->d_plan[slot], hp, (size_t)S * sizeof(StreamPlan), cudaMemcpyHostToDevice, stc));
+    CU(cudaEventRecord(b->ev_h2d[slot][1], stc));
+    return MP3B_OK;
+  };
+  int slot = 0;
+  bool have = plan_pass(slot);
+  if (have) { rc = issue_h2d(slot); if (rc) return rc; }
+  while (have) {
+    const StreamPlan *hplan = b->h_plan + (size_t)slot * S;
+    // look ahead: plan + start the transfer of the next pass before this one's kernels are queued
+    bool more = false;
+    for (int s = 0; s < S && !more; ++s) more = cursor[s] < n[s] || (want_flush[s] && !flushed[s]);
+    bool have_next = false;
+    if (more) { have_next = plan_pass(slot ^ 1); if (have_next) { rc = issue_h2d(slot ^ 1); if (rc) return rc; } }
+    CU(cudaStreamWaitEvent(st, b->ev_h2d[slot][1], 0));
+    CU(cudaEventRecord(b->ev[0], st));
     CU(cudaEventRecord(b->ev[1], st));
     // ---- device pipeline
     PassBuffers pb = b->pb;
+    pb.plan = b->d_plan[slot];
     pb.max_frames = 0;
-    for (int s = 0; s < S; ++s) pb.max_frames = std::max<int>(pb.max_frames, (int)b->h_plan[s].n_frames);
+    for (int s = 0; s < S; ++s) pb.max_frames = std::max<int>(pb.max_frames, (int)hplan[s].n_frames);
     pb.head_in = b->d_head[b->head_sel]; pb.head_out = b->d_head[b->head_sel ^ 1];
 #define LAUNCH(expr)                                                                                        \
   do {                                                                                                      \
@@ -335,6 +368,7 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
     LAUNCH(launch_frames(cfg, pb, st));
     LAUNCH(launch_carry(cfg, pb, st));
     CU(cudaEventRecord(b->ev[7], st));
+    CU(cudaEventRecord(b->ev_consumed[slot], st));
     b->passes += 1;
     b->head_sel ^= 1;
     CU(cudaMemcpyAsync(b->h_emit_n, pb.emit_n, (size_t)S * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -347,7 +381,8 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
     if (se != cudaSuccess) { b->sticky = MP3B_ERR_CUDA; return fail(MP3B_ERR_CUDA, "device pipeline failed: %s", cudaGetErrorString(se)); }
     {
       static const int stage_of[7] = {MP3B_STAGE_H2D, MP3B_STAGE_PREPASS, MP3B_STAGE_SPECTRUM, MP3B_STAGE_CURVE, MP3B_STAGE_SCAN, MP3B_STAGE_PACK, MP3B_STAGE_FRAMES};
-      for (int i = 0; i < 7; ++i) { float ms = 0; cudaEventElapsedTime(&ms, b->ev[i], b->ev[i + 1]); b->stage_ms[stage_of[i]] += ms; }
+      for (int i = 1; i < 7; ++i) { float ms = 0; cudaEventElapsedTime(&ms, b->ev[i], b->ev[i + 1]); b->stage_ms[stage_of[i]] += ms; }
+      { float ms = 0; cudaEventElapsedTime(&ms, b->ev_h2d[slot][0], b->ev_h2d[slot][1]); b->stage_ms[MP3B_STAGE_H2D] += ms; }
       float ms = 0; cudaEventElapsedTime(&ms, b->ev[0], b->ev[7]); b->stage_ms[MP3B_STAGE_TOTAL] += ms;
     }
     for (int s = 0; s < S; ++s) {
@@ -359,7 +394,7 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
       const int ngc = 2 * cfg.channels;
       std::vector<float> tmpf; std::vector<int32_t> tmpi;
       for (int s = 0; s < S; ++s) {
-        const uint32_t nf = b->h_plan[s].n_frames;
+        const uint32_t nf = hplan[s].n_frames;
         for (uint32_t f = 0; f < nf; ++f) {
           const FrameRec &r = b->h_rec[(size_t)s * (Fc + 1) + 1 + f];
           mp3b_frame_record fr{};
@@ -385,10 +420,8 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
         }
       }
     }
-    first = false;
-    bool more = false;
-    for (int s = 0; s < S && !more; ++s) more = cursor[s] < n[s] || (want_flush[s] && !flushed[s]);
-    if (!more) break;
+    have = have_next;
+    slot ^= 1;
   }
   // ---- results: counters, lengths, optional download
   CU(cudaEventRecord(b->ev[0], st));

@@ -3,8 +3,8 @@
 // Numerical contract (bit-exact against oracle/mp3_oracle.c): every floating-point operation below is an explicit
 // IEEE-754 round-to-nearest intrinsic (__fmul_rn / __fadd_rn / __fmaf_rn / __fdiv_rn) in the order the oracle
 // defines ([OD1]..[OD5] in its header); the file is compiled with -fmad=false so nothing else is contracted.
-// All constant tables are literals (tables_gen.h) so that the fully unrolled loops carry them as instruction
-// immediates: the 32x64 analysis matrix, the 512-tap window and the MDCT matrices cost no memory traffic at all.
+// Constant tables are literals (tables_gen.h): the MDCT matrices are instruction immediates of fully unrolled loops,
+// the 32x64 analysis matrix and the 512-tap window are staged once per CTA in shared memory for the packed FP32x2 loop.
 #include "kernels.h"
 
 #include <cstdio>
