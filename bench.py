@@ -132,6 +132,7 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MP3B_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
