@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SR, CH, KBPS = 44100, 2, 128
-ALGO_BYTES_PER_GC_SPECTRUM = 2304 + 2304 + 4      # PCM in + sign*|x|^0.75 out + meta word
+ALGO_BYTES_PER_GC_SPECTRUM = 2304 + 2304          # PCM in + MDCT spectrum out
 FLOP_PER_GC_SPECTRUM = 18 * (512 + 448 + 2 * 2048) + 32 * (36 + 2 * 648 + 18)   # direct form as executed, long blocks
 
 
@@ -94,6 +94,48 @@ def cpu_reference(seconds_per_stream, min_wall=10.0, max_wall=40.0):
                       "%d threads, %.1f s wall" % (done, seconds_per_stream, cores, el)}, el, audio
 
 
+def bench_c5(a, mp3, L, local, rank, world):
+    """BASELINE config 5: 1024 concurrent sessions fed 1152-sample stereo chunks through encode(samples:) — one batch call
+    per chunk with pinned host buffers in, MP3 bytes out; p50 / p99 latency of a call (= of every frame in it)."""
+    import numpy as np
+    import torch
+    S, steps = 1024, max(a.steps, 200)
+    chunk = 1152 * CH
+    opts = mp3.MP3EncoderOptions(sampleRate=SR, bitrateKbps=KBPS, mode=mp3.Mode.stereo)
+    b = mp3.EncoderBatch(opts, S, local, 8)
+    n_chunks = 64                                                   # distinct chunks per stream, cycled
+    hp = C.c_void_p()
+    assert L.mp3b_host_alloc(S * n_chunks * chunk * 4, C.byref(hp)) == 0, L.mp3b_last_error()
+    pcm = torch.empty((S, n_chunks * chunk), dtype=torch.float32, device="cuda")
+    for i in range(S):
+        fl, fr, seed = stream_params(i)
+        assert L.mp3b_synth_fill(local, pcm[i].data_ptr(), n_chunks * 1152, CH, SR, fl, fr, 0.5, 0.05, seed) == 0
+    assert L.mp3b_device_copy(local, hp, pcm.data_ptr(), S * n_chunks * chunk * 4, 1) == 0
+    ns = (C.c_size_t * S)(*([chunk] * S))
+    lat = []
+    for k in range(steps + 20):
+        ptrs = (C.c_void_p * S)(*[hp.value + (i * n_chunks + k % n_chunks) * chunk * 4 for i in range(S)])
+        t0 = time.perf_counter()
+        b.encode_ptrs(ptrs, ns, flush=False)
+        lat.append(time.perf_counter() - t0)
+    lat = np.array(lat[20:]) * 1e3
+    if rank == 0:
+        import oracle_binding as orc
+        host = pcm[3].cpu().numpy()
+        rs = orc.Session(sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")
+        ref = b"".join(rs.encode(host[(k % n_chunks) * chunk:(k % n_chunks + 1) * chunk]) for k in range(steps + 20))
+        assert b.byte_count(3) == len(ref) and b.output(3) == ref[-len(b.output(3)):], "streaming output differs from the oracle"
+        p50, p99 = float(np.percentile(lat, 50)), float(np.percentile(lat, 99))
+        print(json.dumps({"metric": "per-frame latency, 1024 concurrent sessions (config 5)", "value": p50, "unit": "ms (p50)",
+                          "p99_ms": p99, "mean_ms": float(lat.mean()), "n_gpus": 1, "steps": steps, "higher_is_better": False,
+                          "frame_period_ms": 1152 / SR * 1e3, "realtime_factor_p50": S * 1152 / SR * 1e3 / p50,
+                          "data": "synthetic", "config": {"workload": "C5: 1024 sessions x 1152-sample stereo chunks, host buffers in, bytes out"},
+                          "stage_ms_last_call": b.stage_ms(), "gpu_launches_per_call": b.launch_count,
+                          "parity": "session 3 byte-identical to the oracle over %d chunks" % (steps + 20)}))
+    L.mp3b_host_free(hp)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -104,6 +146,8 @@ def main():
     ap.add_argument("--seconds", type=float, default=30.0)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c4 (default, the headline): batch of 30 s streams; c5: streaming latency, 1024 sessions x 1152-sample chunks")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -148,6 +192,8 @@ def main():
     def sum_over_ranks(v):
         return sharding.sum_over_ranks(v, dist, "cuda")
 
+    if a.workload == "c5":
+        return bench_c5(a, mp3, L, local, rank, world)
     S = a.streams                                                  # weak scaling: a.streams per GPU
     shard_lo, shard_hi = sharding.shard_range(S * world, rank, world)
     assert shard_hi - shard_lo == S
@@ -224,7 +270,13 @@ def main():
         pass
     fp32_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) / 1000.0) / 1000.0   # nominal TFLOP/s, non-tensor FP32
     fp32_ach = gc_per_launch * FLOP_PER_GC_SPECTRUM * (16.0 / 15.0) / (spectrum_ms_per_launch / 1000.0) / 1e12
-    roofline = {"kernel": "k_spectrum (polyphase filterbank + MDCT + |x|^0.75)", "bound": "hbm", "achieved": achieved,
+    out_per_gc = out_bytes / max(gc_per_step, 1)
+    algo = {"prepass": 2304 + 8, "spectrum": ALGO_BYTES_PER_GC_SPECTRUM, "curve": 2304 + 2304 + 84, "scan": 84 + 45,
+            "pack": 2304 + out_per_gc, "frames": 2 * out_per_gc + 30}          # algorithmic bytes per gc, DESIGN.md section 4
+    stage_table = {k: {"ms_per_step": stages[k] / a.steps, "algo_bytes_per_gc": algo[k],
+                       "achieved_GBps": gc_per_step * algo[k] / (stages[k] / a.steps / 1000.0) / 1e9,
+                       "hbm_frac": gc_per_step * algo[k] / (stages[k] / a.steps / 1000.0) / 1e9 / hbm_peak} for k in algo}
+    roofline = {"kernel": "k_spectrum (polyphase filterbank + MDCT)", "bound": "hbm", "achieved": achieved, "stages": stage_table,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": which,
                 "ms_per_launch": spectrum_ms_per_launch, "gc_per_launch": gc_per_launch,
                 "limiter": "fp32 (direct-form 32x64 matrixing kept for bit-exact parity); see fp32",
