@@ -8,6 +8,7 @@
 #include "kernels.h"
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "tables_gen.h"
 
@@ -436,6 +437,243 @@ __global__ void __launch_bounds__(kSteps, 2) k_spectrum(Config cfg, PassBuffers 
     float *spec = pb.spec + gslot * 576;
 #pragma unroll
     for (int j = 0; j < 18; ++j) spec[lane + 32 * j] = X[lane + 32 * j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1+K2, tiled form.  Same arithmetic as k_spectrum above, operation for operation (so the same bits), reorganised so
+// that the FP32 pipe and not the shared-memory pipe is the limiter:
+//   * a CTA (4 warps) owns a run of R granules of one (stream, channel) and walks it in tiles of 128 filterbank steps;
+//   * windowing: a thread owns one window phase n and slides along the steps two at a time, so every PCM sample is
+//     read from shared memory once per (n, parity) instead of once per tap; the pair (Y[n][u], Y[n][u+1]) is one FFMA2;
+//   * matrixing: a register-tiled 32 x 128 x 64 product (thread = 8 subbands x 4 steps, warp = 32 x 32): three
+//     conflict-free LDS.128 feed sixteen FFMA2; the reduction over n stays ascending, one fused multiply-add each;
+//   * MDCT: warp = granule, lane = subband, straight out of the subband tile; rows that the next tile still needs
+//     (the previous granule and the incomplete one) are moved to the front of the tile;
+//   * the PCM rows of tile j+1 are fetched with cp.async while tile j is in its matrixing / MDCT phases.
+constexpr int kTile = 128;                        // filterbank steps per tile
+constexpr int kPRows = kTile + kLook;             // 143 PCM rows of 32 samples, used as a ring
+constexpr int kSbKeep = 35;                       // rows carried to the next tile: previous granule + incomplete one
+constexpr int kSbRows = kTile + kSbKeep;          // 163
+constexpr int kSp2Threads = 128;
+constexpr int kSp2SmemFloats = 64 * 32 + kPRows * 32 + 64 * kTile + kSbRows * kRowPad;
+constexpr int kSp2SmemBytes = kSp2SmemFloats * 4;
+
+__global__ void __launch_bounds__(kSp2Threads, 2) k_spectrum2(Config cfg, PassBuffers pb, int R) {
+  extern __shared__ __align__(16) float sm[];
+  float *sMp = sm;                                 // [64 n][4 kg][8 i] = M[kg + 4 i][n]
+  float *P = sMp + 64 * 32;                        // [143][32] PCM rows of the tile: 15 rows of look-back + 128 new
+  float *Y = P + kPRows * 32;                      // [64 n][128 t], 16-byte chunks XOR-swizzled with n & 7; later X[4][576]
+  float *Sb = Y + 64 * kTile;                      // [163][33] subband samples [step][sb]
+  const int c = blockIdx.x, s = blockIdx.y, run = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const StreamPlan &plan = pb.plan[s];
+  const int ngr = 2 * (int)plan.n_frames;
+  const int g_begin = run * R;
+  if (g_begin >= ngr) return;
+  const int g_cnt = min(R, ngr - g_begin);
+  const int U = 18 * (g_cnt + 1);                  // steps of the run; step u = 0 opens the recomputed granule g_begin - 1
+  const int n_tiles = (U + kTile - 1) / kTile;
+  const int rows_total = kLook + U;                // run row r holds samples n_start + 32 r ... + 31; step u reads rows u ... u + 15
+  const int ch = cfg.channels;
+  const PcmView pv = pcm_view(cfg, pb, s);
+  const uint8_t *msrow = pb.ms + (size_t)s * (pb.Fc + 1);
+  const uint32_t ms_prev = pb.state[s].ms_prev;
+  const bool joint = cfg.mode == 2;
+  const int n_start = 576 * (g_begin - 1) - 480;
+
+  for (int e = tid; e < 64 * 32; e += kSp2Threads) {
+    const int n = e >> 5, q = e & 31;
+    sMp[e] = __ldg(tab::kAnalysisT + n * 32 + (q >> 3) + 4 * (q & 7));
+  }
+
+  // PCM rows [ra, rb) of the run -> ring.  Fast path: the rows are contiguous in this pass's PCM and need no mid/side
+  // transform: one 4-byte cp.async per sample, nothing waits until the next tile starts.
+  auto load_rows = [&](int ra, int rb, int slot0) {          // run rows [ra, rb) -> P rows slot0 ...
+    rb = min(rb, rows_total);
+    if (ra < rb) {
+      const int64_t rel = (int64_t)(n_start + 32 * ra + 1152) * ch - (int64_t)pv.head_n;
+      if (!joint && rel >= 0 && rel + (int64_t)(rb - ra) * 32 * ch <= (int64_t)pv.cur_n) {
+        const float *src = pv.cur + rel + (ch == 1 ? lane : 2 * lane + c);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(P + slot0 * 32 + lane);
+        for (int r = warp; r < rb - ra; r += 4)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + r * 128), "l"(src + (size_t)r * 32 * ch));
+      } else {
+        for (int r = ra + warp; r < rb; r += 4) {
+          const int nrow = n_start + 32 * r;
+          const int64_t q = (int64_t)(nrow + 1152) * ch;
+          float v;
+          if (ch == 1) v = pv.at(q + lane);
+          else {
+            const float l = pv.at(q + 2 * lane), rr = pv.at(q + 2 * lane + 1);
+            const int fr = nrow >= 0 ? nrow / 1152 : -1;
+            const bool ms = joint && (fr < 0 ? ms_prev != 0 : msrow[1 + fr] != 0);
+            if (!ms) v = c == 0 ? l : rr;
+            else v = c == 0 ? __fmul_rn(__fadd_rn(l, rr), 0.5f) : __fmul_rn(__fsub_rn(l, rr), 0.5f);   // SRC:2148-2154
+          }
+          P[(slot0 + r - ra) * 32 + lane] = v;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+  load_rows(0, kPRows, 0);
+
+  // windowing role: n = 32 nh + lane, steps 64 seg ... 64 seg + 63 of the tile
+  const int nh = warp & 1, seg = warp >> 1;
+  float2 wc[8];                                    // (C[n + 64 i], C[n + 64 i])
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float w = __ldg(tab::kWindow + 32 * nh + lane + 64 * i); wc[i] = make_float2(w, w); }
+  const float2 neg0 = make_float2(cfg.f_neg0, cfg.f_neg0), one = make_float2(cfg.f_one, cfg.f_one);
+  // matrixing role: subbands kg + 4 i, steps 32 warp + 4 tg + j of the tile
+  const int tg = lane & 7, kg = lane >> 3;
+
+  int row0_u = 0, keep = 0, next_g = 1;            // Sb row 0 holds step row0_u; rows [0, keep) are carried
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---- windowing (SRC:1386-1399): X[n + 64 i] of step u = sample at run row u + 15 - 2 i - nh, column 31 - lane
+    {
+      const float *Pc = P + (64 * seg + 1 - nh) * 32 + (31 - lane);   // oldest row of the first step pair
+      float2 q[8];
+#pragma unroll
+      for (int k = 1; k <= 7; ++k) { q[k].x = Pc[(2 * k - 2) * 32]; q[k].y = Pc[(2 * k - 1) * 32]; }
+      Pc += 14 * 32;
+      float *yrow = Y + (32 * nh + lane) * kTile;
+      for (int o = 0; o < 4; ++o, Pc += 16 * 32) {
+        float2 ypair[8];
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+          q[ii].x = Pc[(2 * ii) * 32]; q[ii].y = Pc[(2 * ii + 1) * 32];
+          float2 y;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // fma(x, w, -0) == RN(x * w) and fma(y, 1, z) == RN(y + z): two roundings, as the reference's vDSP_vmul +
+            // vDSP_sve; the constants are run-time values so that ptxas cannot contract the pair into one FFMA2.
+            const float2 z = __ffma2_rn(q[(ii - i) & 7], wc[i], neg0);
+            y = i == 0 ? z : __ffma2_rn(y, one, z);
+          }
+          ypair[ii] = y;
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int chunk = (16 * seg + 4 * o + h) ^ (lane & 7);
+          *reinterpret_cast<float4 *>(yrow + 4 * chunk) = make_float4(ypair[2 * h].x, ypair[2 * h].y, ypair[2 * h + 1].x, ypair[2 * h + 1].y);
+        }
+      }
+    }
+    __syncthreads();
+    if (tile + 1 < n_tiles) {
+      // look-back of the next tile = last 15 rows of this one; each warp moves the rows its own cp.async is about to
+      // overwrite (program order inside the warp), so no barrier is needed in between
+      for (int r = kTile + ((warp - (kTile - kLook)) & 3); r < kPRows; r += 4) P[(r - kTile) * 32 + lane] = P[r * 32 + lane];
+      load_rows(kTile * (tile + 1) + kLook, kTile * (tile + 2) + kLook, kLook);     // lands during matrixing + MDCT
+    }
+    // ---- matrixing (SRC:1402-1408): S[k] = sum over ascending n of M[k][n] * Y[n], one fused multiply-add per term
+    {
+      float2 acc[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int ip = 0; ip < 4; ++ip) acc[j][ip] = make_float2(0.0f, 0.0f);
+      const float4 *mrow = reinterpret_cast<const float4 *>(sMp + kg * 8);
+      const int cbase = 8 * warp + tg;
+#pragma unroll 4
+      for (int n = 0; n < 64; ++n) {
+        const float4 ma = mrow[n * 8], mb = mrow[n * 8 + 1];
+        const float4 y = *reinterpret_cast<const float4 *>(Y + n * kTile + ((cbase ^ (n & 7)) << 2));
+        const float yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 yy = make_float2(yv[j], yv[j]);
+          acc[j][0] = __ffma2_rn(yy, make_float2(ma.x, ma.y), acc[j][0]);
+          acc[j][1] = __ffma2_rn(yy, make_float2(ma.z, ma.w), acc[j][1]);
+          acc[j][2] = __ffma2_rn(yy, make_float2(mb.x, mb.y), acc[j][2]);
+          acc[j][3] = __ffma2_rn(yy, make_float2(mb.z, mb.w), acc[j][3]);
+        }
+      }
+      float *dst = Sb + (keep + 32 * warp + 4 * tg) * kRowPad + kg;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int ip = 0; ip < 4; ++ip) { dst[j * kRowPad + 8 * ip] = acc[j][ip].x; dst[j * kRowPad + 8 * ip + 4] = acc[j][ip].y; }
+    }
+    __syncthreads();
+    // ---- MDCT of the granules whose 36 rows are complete (SRC:1512-1565); warp = granule, lane = subband
+    const int avail_u = min(kTile * (tile + 1), U);
+    const int g_last = avail_u / 18 - 1;
+    for (int gi = next_g + warp; gi <= g_last; gi += 4) {
+      const int gp = g_begin + gi - 1;              // granule index inside the pass
+      const int gci = gp * ch + c;
+      const size_t gslot = (size_t)s * pb.GC + gci;
+      const int bt = pb.gc_bt[gslot] & 3;
+      float *X = Y + warp * 576;
+      {
+        const int sb = lane;
+        const bool flip = sb & 1;
+        const float *prev = Sb + (18 * (gi - 1) - row0_u) * kRowPad + sb, *cur = prev + 18 * kRowPad;
+        const bool use_long = bt == 0 || (bt == 1 && sb < 2);      // SRC:1542-1553
+        if (use_long) {                                             // mdctLong SRC:1619-1636
+          float a[18];
+#pragma unroll
+          for (int m = 0; m < 18; ++m) a[m] = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 36; ++k) {
+            float v = k < 18 ? prev[k * kRowPad] : cur[(k - 18) * kRowPad];
+            if (flip && (k & 1)) v = -v;                            // SRC:1520-1524
+            float w = __fmul_rn(v, tab::kWinLong[k]);
+#pragma unroll
+            for (int m = 0; m < 18; ++m) a[m] = __fmaf_rn(w, tab::kMdctLong[m][k], a[m]);
+          }
+#pragma unroll
+          for (int m = 0; m < 18; ++m) X[sb * 18 + m] = __fdiv_rn(a[m], 9.0f);
+        }
+        if (!use_long) {                                            // mdctShort SRC:1639-1662
+#pragma unroll
+          for (int w3 = 0; w3 < 3; ++w3) {
+            float sg[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+              int k = w3 * 6 + 6 + i;
+              float v = k < 18 ? prev[k * kRowPad] : cur[(k - 18) * kRowPad];
+              if (flip && (k & 1)) v = -v;
+              sg[i] = __fmul_rn(v, tab::kWinShort[i]);
+            }
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+              float r = 0.0f;
+#pragma unroll
+              for (int k = 0; k < 12; ++k) r = __fmaf_rn(sg[k], tab::kMdctShort[m][k], r);
+              X[sb * 18 + w3 + 3 * m] = __fdiv_rn(r, 3.0f);
+            }
+          }
+        }
+        __syncwarp();
+        if (bt == 0 && sb < 31) {                                   // applyAliasingReduction SRC:1581-1616 [OD5]
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            int iu = sb * 18 + 17 - i, il = (sb + 1) * 18 + i;
+            float upper = X[iu], lower = X[il];
+            X[iu] = __fadd_rn(__fmul_rn(lower, tab::kAliasCa[i]), __fmul_rn(upper, tab::kAliasCs[i]));
+            X[il] = __fsub_rn(__fmul_rn(lower, tab::kAliasCs[i]), __fmul_rn(upper, tab::kAliasCa[i]));
+          }
+        }
+        __syncwarp();
+      }
+      float *spec = pb.spec + gslot * 576;          // coalesced: line i = lane + 32 j
+#pragma unroll
+      for (int j = 0; j < 18; ++j) spec[lane + 32 * j] = X[lane + 32 * j];
+      __syncwarp();
+    }
+    if (tile + 1 < n_tiles) {
+      // carry the rows of granule g_last (the next granule's overlap) and of the incomplete granule to the front
+      const int rows_have = keep + kTile;
+      const int src = 18 * g_last - row0_u;
+      const int nkeep = rows_have - src;
+      __syncthreads();
+      for (int e = tid; e < nkeep * kRowPad; e += kSp2Threads) Sb[e] = Sb[src * kRowPad + e];   // src >= 93 > nkeep: no overlap
+      keep = nkeep; row0_u = 18 * g_last; next_g = g_last + 1;
+    }
   }
 }
 
@@ -949,14 +1187,29 @@ int launch_prepass(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
 int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   if (pb.max_frames <= 0) return 0;
   static bool attr_set[64] = {};
+  static int variant = -1;
+  if (variant < 0) { const char *v = getenv("MP3B_SPECTRUM_V1"); variant = (v && v[0] == '1') ? 1 : 2; }
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 64 && !attr_set[dev]) {
     cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpecSmemBytes);
     cudaFuncSetAttribute(k_spectrum, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_spectrum2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSp2SmemBytes);
+    cudaFuncSetAttribute(k_spectrum2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set[dev] = true;
   }
-  dim3 grid(cfg.n_streams, cfg.channels, (2 * pb.max_frames + kRunGranules - 1) / kRunGranules);
-  k_spectrum<<<grid, kSteps, kSpecSmemBytes, st>>>(cfg, pb);
+  if (variant == 1) {
+    dim3 grid(cfg.n_streams, cfg.channels, (2 * pb.max_frames + kRunGranules - 1) / kRunGranules);
+    k_spectrum<<<grid, kSteps, kSpecSmemBytes, st>>>(cfg, pb);
+    return check(1);
+  }
+  // run length: 63 granules (+1 recomputed = 1152 steps = 9 full tiles) when that still gives every SM several CTAs,
+  // shorter runs for small batches
+  const int ngr = 2 * pb.max_frames;
+  int R = 63;
+  while (R > 7 && (long long)cfg.n_streams * cfg.channels * ((ngr + R - 1) / R) < 148 * 4) R = (R + 1) / 2 - 1;   // 63, 31, 15, 7
+  if (R > ngr) R = ngr;
+  dim3 grid(cfg.channels, cfg.n_streams, (ngr + R - 1) / R);
+  k_spectrum2<<<grid, kSp2Threads, kSp2SmemBytes, st>>>(cfg, pb, R);
   return check(1);
 }
 int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
