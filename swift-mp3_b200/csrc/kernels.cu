@@ -443,11 +443,11 @@ __global__ void __launch_bounds__(kSteps, 2) k_spectrum(Config cfg, PassBuffers 
 // ------------------------------------------------------------------------------------------------------------
 // K1+K2, tiled form.  Same arithmetic as k_spectrum above, operation for operation (so the same bits), reorganised so
 // that the FP32 pipe and not the shared-memory pipe is the limiter:
-//   * a CTA (4 warps) owns a run of R granules of one (stream, channel) and walks it in tiles of 128 filterbank steps;
+//   * a CTA (8 warps) owns a run of R granules of one (stream, channel) and walks it in tiles of 128 filterbank steps;
 //   * windowing: a thread owns one window phase n and slides along the steps two at a time, so every PCM sample is
 //     read from shared memory once per (n, parity) instead of once per tap; the pair (Y[n][u], Y[n][u+1]) is one FFMA2;
-//   * matrixing: a register-tiled 32 x 128 x 64 product (thread = 8 subbands x 4 steps, warp = 32 x 32): three
-//     conflict-free LDS.128 feed sixteen FFMA2; the reduction over n stays ascending, one fused multiply-add each;
+//   * matrixing: a register-tiled 32 x 128 x 64 product (thread = 4 subbands x 4 steps, warp = 32 x 16): two
+//     conflict-free LDS.128 feed eight FFMA2; the reduction over n stays ascending, one fused multiply-add each;
 //   * MDCT: warp = granule, lane = subband, straight out of the subband tile; rows that the next tile still needs
 //     (the previous granule and the incomplete one) are moved to the front of the tile;
 //   * the PCM rows of tile j+1 are fetched with cp.async while tile j is in its matrixing / MDCT phases.
@@ -455,15 +455,16 @@ constexpr int kTile = 128;                        // filterbank steps per tile
 constexpr int kPRows = kTile + kLook;             // 143 PCM rows of 32 samples, used as a ring
 constexpr int kSbKeep = 35;                       // rows carried to the next tile: previous granule + incomplete one
 constexpr int kSbRows = kTile + kSbKeep;          // 163
-constexpr int kSp2Threads = 128;
+constexpr int kSp2Threads = 256;
+constexpr int kSp2Warps = kSp2Threads / 32;
 constexpr int kSp2SmemFloats = 64 * 32 + kPRows * 32 + 64 * kTile + kSbRows * kRowPad;
 constexpr int kSp2SmemBytes = kSp2SmemFloats * 4;
 
 __global__ void __launch_bounds__(kSp2Threads, 2) k_spectrum2(Config cfg, PassBuffers pb, int R) {
   extern __shared__ __align__(16) float sm[];
-  float *sMp = sm;                                 // [64 n][4 kg][8 i] = M[kg + 4 i][n]
+  float *sMp = sm;                                 // [64 n][8 kg][4 i] = M[k0(kg) + 4 i][n], k0 = (kg & 3) + 16 (kg >> 2)
   float *P = sMp + 64 * 32;                        // [143][32] PCM rows of the tile: 15 rows of look-back + 128 new
-  float *Y = P + kPRows * 32;                      // [64 n][128 t], 16-byte chunks XOR-swizzled with n & 7; later X[4][576]
+  float *Y = P + kPRows * 32;                      // [64 n][128 t], 16-byte chunks XOR-swizzled with n & 7; later X[8][576]
   float *Sb = Y + 64 * kTile;                      // [163][33] subband samples [step][sb]
   const int c = blockIdx.x, s = blockIdx.y, run = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -483,8 +484,8 @@ __global__ void __launch_bounds__(kSp2Threads, 2) k_spectrum2(Config cfg, PassBu
   const int n_start = 576 * (g_begin - 1) - 480;
 
   for (int e = tid; e < 64 * 32; e += kSp2Threads) {
-    const int n = e >> 5, q = e & 31;
-    sMp[e] = __ldg(tab::kAnalysisT + n * 32 + (q >> 3) + 4 * (q & 7));
+    const int n = e >> 5, q = e & 31, g = q >> 2;
+    sMp[e] = __ldg(tab::kAnalysisT + n * 32 + (g & 3) + 16 * (g >> 2) + 4 * (q & 3));
   }
 
   // PCM rows [ra, rb) of the run -> ring.  Fast path: the rows are contiguous in this pass's PCM and need no mid/side
@@ -496,10 +497,10 @@ __global__ void __launch_bounds__(kSp2Threads, 2) k_spectrum2(Config cfg, PassBu
       if (!joint && rel >= 0 && rel + (int64_t)(rb - ra) * 32 * ch <= (int64_t)pv.cur_n) {
         const float *src = pv.cur + rel + (ch == 1 ? lane : 2 * lane + c);
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(P + slot0 * 32 + lane);
-        for (int r = warp; r < rb - ra; r += 4)
+        for (int r = warp; r < rb - ra; r += kSp2Warps)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + r * 128), "l"(src + (size_t)r * 32 * ch));
       } else {
-        for (int r = ra + warp; r < rb; r += 4) {
+        for (int r = ra + warp; r < rb; r += kSp2Warps) {
           const int nrow = n_start + 32 * r;
           const int64_t q = (int64_t)(nrow + 1152) * ch;
           float v;
@@ -519,14 +520,15 @@ __global__ void __launch_bounds__(kSp2Threads, 2) k_spectrum2(Config cfg, PassBu
   };
   load_rows(0, kPRows, 0);
 
-  // windowing role: n = 32 nh + lane, steps 64 seg ... 64 seg + 63 of the tile
+  // windowing role: n = 32 nh + lane, steps 32 seg ... 32 seg + 31 of the tile
   const int nh = warp & 1, seg = warp >> 1;
   float2 wc[8];                                    // (C[n + 64 i], C[n + 64 i])
 #pragma unroll
   for (int i = 0; i < 8; ++i) { const float w = __ldg(tab::kWindow + 32 * nh + lane + 64 * i); wc[i] = make_float2(w, w); }
   const float2 neg0 = make_float2(cfg.f_neg0, cfg.f_neg0), one = make_float2(cfg.f_one, cfg.f_one);
-  // matrixing role: subbands kg + 4 i, steps 32 warp + 4 tg + j of the tile
-  const int tg = lane & 7, kg = lane >> 3;
+  // matrixing role: subbands k0(kg) + 4 i, steps 16 warp + 4 tg + j of the tile
+  const int tg = lane & 3, kg = lane >> 2;
+  const int k0 = (kg & 3) + 16 * (kg >> 2);
 
   int row0_u = 0, keep = 0, next_g = 1;            // Sb row 0 holds step row0_u; rows [0, keep) are carried
   for (int tile = 0; tile < n_tiles; ++tile) {
@@ -534,13 +536,13 @@ __global__ void __launch_bounds__(kSp2Threads, 2) k_spectrum2(Config cfg, PassBu
     __syncthreads();
     // ---- windowing (SRC:1386-1399): X[n + 64 i] of step u = sample at run row u + 15 - 2 i - nh, column 31 - lane
     {
-      const float *Pc = P + (64 * seg + 1 - nh) * 32 + (31 - lane);   // oldest row of the first step pair
+      const float *Pc = P + (32 * seg + 1 - nh) * 32 + (31 - lane);   // oldest row of the first step pair
       float2 q[8];
 #pragma unroll
       for (int k = 1; k <= 7; ++k) { q[k].x = Pc[(2 * k - 2) * 32]; q[k].y = Pc[(2 * k - 1) * 32]; }
       Pc += 14 * 32;
       float *yrow = Y + (32 * nh + lane) * kTile;
-      for (int o = 0; o < 4; ++o, Pc += 16 * 32) {
+      for (int o = 0; o < 2; ++o, Pc += 16 * 32) {
         float2 ypair[8];
 #pragma unroll
         for (int ii = 0; ii < 8; ++ii) {
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(kSp2Threads, 2) k_spectrum2(Config cfg, PassBu
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          const int chunk = (16 * seg + 4 * o + h) ^ (lane & 7);
+          const int chunk = (8 * seg + 4 * o + h) ^ (lane & 7);
           *reinterpret_cast<float4 *>(yrow + 4 * chunk) = make_float4(ypair[2 * h].x, ypair[2 * h].y, ypair[2 * h + 1].x, ypair[2 * h + 1].y);
         }
       }
@@ -566,43 +568,47 @@ __global__ void __launch_bounds__(kSp2Threads, 2) k_spectrum2(Config cfg, PassBu
     if (tile + 1 < n_tiles) {
       // look-back of the next tile = last 15 rows of this one; each warp moves the rows its own cp.async is about to
       // overwrite (program order inside the warp), so no barrier is needed in between
-      for (int r = kTile + ((warp - (kTile - kLook)) & 3); r < kPRows; r += 4) P[(r - kTile) * 32 + lane] = P[r * 32 + lane];
+      for (int r = kTile + ((warp - (kTile - kLook)) & (kSp2Warps - 1)); r < kPRows; r += kSp2Warps) P[(r - kTile) * 32 + lane] = P[r * 32 + lane];
       load_rows(kTile * (tile + 1) + kLook, kTile * (tile + 2) + kLook, kLook);     // lands during matrixing + MDCT
     }
     // ---- matrixing (SRC:1402-1408): S[k] = sum over ascending n of M[k][n] * Y[n], one fused multiply-add per term
     {
-      float2 acc[4][4];
+      float2 acc[4][2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < 4; ++j) { acc[j][0] = make_float2(0.0f, 0.0f); acc[j][1] = make_float2(0.0f, 0.0f); }
+      const float4 *mrow = reinterpret_cast<const float4 *>(sMp + kg * 4);
+      const int cbase = 4 * warp + tg;
+      int yo[8];                                     // swizzled chunk offset for n & 7 = b
 #pragma unroll
-        for (int ip = 0; ip < 4; ++ip) acc[j][ip] = make_float2(0.0f, 0.0f);
-      const float4 *mrow = reinterpret_cast<const float4 *>(sMp + kg * 8);
-      const int cbase = 8 * warp + tg;
-#pragma unroll 4
-      for (int n = 0; n < 64; ++n) {
-        const float4 ma = mrow[n * 8], mb = mrow[n * 8 + 1];
-        const float4 y = *reinterpret_cast<const float4 *>(Y + n * kTile + ((cbase ^ (n & 7)) << 2));
-        const float yv[4] = {y.x, y.y, y.z, y.w};
+      for (int b = 0; b < 8; ++b) yo[b] = b * kTile + ((cbase ^ b) << 2);
+#pragma unroll 1
+      for (int a = 0; a < 8; ++a) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 yy = make_float2(yv[j], yv[j]);
-          acc[j][0] = __ffma2_rn(yy, make_float2(ma.x, ma.y), acc[j][0]);
-          acc[j][1] = __ffma2_rn(yy, make_float2(ma.z, ma.w), acc[j][1]);
-          acc[j][2] = __ffma2_rn(yy, make_float2(mb.x, mb.y), acc[j][2]);
-          acc[j][3] = __ffma2_rn(yy, make_float2(mb.z, mb.w), acc[j][3]);
+        for (int b = 0; b < 8; ++b) {
+          const int n = 8 * a + b;
+          const float4 m = mrow[n * 8];
+          const float4 y = *reinterpret_cast<const float4 *>(Y + a * 8 * kTile + yo[b]);
+          const float yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 yy = make_float2(yv[j], yv[j]);
+            acc[j][0] = __ffma2_rn(yy, make_float2(m.x, m.y), acc[j][0]);
+            acc[j][1] = __ffma2_rn(yy, make_float2(m.z, m.w), acc[j][1]);
+          }
         }
       }
-      float *dst = Sb + (keep + 32 * warp + 4 * tg) * kRowPad + kg;
+      float *dst = Sb + (keep + 16 * warp + 4 * tg) * kRowPad + k0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int ip = 0; ip < 4; ++ip) { dst[j * kRowPad + 8 * ip] = acc[j][ip].x; dst[j * kRowPad + 8 * ip + 4] = acc[j][ip].y; }
+      for (int j = 0; j < 4; ++j) {
+        dst[j * kRowPad] = acc[j][0].x; dst[j * kRowPad + 4] = acc[j][0].y;
+        dst[j * kRowPad + 8] = acc[j][1].x; dst[j * kRowPad + 12] = acc[j][1].y;
+      }
     }
     __syncthreads();
     // ---- MDCT of the granules whose 36 rows are complete (SRC:1512-1565); warp = granule, lane = subband
     const int avail_u = min(kTile * (tile + 1), U);
     const int g_last = avail_u / 18 - 1;
-    for (int gi = next_g + warp; gi <= g_last; gi += 4) {
+    for (int gi = next_g + warp; gi <= g_last; gi += kSp2Warps) {
       const int gp = g_begin + gi - 1;              // granule index inside the pass
       const int gci = gp * ch + c;
       const size_t gslot = (size_t)s * pb.GC + gci;
