@@ -141,7 +141,7 @@ void free_batch(mp3b_batch *b) {
   cudaSetDevice(b->device);
   if (b->st) cudaStreamSynchronize(b->st);
   PassBuffers &p = b->pb;
-  void *dev[] = {p.plan, p.state, b->d_head[0], b->d_head[1], p.ms, p.frame_energy, p.gc_energy, p.gc_bt, p.frame_br, p.spec, p.smag,
+  void *dev[] = {p.plan, p.state, b->d_head[0], b->d_head[1], p.ms, p.frame_energy, p.gc_energy, p.gc_bt, p.frame_br, p.spec, p.sub, p.smag,
                  p.gc_meta, p.gc_bits, p.gc_bv, p.gc_bitoff, p.gc_sel, p.fr_md, p.rec, p.emit, p.md, p.md_tail, p.md_carry, p.out,
                  p.emit_size, p.emit_n, p.tr_ix, p.tr_thr, b->d_stage[0], b->d_stage[1], b->d_plan[1], b->d_offsets, b->d_compact};
   for (void *q : dev) if (q) cudaFree(q);
@@ -191,7 +191,10 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   A(dalloc(p.plan, S)); A(dalloc(b->d_plan[1], S)); A(dalloc(p.state, S));
   A(dalloc(b->d_head[0], S * 2 * cfg.fsc)); A(dalloc(b->d_head[1], S * 2 * cfg.fsc));
   A(dalloc(p.ms, S * (Fc + 1))); A(dalloc(p.frame_energy, S * Fc)); A(dalloc(p.gc_energy, S * (10 + GC)));
-  A(dalloc(p.gc_bt, S * GC)); A(dalloc(p.frame_br, S * Fc)); A(dalloc(p.spec, S * GC * 576, false)); A(dalloc(p.smag, S * GC * 576, false));
+  A(dalloc(p.gc_bt, S * GC)); A(dalloc(p.frame_br, S * Fc)); A(dalloc(p.smag, S * GC * 576, false));
+  p.sub_rows = 18 * (1 + 2 * Fc);                                // + the carried granule in front (MDCT overlap), zero before the first frame
+  A(dalloc(p.sub, S * cfg.channels * (size_t)p.sub_rows * 32, false));
+  A(cudaMemset2D(p.sub, (size_t)p.sub_rows * 32 * sizeof(float), 0, 576 * sizeof(float), S * cfg.channels));
   A(dalloc(p.gc_meta, S * GC)); A(dalloc(p.gc_bits, S * GC * kMaxEntries)); A(dalloc(p.gc_bv, S * GC * kMaxEntries));
   A(dalloc(p.gc_bitoff, S * GC)); A(dalloc(p.gc_sel, S * GC)); A(dalloc(p.fr_md, S * Fc * 2)); A(dalloc(p.rec, S * (Fc + 1))); A(dalloc(p.emit, S * (Fc + 1)));
   p.md_stride = round_up<size_t>(kMdCarryCap + (size_t)Fc * 2 * cfg.channels * 540, 16);
@@ -233,6 +236,7 @@ int ensure_out(mp3b_batch *b, size_t stride) {
 int ensure_trace(mp3b_batch *b) {
   PassBuffers &p = b->pb;
   const size_t n = (size_t)b->S * b->GC * 576;
+  if ((b->trace & 5) && !p.spec) CU(dalloc(p.spec, n, false));      // spectrum trace / input of the threshold trace
   if ((b->trace & 2) && !p.tr_ix) CU(dalloc(p.tr_ix, n));
   if ((b->trace & 4) && !p.tr_thr) CU(dalloc(p.tr_thr, n));
   return MP3B_OK;
@@ -681,6 +685,7 @@ int mp3b_batch_reset(mp3b_batch *b) {
   CU(cudaMemsetAsync(b->pb.state, 0, S * sizeof(StreamState), b->st));
   CU(cudaMemsetAsync(b->d_head[0], 0, S * 2 * b->cfg.fsc * sizeof(float), b->st));
   CU(cudaMemsetAsync(b->d_head[1], 0, S * 2 * b->cfg.fsc * sizeof(float), b->st));
+  CU(cudaMemset2DAsync(b->pb.sub, (size_t)b->pb.sub_rows * 32 * sizeof(float), 0, 576 * sizeof(float), S * b->cfg.channels, b->st));
   CU(cudaStreamSynchronize(b->st));
   std::fill(b->pending.begin(), b->pending.end(), 0u);
   std::fill(b->out_len.begin(), b->out_len.end(), 0u);

@@ -234,23 +234,7 @@ __global__ void k_bitrate(Config cfg, PassBuffers pb) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K1+K2: polyphase filterbank (SRC:1367-1411) + MDCT / alias reduction (SRC:1512-1662) + |x|^0.75, peak -> g0
-// (SRC:989-1006), preflag (SRC:2042-2066).
-//
-// One CTA = one run of up to 15 consecutive granules of one (stream, channel); the granule in front of the run is
-// recomputed for the MDCT overlap, so 288 filterbank steps = 288 threads.  Phase A: thread = time step; its 32
-// subband accumulators live in registers and every window / matrix coefficient is an instruction immediate; the
-// only memory operands are the 512 PCM samples of the step, read from a 33-float-padded shared tile (conflict
-// free).  Phase B: warp = granule, lane = subband: 18x36 / 6x12 MDCT with immediate coefficients, butterflies through
-// shared memory.  Phase C: same warp, coalesced over the 576 lines.
-constexpr int kSteps = 18 * (kRunGranules + 1);   // 288
 constexpr int kLook = 15;                         // 480 samples of look-back = 15 rows of 32
-constexpr int kRows = kSteps + kLook;             // 303
-constexpr int kPcmPad = 34;                       // PCM tile row stride: even, so that two adjacent columns are one aligned LDS.64
-constexpr int kRowPad = 33;                       // subband tile row stride
-constexpr int kPcmFloats = (kRows * kPcmPad + 3) & ~3;   // keeps everything behind it 16-byte aligned
-constexpr int kSpecSmemFloats = 64 * 32 + 32 * 8 * 2 + kPcmFloats + kSteps * kRowPad;
-constexpr int kSpecSmemBytes = kSpecSmemFloats * 4;
 
 __device__ __forceinline__ int gain_from_peak(float peak) {      // computeGlobalGain SRC:989-1006
   if (!(peak > 0.0f)) return 210;
@@ -266,206 +250,32 @@ __device__ __forceinline__ int gain_from_peak(float peak) {      // computeGloba
   return gain > 255 ? 255 : gain;
 }
 
-__global__ void __launch_bounds__(kSteps, 2) k_spectrum(Config cfg, PassBuffers pb) {
-  extern __shared__ __align__(16) float sm[];
-  float *sM = sm;                                  // [64][32] analysis matrix, transposed: M[k][n] at n*32 + k
-  float2 *sW = reinterpret_cast<float2 *>(sM + 64 * 32);   // [32][8] window pairs (C[2p+1+64i], C[2p+64i])
-  float *P = sM + 64 * 32 + 32 * 8 * 2;            // [kRows][34] PCM tile, later X[15][576]
-  float *Sb = P + kPcmFloats;                      // [kSteps][33] subband samples [step][sb]
-  const int s = blockIdx.x, c = blockIdx.y, run = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const StreamPlan &plan = pb.plan[s];
-  const int ngr = 2 * (int)plan.n_frames;
-  const int g_begin = run * kRunGranules;
-  if (g_begin >= ngr) return;
-  const int g_cnt = min(kRunGranules, ngr - g_begin);
-  const int ch = cfg.channels;
-  const PcmView pv = pcm_view(cfg, pb, s);
-  const uint8_t *msrow = pb.ms + (size_t)s * (pb.Fc + 1);
-  const uint32_t ms_prev = pb.state[s].ms_prev;
-
-  // ---- coefficient tables -> shared memory (tiny loop body in phase A instead of 56 KB of immediates)
-  {
-    const float4 *srcm = reinterpret_cast<const float4 *>(tab::kAnalysisT), *srcw = reinterpret_cast<const float4 *>(tab::kWindowPairs);
-    float4 *dstm = reinterpret_cast<float4 *>(sM), *dstw = reinterpret_cast<float4 *>(sW);
-    for (int e = tid; e < 64 * 32 / 4; e += kSteps) dstm[e] = __ldg(srcm + e);
-    for (int e = tid; e < 32 * 8 * 2 / 4; e += kSteps) dstw[e] = __ldg(srcw + e);
-  }
-
-  // ---- stage PCM: sample n (per channel, relative to frame 0 of the pass) = n0 + 32*row + col; warp = row, lane = col.
-  // 1152 = 36 * 32 and n0 is a multiple of 32, so a row never straddles a frame: one stereo decision per row.
-  const int n0 = 576 * (g_begin - 1) - 480;
-  const int rows_needed = kLook + 18 * (g_cnt + 1);
-  const bool joint = cfg.mode == 2;
-  const int64_t rel0 = (int64_t)(n0 + 1152) * ch - (int64_t)pv.head_n;      // offset of the tile inside `cur`
-  const bool tile_in_cur = rel0 >= 0 && rel0 + (int64_t)rows_needed * 32 * ch <= (int64_t)pv.cur_n &&
-                           (ch == 1 || (reinterpret_cast<uintptr_t>(pv.cur + rel0) & 7) == 0);
-  if (tile_in_cur && !joint) {
-    // common case: the whole tile is contiguous in this pass's PCM and needs no mid/side transform: every element is
-    // one 4-byte cp.async (LDGSTS) straight into the padded tile — all rows of a warp are in flight at once, no
-    // registers, one exposed memory latency per CTA.
-    const float *src = pv.cur + rel0 + (ch == 1 ? lane : 2 * lane + c);
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(P + lane);
-    for (int r = warp; r < rows_needed; r += 9)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + r * kPcmPad * 4), "l"(src + (size_t)r * 32 * ch));
-    asm volatile("cp.async.commit_group;");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-  } else {
-    // general case: rows may come from the carried head, straddle head / cur, be zero padding, or need mid/side
-    for (int r = warp; r < rows_needed; r += 9) {
-      const int nrow = n0 + 32 * r;
-      const int64_t q = (int64_t)(nrow + 1152) * ch;
-      float v;
-      if (ch == 1) v = pv.at(q + lane);
-      else {
-        const float l = pv.at(q + 2 * lane), rr = pv.at(q + 2 * lane + 1);
-        const int fr = nrow >= 0 ? nrow / 1152 : -1;
-        const bool ms = joint && (fr < 0 ? ms_prev != 0 : msrow[1 + fr] != 0);
-        if (!ms) v = c == 0 ? l : rr;
-        else v = c == 0 ? __fmul_rn(__fadd_rn(l, rr), 0.5f) : __fmul_rn(__fsub_rn(l, rr), 0.5f);   // SRC:2148-2154
-      }
-      P[r * kPcmPad + lane] = v;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase A: filterbank step `tid` (SRC:1367-1411).  Packed FP32x2 math (FMUL2 / FADD2 / FFMA2, sm_100): two window
-  // taps n = 2p, 2p+1 share every PCM load (adjacent columns), and two subbands share every FMA instruction.  Each lane
-  // of a packed operation is an independent IEEE round-to-nearest operation, so the results are those of the scalar code.
-  if (tid < 18 * (g_cnt + 1)) {
-    float2 acc[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = make_float2(0.0f, 0.0f);
-    const float *rowp = P + (tid + kLook) * kPcmPad;
-    const float2 neg0 = make_float2(cfg.f_neg0, cfg.f_neg0), one = make_float2(cfg.f_one, cfg.f_one);
-#pragma unroll 2
-    for (int p = 0; p < 32; ++p) {
-      // X[n + 64 i] = pcm[32 s + 31 - n - 64 i]: row s - 2i (- 1 when n >= 32), column (31 - n) & 31.  Lower column <-> n + 1.
-      const float *src = rowp - (p >= 16 ? kPcmPad : 0) + ((30 - 2 * p) & 31);
-      const float2 *w = sW + p * 8;
-      float2 y;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 x = *reinterpret_cast<const float2 *>(src - 2 * i * kPcmPad);
-        // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under --fmad=false (and folds fma(x, w, -0) /
-        // fma(y, 1, z) with literal constants back into that), which would skip the rounding of the product.  Spelling
-        // both as FMAs whose constant operand is a run-time value (cfg.f_neg0 = -0.0f, cfg.f_one = 1.0f) keeps the two
-        // roundings: fma(x, w, -0) == RN(x * w) and fma(y, 1, z) == RN(y + z), bit for bit (signs of zero included).
-        const float2 z = __ffma2_rn(x, w[i], neg0);                        // SRC:1386-1389
-        y = i == 0 ? z : __ffma2_rn(y, one, z);                            // SRC:1392-1399
-      }
-      const float2 ya = make_float2(y.y, y.y), yb = make_float2(y.x, y.x);  // n = 2p, then n = 2p + 1 (ascending n)
-      const float4 *m0 = reinterpret_cast<const float4 *>(sM + (2 * p) * 32), *m1 = m0 + 8;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {                                         // SRC:1402-1408
-        const float4 m = m0[q];
-        acc[2 * q] = __ffma2_rn(ya, make_float2(m.x, m.y), acc[2 * q]);
-        acc[2 * q + 1] = __ffma2_rn(ya, make_float2(m.z, m.w), acc[2 * q + 1]);
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 m = m1[q];
-        acc[2 * q] = __ffma2_rn(yb, make_float2(m.x, m.y), acc[2 * q]);
-        acc[2 * q + 1] = __ffma2_rn(yb, make_float2(m.z, m.w), acc[2 * q + 1]);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { Sb[tid * kRowPad + 2 * k] = acc[k].x; Sb[tid * kRowPad + 2 * k + 1] = acc[k].y; }
-  }
-  __syncthreads();
-
-  // ---- phase B + C: warp per granule
-  for (int gl = warp; gl < g_cnt; gl += kSteps / 32) {
-    const int gp = g_begin + gl;                    // granule index inside the pass
-    const int gci = gp * ch + c;
-    const size_t gslot = (size_t)s * pb.GC + gci;
-    const int bt = pb.gc_bt[gslot] & 3;
-    float *X = P + gl * 576;
-    {
-      const int sb = lane;
-      const bool flip = sb & 1;
-      const float *prev = Sb + (18 * gl) * kRowPad + sb, *cur = prev + 18 * kRowPad;
-      const bool use_long = bt == 0 || (bt == 1 && sb < 2);      // SRC:1542-1553
-      if (use_long) {                                             // mdctLong SRC:1619-1636
-        float a[18];
-#pragma unroll
-        for (int m = 0; m < 18; ++m) a[m] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 36; ++k) {
-          float v = k < 18 ? prev[k * kRowPad] : cur[(k - 18) * kRowPad];
-          if (flip && (k & 1)) v = -v;                            // SRC:1520-1524
-          float w = __fmul_rn(v, tab::kWinLong[k]);
-#pragma unroll
-          for (int m = 0; m < 18; ++m) a[m] = __fmaf_rn(w, tab::kMdctLong[m][k], a[m]);
-        }
-#pragma unroll
-        for (int m = 0; m < 18; ++m) X[sb * 18 + m] = __fdiv_rn(a[m], 9.0f);
-      }
-      if (!use_long) {                                            // mdctShort SRC:1639-1662
-#pragma unroll
-        for (int w3 = 0; w3 < 3; ++w3) {
-          float seg[12];
-#pragma unroll
-          for (int i = 0; i < 12; ++i) {
-            int k = w3 * 6 + 6 + i;
-            float v = k < 18 ? prev[k * kRowPad] : cur[(k - 18) * kRowPad];
-            if (flip && (k & 1)) v = -v;
-            seg[i] = __fmul_rn(v, tab::kWinShort[i]);
-          }
-#pragma unroll
-          for (int m = 0; m < 6; ++m) {
-            float r = 0.0f;
-#pragma unroll
-            for (int k = 0; k < 12; ++k) r = __fmaf_rn(seg[k], tab::kMdctShort[m][k], r);
-            X[sb * 18 + w3 + 3 * m] = __fdiv_rn(r, 3.0f);
-          }
-        }
-      }
-      __syncwarp();
-      if (bt == 0 && sb < 31) {                                   // applyAliasingReduction SRC:1581-1616 [OD5]
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          int iu = sb * 18 + 17 - i, il = (sb + 1) * 18 + i;
-          float upper = X[iu], lower = X[il];
-          X[iu] = __fadd_rn(__fmul_rn(lower, tab::kAliasCa[i]), __fmul_rn(upper, tab::kAliasCs[i]));
-          X[il] = __fsub_rn(__fmul_rn(lower, tab::kAliasCs[i]), __fmul_rn(upper, tab::kAliasCa[i]));
-        }
-      }
-      __syncwarp();
-    }
-    // spectrum -> HBM, coalesced (line i = lane + 32 j); |x|^0.75, peak and preflag belong to k_curve
-    float *spec = pb.spec + gslot * 576;
-#pragma unroll
-    for (int j = 0; j < 18; ++j) spec[lane + 32 * j] = X[lane + 32 * j];
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------
-// K1+K2, tiled form.  Same arithmetic as k_spectrum above, operation for operation (so the same bits), reorganised so
-// that the FP32 pipe and not the shared-memory pipe is the limiter:
-//   * a CTA (8 warps) owns a run of R granules of one (stream, channel) and walks it in tiles of 128 filterbank steps;
+// K1: polyphase analysis filterbank (SRC:917-944, 1367-1411), PCM -> subband samples sub[s][c][step][32] in HBM.
+// Same arithmetic as the reference's direct form, operation for operation, organised so that the FP32 pipe and not the
+// shared-memory pipe is the limiter (tools/microbench/mb.cu holds the measurements the shapes below come from):
+//   * a CTA (4 warps) owns a run of R granules of one (stream, channel) and walks it in tiles of 256 filterbank steps;
 //   * windowing: a thread owns one window phase n and slides along the steps two at a time, so every PCM sample is
 //     read from shared memory once per (n, parity) instead of once per tap; the pair (Y[n][u], Y[n][u+1]) is one FFMA2;
-//   * matrixing: a register-tiled 32 x 128 x 64 product (thread = 4 subbands x 4 steps, warp = 32 x 16): two
-//     conflict-free LDS.128 feed eight FFMA2; the reduction over n stays ascending, one fused multiply-add each;
-//   * MDCT: warp = granule, lane = subband, straight out of the subband tile; rows that the next tile still needs
-//     (the previous granule and the incomplete one) are moved to the front of the tile;
-//   * the PCM rows of tile j+1 are fetched with cp.async while tile j is in its matrixing / MDCT phases.
-constexpr int kTile = 128;                        // filterbank steps per tile
-constexpr int kPRows = kTile + kLook;             // 143 PCM rows of 32 samples, used as a ring
-constexpr int kSbKeep = 35;                       // rows carried to the next tile: previous granule + incomplete one
-constexpr int kSbRows = kTile + kSbKeep;          // 163
-constexpr int kSp2Threads = 256;
-constexpr int kSp2Warps = kSp2Threads / 32;
-constexpr int kSp2SmemFloats = 64 * 32 + kPRows * 32 + 64 * kTile + kSbRows * kRowPad;
-constexpr int kSp2SmemBytes = kSp2SmemFloats * 4;
+//   * matrixing: a register-tiled 32 x 256 x 64 product, thread = 16 subbands x 4 steps (64 accumulators): five
+//     LDS.128 (twelve shared-memory wavefronts) feed 32 FFMA2; the reduction over n stays ascending, one fused
+//     multiply-add per term;
+//   * n is processed in two halves (window 0..31, matrix 0..31, window 32..63, matrix 32..63) so that Y is 32 KB and
+//     three CTAs fit an SM;
+//   * the PCM rows of tile j+1 are fetched with cp.async while tile j is in its second matrixing half.
+// The MDCT lives in k_granule: it is warp-local work that wants many resident warps, this kernel wants shared memory.
+constexpr int kTile = 256;                        // filterbank steps per tile
+constexpr int kPRows = kTile + kLook;             // 271 PCM rows of 32 samples: 15 rows of look-back + 256 new
+constexpr int kFbThreads = 128;
+constexpr int kFbWarps = kFbThreads / 32;
+constexpr int kFbSmemFloats = 64 * 32 + kPRows * 32 + 32 * kTile;
+constexpr int kFbSmemBytes = kFbSmemFloats * 4;
 
-__global__ void __launch_bounds__(kSp2Threads, 2) k_spectrum2(Config cfg, PassBuffers pb, int R) {
+__global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBuffers pb, int R) {
   extern __shared__ __align__(16) float sm[];
-  float *sMp = sm;                                 // [64 n][8 kg][4 i] = M[k0(kg) + 4 i][n], k0 = (kg & 3) + 16 (kg >> 2)
-  float *P = sMp + 64 * 32;                        // [143][32] PCM rows of the tile: 15 rows of look-back + 128 new
-  float *Y = P + kPRows * 32;                      // [64 n][128 t], 16-byte chunks XOR-swizzled with n & 7; later X[8][576]
-  float *Sb = Y + 64 * kTile;                      // [163][33] subband samples [step][sb]
+  float *sM = sm;                                  // [64 n][32 k] analysis matrix, transposed
+  float *P = sM + 64 * 32;                         // [271][32] PCM rows of the tile
+  float *Y = P + kPRows * 32;                      // [32 n][256 t] of the current n half, 16-byte chunks XOR-swizzled with n & 7
   const int c = blockIdx.x, s = blockIdx.y, run = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const StreamPlan &plan = pb.plan[s];
@@ -473,7 +283,7 @@ __global__ void __launch_bounds__(kSp2Threads, 2) k_spectrum2(Config cfg, PassBu
   const int g_begin = run * R;
   if (g_begin >= ngr) return;
   const int g_cnt = min(R, ngr - g_begin);
-  const int U = 18 * (g_cnt + 1);                  // steps of the run; step u = 0 opens the recomputed granule g_begin - 1
+  const int U = 18 * g_cnt;                        // steps of the run
   const int n_tiles = (U + kTile - 1) / kTile;
   const int rows_total = kLook + U;                // run row r holds samples n_start + 32 r ... + 31; step u reads rows u ... u + 15
   const int ch = cfg.channels;
@@ -481,26 +291,28 @@ __global__ void __launch_bounds__(kSp2Threads, 2) k_spectrum2(Config cfg, PassBu
   const uint8_t *msrow = pb.ms + (size_t)s * (pb.Fc + 1);
   const uint32_t ms_prev = pb.state[s].ms_prev;
   const bool joint = cfg.mode == 2;
-  const int n_start = 576 * (g_begin - 1) - 480;
+  const int n_start = 576 * g_begin - 480;
+  float *out = pb.sub + ((size_t)(s * ch + c) * pb.sub_rows + 18 * (g_begin + 1)) * 32;
 
-  for (int e = tid; e < 64 * 32; e += kSp2Threads) {
-    const int n = e >> 5, q = e & 31, g = q >> 2;
-    sMp[e] = __ldg(tab::kAnalysisT + n * 32 + (g & 3) + 16 * (g >> 2) + 4 * (q & 3));
+  {
+    const float4 *srcm = reinterpret_cast<const float4 *>(tab::kAnalysisT);
+    float4 *dstm = reinterpret_cast<float4 *>(sM);
+    for (int e = tid; e < 64 * 32 / 4; e += kFbThreads) dstm[e] = __ldg(srcm + e);
   }
 
-  // PCM rows [ra, rb) of the run -> ring.  Fast path: the rows are contiguous in this pass's PCM and need no mid/side
-  // transform: one 4-byte cp.async per sample, nothing waits until the next tile starts.
-  auto load_rows = [&](int ra, int rb, int slot0) {          // run rows [ra, rb) -> P rows slot0 ...
+  // PCM rows [ra, rb) of the run -> P rows slot0 ...  Fast path: the rows are contiguous in this pass's PCM and need no
+  // mid/side transform: one 4-byte cp.async per sample, nothing waits until the next tile starts.
+  auto load_rows = [&](int ra, int rb, int slot0) {
     rb = min(rb, rows_total);
     if (ra < rb) {
       const int64_t rel = (int64_t)(n_start + 32 * ra + 1152) * ch - (int64_t)pv.head_n;
       if (!joint && rel >= 0 && rel + (int64_t)(rb - ra) * 32 * ch <= (int64_t)pv.cur_n) {
         const float *src = pv.cur + rel + (ch == 1 ? lane : 2 * lane + c);
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(P + slot0 * 32 + lane);
-        for (int r = warp; r < rb - ra; r += kSp2Warps)
+        for (int r = warp; r < rb - ra; r += kFbWarps)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + r * 128), "l"(src + (size_t)r * 32 * ch));
       } else {
-        for (int r = ra + warp; r < rb; r += kSp2Warps) {
+        for (int r = ra + warp; r < rb; r += kFbWarps) {
           const int nrow = n_start + 32 * r;
           const int64_t q = (int64_t)(nrow + 1152) * ch;
           float v;
@@ -520,171 +332,105 @@ __global__ void __launch_bounds__(kSp2Threads, 2) k_spectrum2(Config cfg, PassBu
   };
   load_rows(0, kPRows, 0);
 
-  // windowing role: n = 32 nh + lane, steps 32 seg ... 32 seg + 31 of the tile
-  const int nh = warp & 1, seg = warp >> 1;
-  float2 wc[8];                                    // (C[n + 64 i], C[n + 64 i])
+  // windowing role: n = 32 H + lane in half H, steps 64 warp ... 64 warp + 63 of the tile
+  float wc[2][8];                                  // C[32 H + lane + 64 i]
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { const float w = __ldg(tab::kWindow + 32 * nh + lane + 64 * i); wc[i] = make_float2(w, w); }
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wc[h][i] = __ldg(tab::kWindow + 32 * h + lane + 64 * i);
   const float2 neg0 = make_float2(cfg.f_neg0, cfg.f_neg0), one = make_float2(cfg.f_one, cfg.f_one);
-  // matrixing role: subbands k0(kg) + 4 i, steps 16 warp + 4 tg + j of the tile
-  const int tg = lane & 3, kg = lane >> 2;
-  const int k0 = (kg & 3) + 16 * (kg >> 2);
+  // matrixing role: subbands 16 kg ... 16 kg + 15, steps 64 warp + 4 tg + j of the tile
+  const int tg = lane & 15, kg = lane >> 4;
+  int yo[8];                                       // XOR-swizzled chunk of this thread's four steps in row n, n & 7 = b
+#pragma unroll
+  for (int b = 0; b < 8; ++b) yo[b] = b * kTile + (((16 * warp + tg) ^ b) << 2);
 
-  int row0_u = 0, keep = 0, next_g = 1;            // Sb row 0 holds step row0_u; rows [0, keep) are carried
   for (int tile = 0; tile < n_tiles; ++tile) {
+    float2 acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[j][i] = make_float2(0.0f, 0.0f);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    // ---- windowing (SRC:1386-1399): X[n + 64 i] of step u = sample at run row u + 15 - 2 i - nh, column 31 - lane
-    {
-      const float *Pc = P + (32 * seg + 1 - nh) * 32 + (31 - lane);   // oldest row of the first step pair
-      float2 q[8];
+    const int valid = min(kTile, U - kTile * tile);
 #pragma unroll
-      for (int k = 1; k <= 7; ++k) { q[k].x = Pc[(2 * k - 2) * 32]; q[k].y = Pc[(2 * k - 1) * 32]; }
-      Pc += 14 * 32;
-      float *yrow = Y + (32 * nh + lane) * kTile;
-      for (int o = 0; o < 2; ++o, Pc += 16 * 32) {
-        float2 ypair[8];
+    for (int H = 0; H < 2; ++H) {
+      __syncthreads();                             // PCM landed (H = 0) / matrixing of the first half has read Y (H = 1)
+      // ---- windowing (SRC:1386-1399): X[n + 64 i] of step u = sample at tile row u + 15 - 2 i - H, column 31 - lane
+      if (64 * warp < valid) {                     // warp-uniform: a short last tile skips the steps beyond the run
+        const float *Pc = P + (64 * warp + 1 - H) * 32 + (31 - lane);   // oldest row of the first step pair
+        float2 q[8];
 #pragma unroll
-        for (int ii = 0; ii < 8; ++ii) {
-          q[ii].x = Pc[(2 * ii) * 32]; q[ii].y = Pc[(2 * ii + 1) * 32];
-          float2 y;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            // fma(x, w, -0) == RN(x * w) and fma(y, 1, z) == RN(y + z): two roundings, as the reference's vDSP_vmul +
-            // vDSP_sve; the constants are run-time values so that ptxas cannot contract the pair into one FFMA2.
-            const float2 z = __ffma2_rn(q[(ii - i) & 7], wc[i], neg0);
-            y = i == 0 ? z : __ffma2_rn(y, one, z);
-          }
-          ypair[ii] = y;
-        }
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int chunk = (8 * seg + 4 * o + h) ^ (lane & 7);
-          *reinterpret_cast<float4 *>(yrow + 4 * chunk) = make_float4(ypair[2 * h].x, ypair[2 * h].y, ypair[2 * h + 1].x, ypair[2 * h + 1].y);
-        }
-      }
-    }
-    __syncthreads();
-    if (tile + 1 < n_tiles) {
-      // look-back of the next tile = last 15 rows of this one; each warp moves the rows its own cp.async is about to
-      // overwrite (program order inside the warp), so no barrier is needed in between
-      for (int r = kTile + ((warp - (kTile - kLook)) & (kSp2Warps - 1)); r < kPRows; r += kSp2Warps) P[(r - kTile) * 32 + lane] = P[r * 32 + lane];
-      load_rows(kTile * (tile + 1) + kLook, kTile * (tile + 2) + kLook, kLook);     // lands during matrixing + MDCT
-    }
-    // ---- matrixing (SRC:1402-1408): S[k] = sum over ascending n of M[k][n] * Y[n], one fused multiply-add per term
-    {
-      float2 acc[4][2];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { acc[j][0] = make_float2(0.0f, 0.0f); acc[j][1] = make_float2(0.0f, 0.0f); }
-      const float4 *mrow = reinterpret_cast<const float4 *>(sMp + kg * 4);
-      const int cbase = 4 * warp + tg;
-      int yo[8];                                     // swizzled chunk offset for n & 7 = b
-#pragma unroll
-      for (int b = 0; b < 8; ++b) yo[b] = b * kTile + ((cbase ^ b) << 2);
+        for (int k = 1; k <= 7; ++k) { q[k].x = Pc[(2 * k - 2) * 32]; q[k].y = Pc[(2 * k - 1) * 32]; }
+        Pc += 14 * 32;
+        float *yrow = Y + lane * kTile;
 #pragma unroll 1
-      for (int a = 0; a < 8; ++a) {
+        for (int o = 0; o < 4; ++o, Pc += 16 * 32) {
+          float2 ypair[8];
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const int n = 8 * a + b;
-          const float4 m = mrow[n * 8];
-          const float4 y = *reinterpret_cast<const float4 *>(Y + a * 8 * kTile + yo[b]);
-          const float yv[4] = {y.x, y.y, y.z, y.w};
+          for (int ii = 0; ii < 8; ++ii) {
+            q[ii].x = Pc[(2 * ii) * 32]; q[ii].y = Pc[(2 * ii + 1) * 32];
+            float2 y;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 yy = make_float2(yv[j], yv[j]);
-            acc[j][0] = __ffma2_rn(yy, make_float2(m.x, m.y), acc[j][0]);
-            acc[j][1] = __ffma2_rn(yy, make_float2(m.z, m.w), acc[j][1]);
-          }
-        }
-      }
-      float *dst = Sb + (keep + 16 * warp + 4 * tg) * kRowPad + k0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        dst[j * kRowPad] = acc[j][0].x; dst[j * kRowPad + 4] = acc[j][0].y;
-        dst[j * kRowPad + 8] = acc[j][1].x; dst[j * kRowPad + 12] = acc[j][1].y;
-      }
-    }
-    __syncthreads();
-    // ---- MDCT of the granules whose 36 rows are complete (SRC:1512-1565); warp = granule, lane = subband
-    const int avail_u = min(kTile * (tile + 1), U);
-    const int g_last = avail_u / 18 - 1;
-    for (int gi = next_g + warp; gi <= g_last; gi += kSp2Warps) {
-      const int gp = g_begin + gi - 1;              // granule index inside the pass
-      const int gci = gp * ch + c;
-      const size_t gslot = (size_t)s * pb.GC + gci;
-      const int bt = pb.gc_bt[gslot] & 3;
-      float *X = Y + warp * 576;
-      {
-        const int sb = lane;
-        const bool flip = sb & 1;
-        const float *prev = Sb + (18 * (gi - 1) - row0_u) * kRowPad + sb, *cur = prev + 18 * kRowPad;
-        const bool use_long = bt == 0 || (bt == 1 && sb < 2);      // SRC:1542-1553
-        if (use_long) {                                             // mdctLong SRC:1619-1636
-          float a[18];
-#pragma unroll
-          for (int m = 0; m < 18; ++m) a[m] = 0.0f;
-#pragma unroll
-          for (int k = 0; k < 36; ++k) {
-            float v = k < 18 ? prev[k * kRowPad] : cur[(k - 18) * kRowPad];
-            if (flip && (k & 1)) v = -v;                            // SRC:1520-1524
-            float w = __fmul_rn(v, tab::kWinLong[k]);
-#pragma unroll
-            for (int m = 0; m < 18; ++m) a[m] = __fmaf_rn(w, tab::kMdctLong[m][k], a[m]);
-          }
-#pragma unroll
-          for (int m = 0; m < 18; ++m) X[sb * 18 + m] = __fdiv_rn(a[m], 9.0f);
-        }
-        if (!use_long) {                                            // mdctShort SRC:1639-1662
-#pragma unroll
-          for (int w3 = 0; w3 < 3; ++w3) {
-            float sg[12];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) {
-              int k = w3 * 6 + 6 + i;
-              float v = k < 18 ? prev[k * kRowPad] : cur[(k - 18) * kRowPad];
-              if (flip && (k & 1)) v = -v;
-              sg[i] = __fmul_rn(v, tab::kWinShort[i]);
+            for (int i = 0; i < 8; ++i) {
+              // fma(x, w, -0) == RN(x * w) and fma(y, 1, z) == RN(y + z): two roundings, as the reference's vDSP_vmul +
+              // vDSP_sve; the constants are run-time values so that ptxas cannot contract the pair into one FFMA2.
+              const float2 z = __ffma2_rn(q[(ii - i) & 7], make_float2(wc[H][i], wc[H][i]), neg0);
+              y = i == 0 ? z : __ffma2_rn(y, one, z);
             }
+            ypair[ii] = y;
+          }
 #pragma unroll
-            for (int m = 0; m < 6; ++m) {
-              float r = 0.0f;
-#pragma unroll
-              for (int k = 0; k < 12; ++k) r = __fmaf_rn(sg[k], tab::kMdctShort[m][k], r);
-              X[sb * 18 + w3 + 3 * m] = __fdiv_rn(r, 3.0f);
-            }
+          for (int h = 0; h < 4; ++h) {
+            const int chunk = (16 * warp + 4 * o + h) ^ (lane & 7);
+            *reinterpret_cast<float4 *>(yrow + 4 * chunk) = make_float4(ypair[2 * h].x, ypair[2 * h].y, ypair[2 * h + 1].x, ypair[2 * h + 1].y);
           }
         }
-        __syncwarp();
-        if (bt == 0 && sb < 31) {                                   // applyAliasingReduction SRC:1581-1616 [OD5]
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            int iu = sb * 18 + 17 - i, il = (sb + 1) * 18 + i;
-            float upper = X[iu], lower = X[il];
-            X[iu] = __fadd_rn(__fmul_rn(lower, tab::kAliasCa[i]), __fmul_rn(upper, tab::kAliasCs[i]));
-            X[il] = __fsub_rn(__fmul_rn(lower, tab::kAliasCs[i]), __fmul_rn(upper, tab::kAliasCa[i]));
-          }
-        }
-        __syncwarp();
       }
-      float *spec = pb.spec + gslot * 576;          // coalesced: line i = lane + 32 j
-#pragma unroll
-      for (int j = 0; j < 18; ++j) spec[lane + 32 * j] = X[lane + 32 * j];
-      __syncwarp();
-    }
-    if (tile + 1 < n_tiles) {
-      // carry the rows of granule g_last (the next granule's overlap) and of the incomplete granule to the front
-      const int rows_have = keep + kTile;
-      const int src = 18 * g_last - row0_u;
-      const int nkeep = rows_have - src;
       __syncthreads();
-      for (int e = tid; e < nkeep * kRowPad; e += kSp2Threads) Sb[e] = Sb[src * kRowPad + e];   // src >= 93 > nkeep: no overlap
-      keep = nkeep; row0_u = 18 * g_last; next_g = g_last + 1;
+      if (H == 1 && tile + 1 < n_tiles) {
+        // look-back of the next tile = last 15 rows of this one; each warp moves the rows its own cp.async is about to
+        // overwrite (program order inside the warp), so no barrier is needed in between
+        for (int r = kTile + ((warp - (kTile - kLook)) & (kFbWarps - 1)); r < kPRows; r += kFbWarps) P[(r - kTile) * 32 + lane] = P[r * 32 + lane];
+        load_rows(kTile * (tile + 1) + kLook, kTile * (tile + 2) + kLook, kLook);     // lands during the matrixing
+      }
+      // ---- matrixing (SRC:1402-1408): S[k] = sum over ascending n of M[k][n] * Y[n], one fused multiply-add per term
+      if (64 * warp < valid) {
+        const float4 *mrow = reinterpret_cast<const float4 *>(sM + (32 * H) * 32 + kg * 16);
+#pragma unroll 1
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            const int nl = 8 * a + b;
+            const float4 m0 = mrow[nl * 8], m1 = mrow[nl * 8 + 1], m2 = mrow[nl * 8 + 2], m3 = mrow[nl * 8 + 3];
+            const float4 y = *reinterpret_cast<const float4 *>(Y + a * 8 * kTile + yo[b]);
+            const float yv[4] = {y.x, y.y, y.z, y.w};
+            const float mv[16] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w, m3.x, m3.y, m3.z, m3.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[j][i] = __ffma2_rn(make_float2(yv[j], yv[j]), make_float2(mv[2 * i], mv[2 * i + 1]), acc[j][i]);
+          }
+        }
+      }
+    }
+    // subband samples -> HBM: step row = 32 floats, this thread owns 16 of them for four consecutive steps
+    {
+      const int t0 = 64 * warp + 4 * tg;
+      float4 *dst = reinterpret_cast<float4 *>(out + (size_t)(kTile * tile + t0) * 32 + 16 * kg);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (t0 + j < valid) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[j * 8 + i] = make_float4(acc[j][2 * i].x, acc[j][2 * i].y, acc[j][2 * i + 1].x, acc[j][2 * i + 1].y);
+        }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K4: bits-vs-gain curve of quantizeToFitBudget (SRC:734-794).  One warp per gc.  The loop's gain sequence does not
+// K2+K4: MDCT / alias reduction (SRC:1512-1662), then the bits-vs-gain curve of quantizeToFitBudget (SRC:734-794).
+// One warp per gc, everything between the subband samples and the curve stays in the warp.  The loop's gain sequence does not
 // depend on maxBits (only where it stops does), so the warp evaluates it until the bit count fits the smallest
 // budget the frame can have (no reservoir, no padding) or the loop's own exits fire; the serial scan (K_scan) then
 // only looks entries up.
@@ -692,7 +438,7 @@ __device__ __forceinline__ int lo_bits_of(const Config &cfg, int bri) {
   return ((cfg.frame_base[bri] - cfg.header_bytes) * 8) / (2 * cfg.channels);
 }
 
-__global__ void __launch_bounds__(256) k_curve(Config cfg, PassBuffers pb) {
+__global__ void __launch_bounds__(256) k_granule(Config cfg, PassBuffers pb) {
   __shared__ uint8_t len15[256];
   __shared__ __align__(8) float smg[8][576];
   len15[threadIdx.x] = c_len15[threadIdx.x];
@@ -704,13 +450,78 @@ __global__ void __launch_bounds__(256) k_curve(Config cfg, PassBuffers pb) {
   const size_t gslot = (size_t)s * pb.GC + gci;
   const int f = gci / (2 * ch);
   const int lo_bits = lo_bits_of(cfg, pb.frame_br[(size_t)s * pb.Fc + f]);
+  // ---- MDCT (SRC:1512-1565): lane = subband; the 36 time samples are the previous and the current granule's rows of
+  // the subband array (row 18 (g + 1) + t = step t of granule g; rows 0..17 = last granule of the previous pass)
+  {
+    const int g = gci / ch, c = gci - g * ch;
+    const int bt = pb.gc_bt[gslot] & 3;
+    const float *prev = pb.sub + ((size_t)(s * ch + c) * pb.sub_rows + 18 * g) * 32 + lane;
+    float *X = smg[warp];
+    const int sb = lane;
+    const bool flip = sb & 1;
+    float v[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) v[k] = __ldg(prev + k * 32);
+    const bool use_long = bt == 0 || (bt == 1 && sb < 2);      // SRC:1542-1553
+    if (use_long) {                                             // mdctLong SRC:1619-1636
+      float a[18];
+#pragma unroll
+      for (int m = 0; m < 18; ++m) a[m] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 36; ++k) {
+        float x = v[k];
+        if (flip && (k & 1)) x = -x;                            // SRC:1520-1524
+        float w = __fmul_rn(x, tab::kWinLong[k]);
+#pragma unroll
+        for (int m = 0; m < 18; ++m) a[m] = __fmaf_rn(w, tab::kMdctLong[m][k], a[m]);
+      }
+#pragma unroll
+      for (int m = 0; m < 18; ++m) X[sb * 18 + m] = __fdiv_rn(a[m], 9.0f);
+    }
+    if (!use_long) {                                            // mdctShort SRC:1639-1662
+#pragma unroll
+      for (int w3 = 0; w3 < 3; ++w3) {
+        float sg[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const int k = w3 * 6 + 6 + i;
+          float x = v[k];
+          if (flip && (k & 1)) x = -x;
+          sg[i] = __fmul_rn(x, tab::kWinShort[i]);
+        }
+#pragma unroll
+        for (int m = 0; m < 6; ++m) {
+          float r = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) r = __fmaf_rn(sg[k], tab::kMdctShort[m][k], r);
+          X[sb * 18 + w3 + 3 * m] = __fdiv_rn(r, 3.0f);
+        }
+      }
+    }
+    __syncwarp();
+    if (bt == 0 && sb < 31) {                                   // applyAliasingReduction SRC:1581-1616 [OD5]
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int iu = sb * 18 + 17 - i, il = (sb + 1) * 18 + i;
+        float upper = X[iu], lower = X[il];
+        X[iu] = __fadd_rn(__fmul_rn(lower, tab::kAliasCa[i]), __fmul_rn(upper, tab::kAliasCs[i]));
+        X[il] = __fsub_rn(__fmul_rn(lower, tab::kAliasCs[i]), __fmul_rn(upper, tab::kAliasCa[i]));
+      }
+    }
+    __syncwarp();
+  }
   // |x|^0.75 (SRC:805-813 [OD3]), peak -> g0 (SRC:989-1006), preflag (SRC:2042-2066); line i = lane + 32 j
   {
-    const float *spec = pb.spec + gslot * 576;
+    float *spec = pb.spec ? pb.spec + gslot * 576 : nullptr;   // trace plane only
     float *smag = pb.smag + gslot * 576;
     float x[18];
 #pragma unroll
-    for (int j = 0; j < 18; ++j) x[j] = __ldg(spec + lane + 32 * j);
+    for (int j = 0; j < 18; ++j) x[j] = smg[warp][lane + 32 * j];
+    __syncwarp();
+    if (spec) {
+#pragma unroll
+      for (int j = 0; j < 18; ++j) spec[lane + 32 * j] = x[j];
+    }
     float peak = 0.0f, plo = 0.0f, phi = 0.0f;
 #pragma unroll
     for (int j = 0; j < 18; ++j) {
@@ -1093,6 +904,14 @@ __global__ void __launch_bounds__(256) k_carry(Config cfg, PassBuffers pb) {
   for (uint32_t i = tid; i < len; i += 256) { uint32_t o = R + i; tail[i] = o < B0 ? carry[o] : md[o]; }
   __syncthreads();
   for (uint32_t i = tid; i < len; i += 256) carry[i] = tail[i];
+  // MDCT overlap (SRC:1534-1535): the last granule's subband rows become rows 0..17 of the next pass
+  if (plan.n_frames) {
+    const int ngr = 2 * (int)plan.n_frames;
+    for (int c = 0; c < cfg.channels; ++c) {
+      float *base = pb.sub + (size_t)(s * cfg.channels + c) * pb.sub_rows * 32;
+      for (int i = tid; i < 576; i += 256) base[i] = base[(size_t)18 * ngr * 32 + i];
+    }
+  }
   StreamState &st = pb.state[s];
   const int ngc = (int)plan.n_frames * 2 * cfg.channels;
   if (tid == 0 && plan.n_frames) {
@@ -1193,35 +1012,26 @@ int launch_prepass(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
 int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   if (pb.max_frames <= 0) return 0;
   static bool attr_set[64] = {};
-  static int variant = -1;
-  if (variant < 0) { const char *v = getenv("MP3B_SPECTRUM_V1"); variant = (v && v[0] == '1') ? 1 : 2; }
   int dev = 0; cudaGetDevice(&dev);
   if (dev < 64 && !attr_set[dev]) {
-    cudaFuncSetAttribute(k_spectrum, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpecSmemBytes);
-    cudaFuncSetAttribute(k_spectrum, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_spectrum2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSp2SmemBytes);
-    cudaFuncSetAttribute(k_spectrum2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_filterbank, cudaFuncAttributeMaxDynamicSharedMemorySize, kFbSmemBytes);
+    cudaFuncSetAttribute(k_filterbank, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set[dev] = true;
   }
-  if (variant == 1) {
-    dim3 grid(cfg.n_streams, cfg.channels, (2 * pb.max_frames + kRunGranules - 1) / kRunGranules);
-    k_spectrum<<<grid, kSteps, kSpecSmemBytes, st>>>(cfg, pb);
-    return check(1);
-  }
-  // run length: 63 granules (+1 recomputed = 1152 steps = 9 full tiles) when that still gives every SM several CTAs,
-  // shorter runs for small batches
+  // run length: 128 granules (2304 steps = 9 full tiles) when that still gives every SM several CTAs, shorter runs for
+  // small batches (64 -> 4.5 tiles, 28 -> 1.97, 14 -> 0.98)
   const int ngr = 2 * pb.max_frames;
-  int R = 63;
-  while (R > 7 && (long long)cfg.n_streams * cfg.channels * ((ngr + R - 1) / R) < 148 * 4) R = (R + 1) / 2 - 1;   // 63, 31, 15, 7
+  int R = 128;
+  while (R > 14 && (long long)cfg.n_streams * cfg.channels * ((ngr + R - 1) / R) < 148 * 6) R = R > 64 ? 64 : R > 28 ? 28 : 14;
   if (R > ngr) R = ngr;
   dim3 grid(cfg.channels, cfg.n_streams, (ngr + R - 1) / R);
-  k_spectrum2<<<grid, kSp2Threads, kSp2SmemBytes, st>>>(cfg, pb, R);
+  k_filterbank<<<grid, kFbThreads, kFbSmemBytes, st>>>(cfg, pb, R);
   return check(1);
 }
 int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   if (pb.max_frames <= 0) return 0;
   dim3 grid(cfg.n_streams, (pb.max_frames * 2 * cfg.channels + 7) / 8);
-  k_curve<<<grid, 256, 0, st>>>(cfg, pb);
+  k_granule<<<grid, 256, 0, st>>>(cfg, pb);
   return check(1);
 }
 int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {

@@ -14,7 +14,6 @@ namespace mp3b {
 
 constexpr int kMaxEntries = 20;     // gain-loop iterations, SRC:745
 constexpr int kMdCarryCap = 8192;   // bytes of reservoir backlog that may cross a pass boundary
-constexpr int kRunGranules = 15;    // granules per spectrum block (+1 recomputed for the MDCT overlap)
 
 struct Config {              // constant for the lifetime of a batch; passed to kernels by value
   int n_streams, channels, fsc /* floats per frame = 1152*channels */;
@@ -83,7 +82,10 @@ struct PassBuffers {         // device arrays for one pass; Fc = frame capacity 
   float *gc_energy;          // [S][10 + GC]  (first 10 = carried history, right aligned)
   uint16_t *gc_bt;           // [S][GC] block_type | sbg0<<2 | sbg1<<5 | sbg2<<8
   uint8_t *frame_br;         // [S][Fc] bitrate index
-  float *spec;               // [S][GC][576] MDCT spectrum (K1+K2 output)
+  float *sub;                // [S][ch][sub_rows][32] subband samples (K1 output): row 18 (g + 1) + t = step t of granule g,
+                             // rows 0..17 = last granule of the previous pass (the MDCT overlap, SRC:1534-1535)
+  int sub_rows;              // 18 * (1 + 2 * Fc)
+  float *spec;               // [S][GC][576] MDCT spectrum — trace plane only (nullptr otherwise)
   float *smag;               // [S][GC][576] sign(x) * |x|^0.75 (K4 output, K5 input)
   uint32_t *gc_meta;         // [S][GC] g0 | n_entries<<8 | restart<<16 | preflag<<17
   uint16_t *gc_bits;         // [S][GC][20]
