@@ -59,7 +59,8 @@ struct mp3b_batch {
   float *d_stage[2] = {nullptr, nullptr}; size_t stage_stride = 0;   // double-buffered PCM staging, floats per stream
   StreamPlan *h_plan = nullptr;                          // pinned [2][S]
   StreamPlan *d_plan[2] = {nullptr, nullptr};
-  cudaStream_t st_copy = nullptr;
+  cudaStream_t st_copy = nullptr, st_d2h = nullptr;
+  size_t h_pitch = 0;                                    // > 0: h_out is [S][h_pitch] (progressive download), else compact at h_offsets
   cudaEvent_t ev_h2d[2][2] = {}, ev_consumed[2] = {};
   StreamState *h_state = nullptr;                        // pinned [S]
   uint16_t *h_emit_size = nullptr; uint32_t *h_emit_n = nullptr;
@@ -152,6 +153,7 @@ void free_batch(mp3b_batch *b) {
   for (auto &r : b->ev_h2d) for (auto &e : r) if (e) cudaEventDestroy(e);
   if (b->st) cudaStreamDestroy(b->st);
   if (b->st_copy) cudaStreamDestroy(b->st_copy);
+  if (b->st_d2h) cudaStreamDestroy(b->st_d2h);
   cudaGetLastError();
   delete b;
 }
@@ -188,6 +190,7 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   A(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
   A(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
+  A(cudaStreamCreateWithFlags(&b->st_d2h, cudaStreamNonBlocking));
   A(dalloc(p.plan, S)); A(dalloc(b->d_plan[1], S)); A(dalloc(p.state, S));
   A(dalloc(b->d_head[0], S * 2 * cfg.fsc)); A(dalloc(b->d_head[1], S * 2 * cfg.fsc));
   A(dalloc(p.ms, S * (Fc + 1))); A(dalloc(p.frame_energy, S * Fc)); A(dalloc(p.gc_energy, S * (10 + GC)));
@@ -261,6 +264,24 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
   }
   int rc = ensure_out(b, (max_frames + 1) * (size_t)b->max_frame_bytes);
   if (rc) return rc;
+  // Host input is bound by PCIe, so the call is cut into about a dozen passes: the kernels and the download of pass p hide
+  // behind the upload of pass p + 1 and only the last pass is exposed.  Device input keeps the largest passes.
+  const int Fp = device_ptrs ? Fc : (int)std::min<size_t>((size_t)Fc, std::max<size_t>((max_frames + 11) / 12, (size_t)std::min(Fc, 48)));
+  // progressive download: after every pass the byte columns that pass produced are copied for all streams with one
+  // strided D2H on its own stream into a pitched pinned buffer [S][out_stride]
+  bool progressive = download && !device_ptrs && max_frames > (size_t)Fp;   // single-pass calls keep the compact copy
+  std::vector<uint32_t> opos;
+  if (progressive) {
+    const size_t need = (size_t)S * b->pb.out_stride;
+    if (need > b->h_out_cap) {
+      if (b->h_out) cudaFreeHost(b->h_out);
+      b->h_out = nullptr; b->h_out_cap = 0;
+      CU(cudaHostAlloc((void **)&b->h_out, need, cudaHostAllocDefault));
+      b->h_out_cap = need;
+    }
+    opos.assign(S, 0);
+  }
+  b->h_pitch = 0;
   if (b->trace) { rc = ensure_trace(b); if (rc) return rc; }
   if (!device_ptrs && !b->d_stage[0]) {
     b->stage_stride = (size_t)Fc * fsc;
@@ -284,7 +305,7 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
     for (int s = 0; s < S; ++s) {
       StreamPlan &pl = hp[s];
       size_t remaining = n[s] - cursor[s];
-      size_t room = (size_t)Fc * fsc - b->pending[s];
+      size_t room = (size_t)Fp * fsc - b->pending[s];
       size_t cur_n = std::min(remaining, room);
       size_t total = b->pending[s] + cur_n;
       uint32_t nfr = (uint32_t)(total / fsc), flags = first_plan ? 4u : 0u;
@@ -389,10 +410,21 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
       { float ms = 0; cudaEventElapsedTime(&ms, b->ev_h2d[slot][0], b->ev_h2d[slot][1]); b->stage_ms[MP3B_STAGE_H2D] += ms; }
       float ms = 0; cudaEventElapsedTime(&ms, b->ev[0], b->ev[7]); b->stage_ms[MP3B_STAGE_TOTAL] += ms;
     }
+    size_t cmin = SIZE_MAX, cmax = 0, useful = 0;
     for (int s = 0; s < S; ++s) {
       uint32_t ne = b->h_emit_n[s];
       const uint16_t *sz = b->h_emit_size + (size_t)s * (Fc + 1);
       if (ne) b->frame_sizes[s].insert(b->frame_sizes[s].end(), sz, sz + ne);
+      if (progressive && ne) {
+        uint32_t add = 0;
+        for (uint32_t k = 0; k < ne; ++k) add += sz[k];
+        cmin = std::min<size_t>(cmin, opos[s]); opos[s] += add; cmax = std::max<size_t>(cmax, opos[s]); useful += add;
+      }
+    }
+    if (progressive && useful) {
+      cmin &= ~(size_t)15; cmax = std::min(round_up<size_t>(cmax, 16), pb.out_stride);
+      if ((cmax - cmin) * (size_t)S > 3 * useful + (1u << 20)) progressive = false;   // ragged batch: one compact copy at the end instead
+      else CU(cudaMemcpy2DAsync(b->h_out + cmin, pb.out_stride, pb.out + cmin, pb.out_stride, cmax - cmin, S, cudaMemcpyDeviceToHost, b->st_d2h));
     }
     if (b->trace) {
       const int ngc = 2 * cfg.channels;
@@ -442,7 +474,12 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
   b->out_total = 0;
   for (int s = 0; s < S; ++s) b->out_total += b->out_len[s];
   if (err) { b->sticky = MP3B_ERR_INTERNAL; return fail(MP3B_ERR_INTERNAL, "engine limit exceeded (flags 0x%x: 1 curve, 2 main-data buffer, 4 output buffer, 8 backlog > %d bytes)", err, kMdCarryCap); }
-  if (download) {
+  if (progressive) {
+    CU(cudaStreamSynchronize(b->st_d2h));
+    b->h_pitch = b->pb.out_stride;
+    b->have_host_out = true;
+  } else if (download) {
+    CU(cudaStreamSynchronize(b->st_d2h));                 // a progressive attempt may still be copying into h_out
     const size_t total = (size_t)b->h_offsets[S];
     if (total > b->compact_cap) {
       if (b->d_compact) cudaFree(b->d_compact);
@@ -549,7 +586,7 @@ int mp3b_batch_encode_device(mp3b_batch *b, const float *const *d_pcm, const siz
 int mp3b_batch_output(const mp3b_batch *b, int stream, const uint8_t **data, size_t *len) {
   if (!b || stream < 0 || stream >= b->S || !data || !len) return fail(MP3B_ERR_BAD_ARG, "bad stream index or null pointer");
   if (!b->have_host_out) return fail(MP3B_ERR_BAD_ARG, "the last call did not download its output");
-  *data = b->h_out ? b->h_out + b->h_offsets[stream] : nullptr; *len = b->out_len[stream];
+  *data = b->h_out ? b->h_out + (b->h_pitch ? (size_t)stream * b->h_pitch : (size_t)b->h_offsets[stream]) : nullptr; *len = b->out_len[stream];
   return MP3B_OK;
 }
 int mp3b_batch_output_device(const mp3b_batch *b, int stream, const uint8_t **d_data, size_t *len) {

@@ -294,12 +294,6 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
   const int n_start = 576 * g_begin - 480;
   float *out = pb.sub + ((size_t)(s * ch + c) * pb.sub_rows + 18 * (g_begin + 1)) * 32;
 
-  {
-    const float4 *srcm = reinterpret_cast<const float4 *>(tab::kAnalysisT);
-    float4 *dstm = reinterpret_cast<float4 *>(sM);
-    for (int e = tid; e < 64 * 32 / 4; e += kFbThreads) dstm[e] = __ldg(srcm + e);
-  }
-
   // PCM rows [ra, rb) of the run -> P rows slot0 ...  Fast path: the rows are contiguous in this pass's PCM and need no
   // mid/side transform: one 4-byte cp.async per sample, nothing waits until the next tile starts.
   auto load_rows = [&](int ra, int rb, int slot0) {
@@ -307,10 +301,11 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
     if (ra < rb) {
       const int64_t rel = (int64_t)(n_start + 32 * ra + 1152) * ch - (int64_t)pv.head_n;
       if (!joint && rel >= 0 && rel + (int64_t)(rb - ra) * 32 * ch <= (int64_t)pv.cur_n) {
-        const float *src = pv.cur + rel + (ch == 1 ? lane : 2 * lane + c);
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(P + slot0 * 32 + lane);
-        for (int r = warp; r < rb - ra; r += kFbWarps)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + r * 128), "l"(src + (size_t)r * 32 * ch));
+        const float *src = pv.cur + rel + (ch == 1 ? lane : 2 * lane + c) + (size_t)warp * 32 * ch;
+        uint32_t dst = (uint32_t)__cvta_generic_to_shared(P + (slot0 + warp) * 32 + lane);
+        const int step = kFbWarps * 32 * ch;
+        for (int r = warp; r < rb - ra; r += kFbWarps, src += step, dst += kFbWarps * 128)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src));
       } else {
         for (int r = ra + warp; r < rb; r += kFbWarps) {
           const int nrow = n_start + 32 * r;
@@ -331,6 +326,12 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
     asm volatile("cp.async.commit_group;");
   };
   load_rows(0, kPRows, 0);
+  {                                                // analysis matrix -> shared memory, asynchronously as well
+    const uint32_t dstm = (uint32_t)__cvta_generic_to_shared(sM);
+    for (int e = tid; e < 64 * 32 / 4; e += kFbThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstm + e * 16), "l"(tab::kAnalysisT + e * 4));
+    asm volatile("cp.async.commit_group;");
+  }
 
   // windowing role: n = 32 H + lane in half H, steps 64 warp ... 64 warp + 63 of the tile
   float wc[2][8];                                  // C[32 H + lane + 64 i]
@@ -355,7 +356,9 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
     const int valid = min(kTile, U - kTile * tile);
 #pragma unroll
     for (int H = 0; H < 2; ++H) {
-      __syncthreads();                             // PCM landed (H = 0) / matrixing of the first half has read Y (H = 1)
+      // A warp windows and matrixes the same 64 steps, so its part of Y is private: warp-level ordering is enough
+      // between the phases.  Block-wide barriers only guard P: its arrival here, its reuse after the last windowing.
+      if (H == 0) __syncthreads(); else __syncwarp();
       // ---- windowing (SRC:1386-1399): X[n + 64 i] of step u = sample at tile row u + 15 - 2 i - H, column 31 - lane
       if (64 * warp < valid) {                     // warp-uniform: a short last tile skips the steps beyond the run
         const float *Pc = P + (64 * warp + 1 - H) * 32 + (31 - lane);   // oldest row of the first step pair
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
           }
         }
       }
-      __syncthreads();
+      if (H == 0) __syncwarp(); else __syncthreads();
       if (H == 1 && tile + 1 < n_tiles) {
         // look-back of the next tile = last 15 rows of this one; each warp moves the rows its own cp.async is about to
         // overwrite (program order inside the warp), so no barrier is needed in between
