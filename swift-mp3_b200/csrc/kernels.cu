@@ -87,11 +87,19 @@ __device__ __forceinline__ float pow34(float a) {
 }
 
 // quantizeWithGain SRC:816-821: min(Int32(roundf(mag * inv)), 15); roundf = ties away from zero [OD4].
-__device__ __forceinline__ int quant15(float mag, float inv) {
-  float t = fminf(__fmul_rn(mag, inv), 16.0f);
-  float r = truncf(t);
-  int q = (int)r + (__fsub_rn(t, r) >= 0.5f ? 1 : 0);
+// inv2 = 2 * inv: scaling by two commutes with the rounding of the product (no overflow / underflow at these
+// magnitudes), so floor(RN(mag * inv2)) = floor(2 t) with t = RN(mag * inv), and roundf(t) = (floor(2 t) + 1) >> 1, t >= 0.
+__device__ __forceinline__ int quant15(float mag, float inv2) {
+  const int q = (__float2int_rd(__fmul_rn(mag, inv2)) + 1) >> 1;
   return q > 15 ? 15 : q;
+}
+
+// a / d correctly rounded for d = 9 and d = 3 (r = RN(1 / d)): quotient estimate, exact residual, one correction.
+// tools/check_div.c compares it with the IEEE division for all 2^32 floats (signed zeros and denormals included).
+__device__ __forceinline__ float div_exact(float a, float d, float r) {
+  const float q = __fmul_rn(a, r);
+  const float e = __fmaf_rn(d, q, -a);
+  return __fmaf_rn(-e, r, q);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -442,9 +450,9 @@ __device__ __forceinline__ int lo_bits_of(const Config &cfg, int bri) {
 }
 
 __global__ void __launch_bounds__(256) k_granule(Config cfg, PassBuffers pb) {
-  __shared__ uint8_t len15[256];
+  __shared__ uint8_t len15[256];                  // table-15 code length of a pair + its sign bits (SRC:828-853)
   __shared__ __align__(8) float smg[8][576];
-  len15[threadIdx.x] = c_len15[threadIdx.x];
+  len15[threadIdx.x] = c_len15[threadIdx.x] + ((threadIdx.x >> 4) != 0) + ((threadIdx.x & 15) != 0);
   __syncthreads();
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gci = blockIdx.y * 8 + warp;
@@ -479,7 +487,7 @@ __global__ void __launch_bounds__(256) k_granule(Config cfg, PassBuffers pb) {
         for (int m = 0; m < 18; ++m) a[m] = __fmaf_rn(w, tab::kMdctLong[m][k], a[m]);
       }
 #pragma unroll
-      for (int m = 0; m < 18; ++m) X[sb * 18 + m] = __fdiv_rn(a[m], 9.0f);
+      for (int m = 0; m < 18; ++m) X[sb * 18 + m] = div_exact(a[m], 9.0f, 1.0f / 9.0f);
     }
     if (!use_long) {                                            // mdctShort SRC:1639-1662
 #pragma unroll
@@ -497,7 +505,7 @@ __global__ void __launch_bounds__(256) k_granule(Config cfg, PassBuffers pb) {
           float r = 0.0f;
 #pragma unroll
           for (int k = 0; k < 12; ++k) r = __fmaf_rn(sg[k], tab::kMdctShort[m][k], r);
-          X[sb * 18 + w3 + 3 * m] = __fdiv_rn(r, 3.0f);
+          X[sb * 18 + w3 + 3 * m] = div_exact(r, 3.0f, 1.0f / 3.0f);
         }
       }
     }
@@ -555,13 +563,13 @@ __global__ void __launch_bounds__(256) k_granule(Config cfg, PassBuffers pb) {
   int gain = g0, n = 0, restart = 0;
   uint16_t *bits_out = pb.gc_bits + gslot * kMaxEntries, *bv_out = pb.gc_bv + gslot * kMaxEntries;
   for (int it = 0; it < kMaxEntries; ++it) {
-    const float inv = c_inv_step[gain];
+    const float inv2 = __fmul_rn(c_inv_step[gain], 2.0f);
     int total = 0, last = 0;
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
-      int qx = quant15(mx[j], inv), qy = quant15(my[j], inv);
-      total += len15[qx * 16 + qy] + (qx != 0) + (qy != 0);
-      if (qx | qy) last = lane + 32 * j + 1;
+      const int idx = quant15(mx[j], inv2) * 16 + quant15(my[j], inv2);
+      total += len15[idx];
+      if (idx) last = lane + 32 * j + 1;
     }
     const int bv = warp_max_i(last);                 // pairs up to and including the last non-zero one, SRC:750-763
     const int bits = warp_sum_i(total) - 3 * (288 - bv);   // all-zero pairs beyond big_values are not coded (len15[0][0] = 3)
@@ -781,7 +789,7 @@ __global__ void __launch_bounds__(128) k_pack(Config cfg, PassBuffers pb) {
     const size_t gslot = (size_t)s * pb.GC + gci;
     const uint32_t sel = pb.gc_sel[gslot];
     const int gain = sel & 255, bv = sel >> 8;
-    const float inv = c_inv_step[gain];
+    const float inv = __fmul_rn(c_inv_step[gain], 2.0f);
     const float2 *sm2 = reinterpret_cast<const float2 *>(pb.smag + gslot * 576);
     int32_t *trix = pb.tr_ix ? pb.tr_ix + gslot * 576 : nullptr;
     uint32_t val[9]; int len[9]; int mine = 0;
