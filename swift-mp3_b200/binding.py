@@ -93,6 +93,7 @@ def lib():
         "mp3b_batch_trace_gc_array": (i32, [vp, i32, i32, vp, i32]),
         "mp3b_table": (i32, [i32, vp, sz]),
         "mp3b_synth_fill": (i32, [i32, vp, sz, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint64]),
+        "mp3b_selftest": (i32, [i32, C.POINTER(C.c_uint64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

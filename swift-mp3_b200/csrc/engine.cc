@@ -795,4 +795,21 @@ int mp3b_synth_fill(int device, float *d_pcm, size_t n_samples_per_channel, int 
   return MP3B_OK;
 }
 
+int mp3b_selftest(int device, uint64_t mismatches[3]) {
+  if (!mismatches) return fail(MP3B_ERR_BAD_ARG, "null mismatches");
+  if (!usable_device(device)) return fail(MP3B_ERR_CUDA, "device %d is not compute capability 10.x", device);
+  CU(cudaSetDevice(device));
+  unsigned long long *d = nullptr;
+  CU(cudaMalloc((void **)&d, 3 * sizeof *d));
+  CU(cudaMemset(d, 0, 3 * sizeof *d));
+  int k = launch_selftest(d, nullptr);
+  if (k < 0) { cudaFree(d); return fail(MP3B_ERR_CUDA, "selftest launch failed: %s", cudaGetErrorString((cudaError_t)(-k))); }
+  unsigned long long h[3] = {0, 0, 0};
+  cudaError_t ce = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (ce != cudaSuccess) return fail(MP3B_ERR_CUDA, "selftest failed: %s", cudaGetErrorString(ce));
+  for (int i = 0; i < 3; ++i) mismatches[i] = h[i];
+  return MP3B_OK;
+}
+
 }  // extern "C"

@@ -79,8 +79,26 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   return v;
 }
 
-// [OD3] |x|^0.75 = (float)(sqrt(d) * sqrt(sqrt(d))) in IEEE double.
+// Correctly rounded double square root for arguments in the normal range (no zero / subnormal / huge inputs, which is
+// all this file ever feeds it): reciprocal-square-root seed, one third-order Newton step, then the Markstein correction
+// g + (d - g * g) * h with h = 1 / (2 sqrt d), which rounds correctly.  Same steps as the library's sqrt.rn.f64 without
+// its range guard and slow-path call; mp3b_selftest compares the two on every float of the encoder's range.
+__device__ __forceinline__ double dsqrt_normal(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = __fma_rn(d, -__dmul_rn(y, y), 1.0);             // 1 - d y^2
+  const double p = __fma_rn(e, 0.375, 0.5);
+  y = __fma_rn(p, __dmul_rn(y, e), y);                             // y (1 + e / 2 + 3 e^2 / 8)
+  const double g = __dmul_rn(d, y), h = __dmul_rn(y, 0.5);
+  return __fma_rn(__fma_rn(-g, g, d), h, g);
+}
+
+// [OD3] |x|^0.75 = (float)(sqrt(d) * sqrt(sqrt(d))) in IEEE double; a >= 1e-10f.
 __device__ __forceinline__ float pow34(float a) {
+  const double r = dsqrt_normal((double)a);
+  return __double2float_rn(__dmul_rn(r, dsqrt_normal(r)));
+}
+__device__ __forceinline__ float pow34_reference(float a) {      // the same with the library's IEEE square root
   double d = (double)a;
   double r = __dsqrt_rn(d);
   return __double2float_rn(__dmul_rn(r, __dsqrt_rn(r)));
@@ -1006,6 +1024,30 @@ __global__ void k_synth(float *pcm, size_t n, int channels, int sample_rate, flo
     float v = amp * sinpif(2.0f * ph + (c == 1 ? 0.3f / 3.14159265f : 0.0f)) + noise * rad * (c == 0 ? cs : sn);
     pcm[i * channels + c] = fminf(fmaxf(v, -1.0f), 1.0f);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Self-test (tests only): pow34 against its definition on every float in [1e-10, 65536), div_exact against the IEEE
+// division for every finite float.  mismatch[0] / [1] / [2] count pow34, /9 and /3 disagreements.
+__global__ void k_selftest(unsigned long long *mismatch) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  unsigned long long bad0 = 0, bad1 = 0, bad2 = 0;
+  for (uint64_t u = blockIdx.x * blockDim.x + threadIdx.x; u < (1ull << 32); u += stride) {
+    const float a = __uint_as_float((uint32_t)u);
+    if (a >= 1e-10f && a < 65536.0f) bad0 += __float_as_uint(pow34(a)) != __float_as_uint(pow34_reference(a));
+    if ((((uint32_t)u >> 23) & 255) != 255) {
+      bad1 += __float_as_uint(div_exact(a, 9.0f, 1.0f / 9.0f)) != __float_as_uint(__fdiv_rn(a, 9.0f));
+      bad2 += __float_as_uint(div_exact(a, 3.0f, 1.0f / 3.0f)) != __float_as_uint(__fdiv_rn(a, 3.0f));
+    }
+  }
+  if (bad0) atomicAdd(mismatch, bad0);
+  if (bad1) atomicAdd(mismatch + 1, bad1);
+  if (bad2) atomicAdd(mismatch + 2, bad2);
+}
+int launch_selftest(unsigned long long *d_mismatch, cudaStream_t st) {
+  k_selftest<<<148 * 8, 256, 0, st>>>(d_mismatch);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -(int)e;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -125,5 +125,6 @@ int launch_compact(const Config &cfg, const PassBuffers &pb, uint64_t *offsets /
 int launch_synth(float *d_pcm, size_t n_per_channel, int channels, int sample_rate, float f_left, float f_right,
                  float amp, float noise, uint64_t seed, cudaStream_t st);
 int launch_table_dump(int which, void *d_out, cudaStream_t st);
+int launch_selftest(unsigned long long *d_mismatch /* [3] */, cudaStream_t st);
 
 }  // namespace mp3b
