@@ -661,7 +661,11 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
       if (lane < cnt) sh_bri[lane] = pb.frame_br[(size_t)s * pb.Fc + base + lane];
     }
     __syncwarp();
-    if (lane == 0) {  // (2) the serial chain, SRC:475-568
+    {  // (2) the serial chain, SRC:475-568.  Every lane carries the scalar recurrences (padding, reservoir, cursors)
+       // redundantly, lane j < ngc additionally walks the curve of gc j: the per-frame critical path is the reservoir
+       // update plus one curve look-up plus two shuffles instead of four look-ups in sequence.
+      const int ngc_shift = ch == 1 ? 1 : 2;
+#pragma unroll 2
       for (int l = 0; l < cnt; ++l) {
         const int f = base + l;
         const bool is_final = (plan.flags & 1) && f == nf - 1;
@@ -672,9 +676,10 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
         const int mds = cfg.frame_base[bri] + padding - cfg.header_bytes;   // SRC:497
         const int mdb = is_final ? 0 : (int)min(W - R, 511u);        // SRC:499, 2099-2101
         const int res_bits = is_final ? 0 : avail * 8;               // SRC:500
-        const int bpg = (mds * 8 + (res_bits * 9) / 10) / (2 * ch);  // SRC:647-650
+        const int bpg = (mds * 8 + (res_bits * 9) / 10) >> ngc_shift;  // SRC:647-650: / (2 * channels)
         int total = 0;
-        for (int j = 0; j < ngc; ++j) {
+        if (lane < ngc) {
+          const int j = lane;
           const uint32_t meta = sh_meta[l * ngc + j];
           const int g0 = meta & 255, n = (meta >> 8) & 255, restart = (meta >> 16) & 1;
           const uint16_t *cb = sh_bits + (l * ngc + j) * kMaxEntries;
@@ -690,15 +695,18 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
           }
           sh_sel[l * ngc + j][0] = (uint8_t)chosen; sh_sel[l * ngc + j][1] = (uint8_t)gain_out;
           sh_sel[l * ngc + j][2] = (uint8_t)gain_used; sh_sel[l * ngc + j][3] = (uint8_t)iters;
-          total += cb[chosen];
+          total = cb[chosen];
         }
+        total += __shfl_xor_sync(0xffffffffu, total, 1);
+        total += __shfl_xor_sync(0xffffffffu, total, 2);
+        total = __shfl_sync(0xffffffffu, total, 0);
         const int huff = (total + 7) >> 3;                           // padToByte SRC:729
-        ScanFrame &o = sh_fr[l];
+        ScanFrame o;
         o.padding = padding; o.mdb = mdb; o.res_bits = res_bits; o.bpg = bpg; o.huff = huff; o.is_final = is_final;
         o.w_off = W;
         W += (uint32_t)huff;                                         // appendHuffmanData SRC:511
         if (W > pb.md_stride) { err |= 2; W = (uint32_t)pb.md_stride; }
-        o.e_take = 0xFFFFFFFFu;
+        o.e_take = 0xFFFFFFFFu; o.e_src = 0; o.e_out = 0;
         if (prev_slot >= 0) {                                        // emit the buffered frame, SRC:548-556 + fillSlot 2110-2121
           uint32_t take = min((uint32_t)prev_slot, W - R);
           o.e_src = R; o.e_take = take; o.e_out = out_pos;
@@ -706,6 +714,7 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
           uint32_t sz = (uint32_t)cfg.header_bytes + (uint32_t)prev_slot;
           out_pos += sz; frame_count += 1; total_bytes += sz; n_emit += 1;
         }
+        if (lane == 0) sh_fr[l] = o;
         prev_slot = mds;
         int a = avail + mds - huff;                                  // updateReservoir SRC:565, 2125-2128
         avail = a < 0 ? 0 : a > 511 ? 511 : a;
@@ -755,6 +764,8 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
   }
   __syncwarp();
   // tail: flush emission, state write-back
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) err |= __shfl_xor_sync(0xffffffffu, err, m);
   if (lane == 0) {
     FrameEmit em; em.emit = 0; em.src_off = em.take = em.out_off = 0;
     if ((plan.flags & 2) && prev_slot >= 0) {                        // flush SRC:335-347
