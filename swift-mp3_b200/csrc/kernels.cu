@@ -470,7 +470,7 @@ __device__ __forceinline__ int lo_bits_of(const Config &cfg, int bri) {
 __global__ void __launch_bounds__(256) k_granule(Config cfg, PassBuffers pb) {
   __shared__ uint8_t len15[256];                  // table-15 code length of a pair + its sign bits (SRC:828-853)
   __shared__ __align__(8) float smg[8][576];
-  len15[threadIdx.x] = c_len15[threadIdx.x] + ((threadIdx.x >> 4) != 0) + ((threadIdx.x & 15) != 0);
+  len15[threadIdx.x] = tab::kHuff15Len[threadIdx.x] + ((threadIdx.x >> 4) != 0) + ((threadIdx.x & 15) != 0);
   __syncthreads();
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gci = blockIdx.y * 8 + warp;
@@ -806,10 +806,10 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
 // position; codes are OR-ed MSB-first into a shared bit buffer and the frame's bytes are written once.
 __global__ void __launch_bounds__(128) k_pack(Config cfg, PassBuffers pb) {
   __shared__ uint32_t buf[548];
-  __shared__ uint8_t len15[256], code15[256];
+  __shared__ uint16_t tab15[256];                  // code | length << 8
   const int s = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (f >= (int)pb.plan[s].n_frames) return;
-  for (int i = tid; i < 256; i += 128) { len15[i] = c_len15[i]; code15[i] = c_code15[i]; }
+  for (int i = tid; i < 256; i += 128) tab15[i] = (uint16_t)(tab::kHuff15Code[i] | tab::kHuff15Len[i] << 8);   // global, coalesced: a lane-indexed constant-bank read would serialise
   for (int i = tid; i < 548; i += 128) buf[i] = 0;
   __syncthreads();
   const int ch = cfg.channels, ngc = 2 * ch;
@@ -828,7 +828,8 @@ __global__ void __launch_bounds__(128) k_pack(Config cfg, PassBuffers pb) {
       float2 v = sm2[p];
       int qx = quant15(fabsf(v.x), inv), qy = quant15(fabsf(v.y), inv);
       if (trix) { trix[2 * p] = v.x < 0.0f ? -qx : qx; trix[2 * p + 1] = v.y < 0.0f ? -qy : qy; }
-      uint32_t code = code15[qx * 16 + qy]; int l = len15[qx * 16 + qy];
+      const uint32_t t15 = tab15[qx * 16 + qy];
+      uint32_t code = t15 & 255u; int l = (int)(t15 >> 8);
       if (qx) { code = code << 1 | (v.x < 0.0f ? 1u : 0u); ++l; }   // SRC:1729-1736
       if (qy) { code = code << 1 | (v.y < 0.0f ? 1u : 0u); ++l; }
       if (p >= bv) l = 0;
