@@ -28,8 +28,16 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SR, CH, KBPS = 44100, 2, 128
-ALGO_BYTES_PER_GC_SPECTRUM = 2304 + 2304          # PCM in + MDCT spectrum out
-FLOP_PER_GC_SPECTRUM = 18 * (512 + 448 + 2 * 2048) + 32 * (36 + 2 * 648 + 18)   # direct form as executed, long blocks
+# Algorithmic bytes / flops per granule-channel (gc = 576 samples of one channel), DESIGN.md section 4
+ALGO_BYTES = {"prepass": 2304 + 8,                 # PCM in, decisions out
+              "filterbank": 2304 + 2304,           # PCM in, 18 x 32 subband samples out
+              "granule": 2304 + 2304 + 84,         # subband samples in, sign * |x|^0.75 out, curve tables out
+              "scan": 84 + 45}                     # curve tables in, records out ("pack" / "frames" depend on the output size)
+FLOP_FILTERBANK = 18 * (512 + 448 + 2 * 2048)      # window products + sums + 32 x 64 matrixing, direct form as executed
+FLOP_GRANULE = 32 * (36 + 2 * 648 + 18 * 3) + 8 * 31 * 6 + 576 * 4   # long-block MDCT + scaling, alias butterflies, energies
+KERNEL_OF = {"prepass": "k_prepass", "filterbank": "k_filterbank (polyphase analysis: windowing + 32x64 matrixing)",
+             "granule": "k_granule (MDCT + alias reduction + |x|^0.75 + bits-vs-gain curve)", "scan": "k_scan",
+             "pack": "k_pack", "frames": "k_frames"}
 
 
 sharding = importlib.import_module("swift-mp3_b200.sharding")
@@ -251,7 +259,8 @@ def main():
     value = world * audio_per_step / (ms_per_step / 1000.0)
     out_bytes = b.output_total
 
-    # ---- roofline of the dominant kernel (k_spectrum: filterbank + MDCT), from the engine's CUDA events
+    # ---- roofline: per-stage table from the engine's CUDA events (recorded on its own stream around every kernel), the
+    # dominant kernel = the stage with the largest share of the step
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -260,29 +269,42 @@ def main():
     hbm_peak, which = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
     frames = (n_per + 1151) // 1152
     gc_per_step = S * frames * 2 * CH
-    spectrum_ms_per_launch = stages["spectrum"] / max(passes, 1)
     gc_per_launch = gc_per_step * a.steps / max(passes, 1)
-    achieved = gc_per_launch * ALGO_BYTES_PER_GC_SPECTRUM / (spectrum_ms_per_launch / 1000.0) / 1e9
-    traffic = None
+    out_per_gc = out_bytes / max(gc_per_step, 1)
+    algo = dict(ALGO_BYTES, pack=2304 + out_per_gc, frames=2 * out_per_gc + 30)
+    fp32_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) / 1000.0) / 1000.0   # nominal TFLOP/s, non-tensor FP32
+    flops = {"filterbank": FLOP_FILTERBANK, "granule": FLOP_GRANULE}
+    ncu = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "spectrum_traffic.json")))["dram_bytes_per_gc"] * gc_per_launch
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")))
     except Exception:
         pass
-    fp32_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) / 1000.0) / 1000.0   # nominal TFLOP/s, non-tensor FP32
-    fp32_ach = gc_per_launch * FLOP_PER_GC_SPECTRUM * (16.0 / 15.0) / (spectrum_ms_per_launch / 1000.0) / 1e12
-    out_per_gc = out_bytes / max(gc_per_step, 1)
-    algo = {"prepass": 2304 + 8, "spectrum": ALGO_BYTES_PER_GC_SPECTRUM, "curve": 2304 + 2304 + 84, "scan": 84 + 45,
-            "pack": 2304 + out_per_gc, "frames": 2 * out_per_gc + 30}          # algorithmic bytes per gc, DESIGN.md section 4
-    stage_table = {k: {"ms_per_step": stages[k] / a.steps, "algo_bytes_per_gc": algo[k],
-                       "achieved_GBps": gc_per_step * algo[k] / (stages[k] / a.steps / 1000.0) / 1e9,
-                       "hbm_frac": gc_per_step * algo[k] / (stages[k] / a.steps / 1000.0) / 1e9 / hbm_peak} for k in algo}
-    roofline = {"kernel": "k_spectrum (polyphase filterbank + MDCT)", "bound": "hbm", "achieved": achieved, "stages": stage_table,
-                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": which,
-                "ms_per_launch": spectrum_ms_per_launch, "gc_per_launch": gc_per_launch,
-                "limiter": "fp32 (direct-form 32x64 matrixing kept for bit-exact parity); see fp32",
-                "fp32": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
-                         "peak_source": "nominal 148 SM x 128 lanes x 2 x sm_max_mhz"},
-                "stage_ms_per_step": {k: v / a.steps for k, v in stages.items()}}
+    stage_table = {}
+    for k in algo:
+        sec = stages[k] / a.steps / 1000.0
+        row = {"ms_per_step": 1000.0 * sec, "share": stages[k] / max(stages["total"], 1e-9), "algo_bytes_per_gc": algo[k],
+               "achieved_GBps": gc_per_step * algo[k] / sec / 1e9, "hbm_frac": gc_per_step * algo[k] / sec / 1e9 / hbm_peak}
+        if k in flops:
+            row["fp32_TFLOPs"] = gc_per_step * flops[k] / sec / 1e12
+            row["fp32_frac_of_nominal"] = row["fp32_TFLOPs"] / fp32_peak
+        if k in ncu:
+            row["ncu"] = ncu[k]
+        stage_table[k] = row
+    dom = max(algo, key=lambda k: stages[k])
+    dom_ms_per_launch = stages[dom] / max(passes, 1)
+    achieved = gc_per_launch * algo[dom] / (dom_ms_per_launch / 1000.0) / 1e9
+    traffic = ncu[dom]["dram_bytes_per_gc"] * gc_per_launch if dom in ncu and "dram_bytes_per_gc" in ncu[dom] else None
+    roofline = {"kernel": KERNEL_OF[dom], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": which, "ms_per_launch": dom_ms_per_launch,
+                "gc_per_launch": gc_per_launch, "share_of_step": stages[dom] / max(stages["total"], 1e-9),
+                "limiter": ("FP32 FMA pipe and shared-memory wavefronts, not HBM: the reference's direct-form 32x64 matrixing is kept "
+                            "operation for operation (bit-exact parity); see fp32 and DESIGN.md section 4") if dom == "filterbank" else
+                           "instruction issue (MDCT with immediate coefficients, FP64 |x|^0.75, integer bit counting); see DESIGN.md section 4",
+                "stages": stage_table, "stage_ms_per_step": {k: v / a.steps for k, v in stages.items()}}
+    if dom in flops:
+        ach = gc_per_launch * flops[dom] / (dom_ms_per_launch / 1000.0) / 1e12
+        roofline["fp32"] = {"achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+                            "peak_source": "nominal 148 SM x 128 lanes x 2 x sm_max_mhz (no measured FP32 peak in MEASURED_PEAKS.json)"}
 
     # ---- e2e: host plane (pinned PCM in, MP3 bytes out), wall clock
     e2e_steps = a.e2e_steps or min(a.steps, 5)

@@ -130,7 +130,7 @@ int mp3b_device_sync(int device);
 /* Per-stage device time of the last batch call, in milliseconds, summed over the call's passes.
  * Stage order: see MP3B_STAGE_*.  n = entries available in ms[]. */
 enum {
-  MP3B_STAGE_H2D = 0, MP3B_STAGE_PREPASS, MP3B_STAGE_SPECTRUM, MP3B_STAGE_CURVE, MP3B_STAGE_SCAN, MP3B_STAGE_PACK,
+  MP3B_STAGE_H2D = 0, MP3B_STAGE_PREPASS, MP3B_STAGE_SPECTRUM /* k_filterbank */, MP3B_STAGE_CURVE /* k_granule: MDCT + curve */, MP3B_STAGE_SCAN, MP3B_STAGE_PACK,
   MP3B_STAGE_FRAMES, MP3B_STAGE_D2H, MP3B_STAGE_TOTAL, MP3B_STAGE_COUNT
 };
 int mp3b_batch_stage_ms(const mp3b_batch *b, float *ms, int n);

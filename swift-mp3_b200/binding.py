@@ -37,7 +37,7 @@ GC_RECORD = np.dtype([("part23_length", "<i4"), ("big_values", "<i4"), ("global_
 FRAME_RECORD = np.dtype([("bitrate_index", "<i4"), ("padding", "<i4"), ("frame_size", "<i4"), ("main_data_size", "<i4"),
                          ("main_data_begin", "<i4"), ("reservoir_bits", "<i4"), ("huff_bytes", "<i4"), ("ms", "<i4"),
                          ("is_final", "<i4"), ("frame_energy", "<f4")])
-STAGES = ("h2d", "prepass", "spectrum", "curve", "scan", "pack", "frames", "d2h", "total")
+STAGES = ("h2d", "prepass", "filterbank", "granule", "scan", "pack", "frames", "d2h", "total")   # MP3B_STAGE_* order
 
 _lib = None
 

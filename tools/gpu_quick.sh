@@ -8,6 +8,6 @@ python - <<PY
 import json
 d = json.load(open("gpurun_out/bench_$1.json"))
 print("value", d["value"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"])
-print({k: round(v, 3) for k, v in d["roofline"]["stage_ms_per_step"].items()})
+print({k: round(v, 3) for k, v in d["roofline"]["stage_ms_per_step"].items()}); print("dominant", d["roofline"]["kernel"][:14], "hbm frac", round(d["roofline"]["frac"], 3), "fp32", d["roofline"].get("fp32", {}).get("frac"))
 print(open("gpurun_out/pytest_$1.txt").read().strip().splitlines()[-1])
 PY
