@@ -126,3 +126,58 @@ def test_exact_arithmetic_shortcuts(mp3):
     rc = mp3.lib().mp3b_selftest(0, bad)
     assert rc == 0, mp3.lib().mp3b_last_error()
     assert list(bad) == [0, 0, 0]
+
+
+def _bytes_equal(mp3, orc, pcm, **o):
+    b = mp3.EncoderBatch(_opts(mp3, **o), 1, 0)
+    out = b.encode([pcm], flush=True)[0]
+    ref, rs = orc.encode_all(pcm, **o)
+    assert b.frame_count(0) == rs.frame_count and b.byte_count(0) == rs.byte_count
+    assert out == ref
+    b.close()
+    return rs.frame_count
+
+
+def test_baseline_configs_at_full_size(mp3, orc):
+    """BASELINE.json configs 1-3 at their full sizes, byte for byte against the oracle: C1 10 s 44.1 kHz stereo CBR 128,
+    C2 60 s 48 kHz mono CBR 320 (white and pink noise), C3 30 s joint-stereo VBR q2 with transients."""
+    assert _bytes_equal(mp3, orc, signals.sine_noise(10.0)) == 383                                        # SURVEY 8: 383 frames
+    assert _bytes_equal(mp3, orc, signals.white(60.0), sample_rate=48000, bitrate_kbps=320, mode="mono") == 2500
+    _bytes_equal(mp3, orc, signals.pink(60.0), sample_rate=48000, bitrate_kbps=320, mode="mono")
+    _bytes_equal(mp3, orc, signals.castanets(30.0), sample_rate=44100, bitrate_kbps=128, mode="jointStereo", vbr=True, quality=2)
+
+
+def test_batch_shard_properties(mp3, orc):
+    """A slice of BASELINE config 4 (64 streams x 30 s, synthesised on the device like bench.py does) through the device
+    plane: every stream has the frame count and byte count the format dictates, the batch is deterministic, duplicate
+    streams give duplicate bytes, and two of the streams equal the oracle."""
+    import ctypes as C
+    import importlib
+    import torch
+    sharding = importlib.import_module("swift-mp3_b200.sharding")
+    L = mp3.lib()
+    S, n_per = 64, 30 * 44100
+    pcm = torch.empty((S, n_per * 2), dtype=torch.float32, device="cuda")
+    for i in range(S):
+        fl, fr, seed = sharding.stream_params(i % 48)                       # streams 48..63 repeat streams 0..15
+        assert L.mp3b_synth_fill(0, pcm[i].data_ptr(), n_per, 2, 44100, fl, fr, 0.5, 0.05, seed) == 0
+    torch.cuda.synchronize()
+    ptrs = (C.c_void_p * S)(*[pcm[i].data_ptr() for i in range(S)])
+    ns = (C.c_size_t * S)(*([n_per * 2] * S))
+    b = mp3.EncoderBatch(_opts(mp3), S, 0)
+    b.encode_device(ptrs, ns, flush=True, download=True)
+    first = [b.output(i) for i in range(S)]
+    frames = -(-n_per // 1152)
+    for i in range(S):
+        assert b.frame_count(i) == frames and b.byte_count(i) == len(first[i])
+        assert abs(len(first[i]) - frames * 144 * 128000 / 44100) < 2         # padding accumulator: 417.96 bytes / frame
+        assert first[i][0] == 0xFF and (first[i][1] & 0xE0) == 0xE0
+    for i in range(48, S):
+        assert first[i] == first[i - 48]
+    b.reset()
+    b.encode_device(ptrs, ns, flush=True, download=True)
+    assert [b.output(i) for i in range(S)] == first
+    for i in (0, 47):
+        ref, _ = orc.encode_all(pcm[i].cpu().numpy())
+        assert first[i] == ref
+    b.close()
