@@ -879,7 +879,7 @@ __device__ inline uint16_t crc16_mpeg(const uint8_t *p, int n) {  // SRC:2190-22
 }
 
 __global__ void __launch_bounds__(128) k_frames(Config cfg, PassBuffers pb) {
-  __shared__ uint8_t hdr[4][40];
+  __shared__ uint32_t hwords[4][12];               // per warp: header + CRC + side info as big-endian words (<= 38 bytes)
   const int s = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.y * 4 + warp;
   if (r > (int)pb.plan[s].n_frames) return;
@@ -887,34 +887,52 @@ __global__ void __launch_bounds__(128) k_frames(Config cfg, PassBuffers pb) {
   const FrameEmit em = pb.emit[(size_t)s * (pb.Fc + 1) + r];
   if (!fr.valid || !em.emit) return;
   const int ch = cfg.channels;
-  if (lane == 0) {
-    BitW w{hdr[warp], 0, 0, 0};
-    w.put(0x7FF, 11); w.put(3, 2); w.put(1, 2); w.put(cfg.crc ? 0 : 1, 1);
-    w.put(fr.br_index, 4); w.put(cfg.sr_index, 2); w.put(fr.padding, 1); w.put(0, 1);
-    w.put(cfg.mode_bits, 2); w.put(cfg.mode_ext, 2); w.put(cfg.copyright ? 1 : 0, 1); w.put(cfg.original ? 1 : 0, 1); w.put(0, 2);
-    if (cfg.crc) { uint16_t crc = crc16_mpeg(hdr[warp], 4); w.put(crc >> 8, 8); w.put(crc & 0xFF, 8); }   // SRC:538-543
-    w.put(min((int)fr.mdb, 511), 9); w.put(0, ch == 1 ? 5 : 3);
-    for (int c = 0; c < ch; ++c) w.put(0, 4);                                        // scfsi SRC:644
-    for (int j = 0; j < 2 * ch; ++j) {
-      const GcSide &g = fr.gc[j];
-      w.put(g.part23, 12); w.put(g.big_values, 9); w.put(g.global_gain, 8); w.put(0, 4);
+  uint32_t *hw = hwords[warp];
+  if (lane < 12) hw[lane] = 0;
+  __syncwarp();
+  // The bit layout is fixed, so the fields are assembled in parallel: lane 4 the header (+ CRC), lane 5 main_data_begin /
+  // private bits / scfsi, lanes 0..2ch-1 one 59-bit granule record each; every lane ORs its bits into the word buffer.
+  {
+    unsigned long long v = 0; int c = 0, o = 0;
+    const int crc_bits = cfg.crc ? 16 : 0, prefix_bits = 9 + (ch == 1 ? 5 : 3) + 4 * ch;
+    if (lane < 2 * ch) {                                                              // buildSideInfo SRC:586-624
+      const GcSide &g = fr.gc[lane];
       const int ws = g.block_type != 0;
-      w.put(ws, 1);
-      if (ws) {
-        w.put(g.block_type, 2); w.put(g.block_type == 1, 1); w.put(15, 5); w.put(15, 5);
-        w.put(g.sbg[0], 3); w.put(g.sbg[1], 3); w.put(g.sbg[2], 3);
-      } else {
-        w.put(15, 5); w.put(15, 5); w.put(15, 5); w.put(g.region0, 4); w.put(g.region1, 3);
+      v = (unsigned long long)(g.part23 & 0xFFF) << 47 | (unsigned long long)(g.big_values & 0x1FF) << 38 |
+          (unsigned long long)g.global_gain << 30 | (unsigned long long)ws << 25;   // scalefac_compress = 0 (4 bits at 26)
+      unsigned long long mid;                                                         // 22 bits at 3
+      if (ws) mid = (unsigned long long)(g.block_type & 3) << 20 | (unsigned long long)(g.block_type == 1) << 19 | 15ull << 14 | 15ull << 9 |
+                    (unsigned long long)(g.sbg[0] & 7) << 6 | (unsigned long long)(g.sbg[1] & 7) << 3 | (unsigned long long)(g.sbg[2] & 7);
+      else mid = 15ull << 17 | 15ull << 12 | 15ull << 7 | (unsigned long long)(g.region0 & 15) << 3 | (unsigned long long)(g.region1 & 7);
+      v |= mid << 3 | (unsigned long long)(g.preflag & 1) << 2;                       // scalefac_scale = count1table_select = 0
+      c = 59; o = 32 + crc_bits + prefix_bits + 59 * lane;
+    } else if (lane == 4) {                                                           // header SRC:522-536, CRC SRC:538-543
+      uint32_t h = 0x7FFu;
+      h = h << 2 | 3u; h = h << 2 | 1u; h = h << 1 | (cfg.crc ? 0u : 1u); h = h << 4 | (fr.br_index & 15u); h = h << 2 | (uint32_t)cfg.sr_index;
+      h = h << 1 | (fr.padding & 1u); h = h << 1; h = h << 2 | (uint32_t)cfg.mode_bits; h = h << 2 | (uint32_t)cfg.mode_ext;
+      h = h << 1 | (cfg.copyright ? 1u : 0u); h = h << 1 | (cfg.original ? 1u : 0u); h = h << 2;
+      v = h; c = 32; o = 0;
+      if (cfg.crc) {
+        const uint8_t hb[4] = {(uint8_t)(h >> 24), (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h};
+        v = (unsigned long long)h << 16 | crc16_mpeg(hb, 4); c = 48;
       }
-      w.put(g.preflag, 1); w.put(0, 1); w.put(0, 1);
+    } else if (lane == 5) {                                                           // SRC:577-584: mdb, private bits, scfsi = 0
+      v = (unsigned long long)min((int)fr.mdb, 511) << (prefix_bits - 9); c = prefix_bits; o = 32 + crc_bits;
     }
-    w.pad();
-    while (w.n < cfg.header_bytes) w.p[w.n++] = 0;
+    if (c) {
+      const unsigned long long hi = v << (64 - c);                                    // left aligned
+      const int w = o >> 5, sft = o & 31;
+      const uint32_t a = (uint32_t)(hi >> (32 + sft)), b2 = (uint32_t)((hi << (32 - sft)) >> 32);
+      const uint32_t d = sft ? (uint32_t)((hi << (64 - sft)) >> 32) : 0u;
+      if (a) atomicOr(&hw[w], a);
+      if (b2) atomicOr(&hw[w + 1], b2);
+      if (d) atomicOr(&hw[w + 2], d);
+    }
   }
   __syncwarp();
   uint8_t *dst = pb.out + (size_t)s * pb.out_stride + em.out_off;
   if ((size_t)em.out_off + cfg.header_bytes + fr.slot > pb.out_stride) return;
-  for (int i = lane; i < cfg.header_bytes; i += 32) dst[i] = hdr[warp][i];
+  for (int i = lane; i < cfg.header_bytes; i += 32) dst[i] = (uint8_t)(hw[i >> 2] >> (24 - 8 * (i & 3)));
   dst += cfg.header_bytes;
   const uint32_t B0 = pb.md_tail[(size_t)s * 4 + 2];
   const uint8_t *carry = pb.md_carry + (size_t)s * kMdCarryCap, *md = pb.md + (size_t)s * pb.md_stride;
