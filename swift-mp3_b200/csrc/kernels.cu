@@ -146,9 +146,11 @@ template <int MODE> struct FrameLoad {
   }
 };
 
-template <int MODE> __device__ __forceinline__ void prepass_frame(const Config &cfg, const PassBuffers &pb, const FrameLoad<MODE> &ld,
+// JOINT / CH are compile-time so that the mid / side variants (and the second channel of mono) cost nothing when unused.
+template <int MODE, bool JOINT, int CH> __device__ __forceinline__ void prepass_frame(const Config &cfg, const PassBuffers &pb, const FrameLoad<MODE> &ld,
                                                                   int s, int f, int lane) {
-  const int ch = cfg.channels;
+  constexpr int ch = CH;
+  constexpr int NV = JOINT ? 4 : CH;               // signal variants: L, R (or mono), mid, side
   // frame energy over the interleaved frame (SRC:477), lane = float index mod 32 [OD1b]
   float pf = 0.0f;
 #pragma unroll 8
@@ -156,7 +158,7 @@ template <int MODE> __device__ __forceinline__ void prepass_frame(const Config &
   const float frame_energy = __fdiv_rn(lane_tree(pf), (float)cfg.fsc);
 
   // per-channel signals; variant 0/1 = L/R (or mono), 2/3 = mid/side
-  const bool joint = cfg.mode == 2;
+  constexpr bool joint = JOINT;
   float eg[4][2], e3[4][2][3];
   float pm = 0.0f, ps = 0.0f;
 #pragma unroll
@@ -180,13 +182,13 @@ template <int MODE> __device__ __forceinline__ void prepass_frame(const Config &
           pm = __fmaf_rn(v[2], v[2], pm); ps = __fmaf_rn(v[3], v[3], ps);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { a3[k] = __fmaf_rn(v[k], v[k], a3[k]); ag[k] = __fmaf_rn(v[k], v[k], ag[k]); }
+        for (int k = 0; k < NV; ++k) { a3[k] = __fmaf_rn(v[k], v[k], a3[k]); ag[k] = __fmaf_rn(v[k], v[k], ag[k]); }
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) e3[k][gr][th] = __fdiv_rn(lane_tree(a3[k]), 192.0f);
+      for (int k = 0; k < NV; ++k) e3[k][gr][th] = __fdiv_rn(lane_tree(a3[k]), 192.0f);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) eg[k][gr] = __fdiv_rn(lane_tree(ag[k]), 576.0f);
+    for (int k = 0; k < NV; ++k) eg[k][gr] = __fdiv_rn(lane_tree(ag[k]), 576.0f);
   }
   int ms = 0;
   if (joint) {
@@ -202,7 +204,7 @@ template <int MODE> __device__ __forceinline__ void prepass_frame(const Config &
     int gr = lane / ch, c = lane % ch, k = c + (ms ? 2 : 0);
     float e[3] = {0.f, 0.f, 0.f}; float g = 0.0f;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
+    for (int kk = 0; kk < NV; ++kk)
 #pragma unroll
       for (int g2 = 0; g2 < 2; ++g2)
         if (kk == k && g2 == gr) { e[0] = e3[kk][g2][0]; e[1] = e3[kk][g2][1]; e[2] = e3[kk][g2][2]; g = eg[kk][g2]; }
@@ -227,11 +229,15 @@ __global__ void __launch_bounds__(128) k_prepass(Config cfg, PassBuffers pb) {
     pb.gc_energy[(size_t)s * (10 + pb.GC) + lane] = lane >= 10 - n ? stt.vbr_hist[lane - (10 - n)] : 0.0f;
   }
   const int64_t rel = q0 - (int64_t)pv.head_n;
-  if (rel >= 0 && rel + cfg.fsc <= (int64_t)pv.cur_n) {
-    const float *p = pv.cur + rel;
-    if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) { FrameLoad<2> ld{pv, q0, p}; prepass_frame<2>(cfg, pb, ld, s, f, lane); }
-    else { FrameLoad<1> ld{pv, q0, p}; prepass_frame<1>(cfg, pb, ld, s, f, lane); }
-  } else { FrameLoad<0> ld{pv, q0, nullptr}; prepass_frame<0>(cfg, pb, ld, s, f, lane); }
+  int mode = 0; const float *p = nullptr;
+  if (rel >= 0 && rel + cfg.fsc <= (int64_t)pv.cur_n) { p = pv.cur + rel; mode = (reinterpret_cast<uintptr_t>(p) & 7) == 0 ? 2 : 1; }
+#define MP3B_PREPASS(M, J, C) { FrameLoad<M> ld{pv, q0, p}; prepass_frame<M, J, C>(cfg, pb, ld, s, f, lane); }
+#define MP3B_PREPASS_M(J, C) { if (mode == 2) MP3B_PREPASS(2, J, C) else if (mode == 1) MP3B_PREPASS(1, J, C) else MP3B_PREPASS(0, J, C) }
+  if (cfg.channels == 1) MP3B_PREPASS_M(false, 1)
+  else if (cfg.mode == 2) MP3B_PREPASS_M(true, 2)
+  else MP3B_PREPASS_M(false, 2)
+#undef MP3B_PREPASS_M
+#undef MP3B_PREPASS
 }
 
 // VBRState.chooseBitrate SRC:1177-1189 + MP3Tables.bitrateIndex SRC:2509-2523: one thread per frame.
