@@ -45,7 +45,8 @@ stream_params = sharding.stream_params      # BASELINE C4 recipe: seed 1000+i, f
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons, one row every 50 ms for the whole run (started before the warm-up: nvidia-smi
+    needs about a second to come up); window(t0, t1) summarises the rows that arrived inside a timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -56,9 +57,9 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
 
@@ -66,15 +67,23 @@ class ClockSampler(threading.Thread):
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+
+    def window(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        note = "sampled inside the timed region"
+        if not rows and self.rows:                 # region shorter than the sampling period: nearest sample
+            rows = [min(self.rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + t1)))[1]]
+            note = "timed region shorter than the 50 ms sampling period: nearest sample"
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()] or [0])
+        pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": max(pw) if pw else None, "note": note}
 
 
 def cpu_reference(seconds_per_stream, min_wall=10.0, max_wall=40.0):
@@ -182,6 +191,7 @@ def main():
     mp3 = importlib.import_module("swift-mp3_b200")
     L = mp3.lib()
     torch.cuda.set_device(local)
+    sampler = ClockSampler(local); sampler.start()
     dist = None
     if world > 1:
         os.environ["NCCL_DEBUG"] = os.environ.get("MP3B_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
@@ -201,7 +211,9 @@ def main():
         return sharding.sum_over_ranks(v, dist, "cuda")
 
     if a.workload == "c5":
-        return bench_c5(a, mp3, L, local, rank, world)
+        rc = bench_c5(a, mp3, L, local, rank, world)
+        sampler.stop()
+        return rc
     S = a.streams                                                  # weak scaling: a.streams per GPU
     shard_lo, shard_hi = sharding.shard_range(S * world, rank, world)
     assert shard_hi - shard_lo == S
@@ -240,8 +252,8 @@ def main():
 
     for _ in range(a.warmup):
         step_device()
-    sampler = ClockSampler(local); sampler.start()
     barrier()
+    t_dev0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
     stages = {k: 0.0 for k in mp3.STAGES}
@@ -253,8 +265,8 @@ def main():
         launches += b.launch_count; passes += b.pass_count
     e1.record(ext)
     barrier()
+    t_dev1 = time.perf_counter()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop()
     ms_per_step = ms_total / a.steps
     value = world * audio_per_step / (ms_per_step / 1000.0)
     out_bytes = b.output_total
@@ -324,7 +336,11 @@ def main():
     for _ in range(e2e_steps):
         step_host()
     barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    t_e2e1 = time.perf_counter()
+    e2e_s = max_over_ranks(t_e2e1 - t0) / e2e_steps
+    sampler.stop()
+    clocks = sampler.window(t_dev0, t_dev1)
+    clocks["e2e_region"] = sampler.window(t0, t_e2e1)
     e2e_stage = b.stage_ms()
     e2e = {"value": world * audio_per_step / e2e_s, "unit": "x realtime", "h2d_bytes_per_step": S * n_floats * 4,
            "d2h_bytes_per_step": int(b.output_total), "ms_per_step": 1000.0 * e2e_s, "steps": e2e_steps,

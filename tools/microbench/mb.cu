@@ -140,6 +140,42 @@ template <int VAR> __global__ void __launch_bounds__(128, 2) mbE(const float *in
   }
   out[blockIdx.x * 128 + threadIdx.x] = s;
 }
+
+// F: 32k x 2t register tile (64 accumulators); the matrix comes from the constant bank as 128-bit uniform loads (LDCU.128 ->
+// uniform registers -> FFMA2 UR operand), Y is one LDS.64 per n.  128 threads, 3 CTAs / SM.
+__constant__ float4 cM4[64 * 8];
+__global__ void __launch_bounds__(128, 3) mbF(const float *in, float *out, int reps) {
+  extern __shared__ __align__(16) float sm[];
+  float *Y = sm;
+  for (int i = threadIdx.x; i < 32 * 256; i += 128) Y[i] = in[i];
+  __syncthreads();
+  float2 acc[2][16];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[j][i] = make_float2(0.f, 0.f);
+  const float2 *yrow = reinterpret_cast<const float2 *>(Y) + threadIdx.x;
+  for (int r = 0; r < reps; ++r) {
+#pragma unroll 2
+    for (int n = 0; n < 32; ++n) {
+      const float2 y = yrow[n * 128];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 m = cM4[n * 8 + q];
+        acc[0][2 * q] = __ffma2_rn(make_float2(y.x, y.x), make_float2(m.x, m.y), acc[0][2 * q]);
+        acc[0][2 * q + 1] = __ffma2_rn(make_float2(y.x, y.x), make_float2(m.z, m.w), acc[0][2 * q + 1]);
+        acc[1][2 * q] = __ffma2_rn(make_float2(y.y, y.y), make_float2(m.x, m.y), acc[1][2 * q]);
+        acc[1][2 * q + 1] = __ffma2_rn(make_float2(y.y, y.y), make_float2(m.z, m.w), acc[1][2 * q + 1]);
+      }
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[j][i].x + acc[j][i].y;
+  out[blockIdx.x * 128 + threadIdx.x] = s;
+}
 static double g_warps = 148.0 * 2 * 8;
 template <typename F> static void run(const char *name, F launch, double ffma2_per_thread) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -165,5 +201,13 @@ int main() {
   cudaFuncSetAttribute(mbE<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smE);
   run("E  8k x 8t tile, 128 thr x 2 CTA/SM (32 FFMA2 + 4 LDS.128 per n)", [&] { mbE<0><<<148 * 2, 128, smE>>>(in, out, reps); }, 32.0 * 32 * reps);
   run("E2 16k x 4t tile, 128 thr x 2 CTA/SM (32 FFMA2 + 5 LDS.128 per n)", [&] { mbE<1><<<148 * 2, 128, smE>>>(in, out, reps); }, 32.0 * 32 * reps);
+  g_warps = 148.0 * 3 * 4;
+  const int smF = 70 * 1024;
+  cudaFuncSetAttribute(mbF, cudaFuncAttributeMaxDynamicSharedMemorySize, smF);
+  cudaMemcpyToSymbol(cM4, h, sizeof(h));
+  run("F  32k x 2t tile, LDCU.128 matrix, 128 thr x 3 CTA/SM (32 FFMA2 + 8 LDCU.128 + 1 LDS.64 per n)", [&] { mbF<<<148 * 3, 128, smF>>>(in, out, reps); }, 32.0 * 32 * reps);
+  g_warps = 148.0 * 3 * 4;
+  cudaFuncSetAttribute(mbE<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smF);
+  run("E2 again at 3 CTA/SM", [&] { mbE<1><<<148 * 3, 128, smF>>>(in, out, reps); }, 32.0 * 32 * reps);
   return 0;
 }
