@@ -191,6 +191,7 @@ def main():
     mp3 = importlib.import_module("swift-mp3_b200")
     L = mp3.lib()
     torch.cuda.set_device(local)
+    numa = sharding.bind_near_gpu(local)           # before any pinned allocation
     sampler = ClockSampler(local); sampler.start()
     dist = None
     if world > 1:
@@ -360,7 +361,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {"workload": workload, "streams_per_gpu": S, "seconds_per_stream": a.seconds,
                                                 "frames_per_pass": b.frames_per_pass, "l2": "inputs larger than L2",
-                                                "parity": parity, "output_bytes_per_step_per_gpu": int(out_bytes)},
+                                                "parity": parity, "output_bytes_per_step_per_gpu": int(out_bytes), "host_numa": numa},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -688,7 +688,9 @@ int mp3b_id3_build(const mp3b_id3 *tag, uint8_t *out, size_t cap, size_t *writte
 // ---- memory helpers ---------------------------------------------------------------------------------------
 int mp3b_host_alloc(size_t bytes, void **out) {
   if (!out) return fail(MP3B_ERR_BAD_ARG, "null out");
-  CU(cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocDefault));
+  // MP3B_HOST_WC=1: write-combined pinned memory for upload buffers the host only writes (not snooped during DMA)
+  static const bool wc = [] { const char *v = getenv("MP3B_HOST_WC"); return v && v[0] == '1'; }();
+  CU(cudaHostAlloc(out, std::max<size_t>(bytes, 1), wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
   return MP3B_OK;
 }
 void mp3b_host_free(void *p) { if (p) cudaFreeHost(p); }
