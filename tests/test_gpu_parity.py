@@ -181,3 +181,31 @@ def test_batch_shard_properties(mp3, orc):
         ref, _ = orc.encode_all(pcm[i].cpu().numpy())
         assert first[i] == ref
     b.close()
+
+
+@pytest.mark.parametrize("cfg", [dict(sample_rate=22050, bitrate_kbps=64),                       # off-table rate: header index 0 (SRC:2541-2542), MPEG-2 bitrate table (Q21)
+                                 dict(sample_rate=32000, bitrate_kbps=320),                      # largest frame: 1440 bytes
+                                 dict(sample_rate=44100, bitrate_kbps=32, mode="mono"),          # smallest budget
+                                 dict(sample_rate=48000, bitrate_kbps=131),                      # off-table bitrate snaps (SRC:2519-2521)
+                                 dict(sample_rate=44100, bitrate_kbps=160, vbr=True, quality=9, mode="mono"),
+                                 dict(sample_rate=44100, bitrate_kbps=96, vbr=True, quality=0, mode="jointStereo", crc_protected=True)])
+def test_unusual_configurations(mp3, orc, cfg):
+    ch = 1 if cfg.get("mode") == "mono" else 2
+    pcm = signals.sine_noise(0.9, sr=cfg["sample_rate"], channels=ch, seed=21, amp=0.7, noise=0.2)
+    _compare(mp3, orc, pcm, **cfg)
+
+
+def test_wide_batch_short_streams(mp3, orc):
+    """2048 sessions in one batch (8 frames per pass), a few frames each, fed in two calls: a sample of the streams is
+    compared with the oracle; covers grids with many streams and few granules."""
+    S = 2048
+    base = [signals.sine_noise(0.2, seed=300 + i, f_left=200.0 + 13 * i, f_right=310.0 + 7 * i) for i in range(8)]
+    pcms = [base[i % 8][: base[i % 8].size - 2 * (i % 5)] for i in range(S)]
+    b = mp3.EncoderBatch(_opts(mp3), S, 0)
+    first = b.encode([p[: p.size // 2] for p in pcms], flush=False)
+    second = b.encode([p[p.size // 2:] for p in pcms], flush=True)
+    for i in list(range(0, 16)) + [777, S - 1]:
+        rs = orc.Session()
+        ref = rs.encode(pcms[i][: pcms[i].size // 2]), rs.encode(pcms[i][pcms[i].size // 2:]) + rs.flush()
+        assert first[i] == ref[0] and second[i] == ref[1], "stream %d" % i
+    b.close()
