@@ -98,6 +98,8 @@ void mp3b_batch_destroy(mp3b_batch *b);
 int mp3b_batch_stream_count(const mp3b_batch *b);
 /* Every stream back to a fresh EncoderSession (SRC:268-282) without reallocating anything. */
 int mp3b_batch_reset(mp3b_batch *b);
+/* The same for one stream (a session slot handed to a new caller). */
+int mp3b_batch_reset_stream(mp3b_batch *b, int stream);
 /* One encode(samples:) per stream: pcm[i] = HOST pointer to n_floats[i] interleaved floats (may be 0 / NULL).
  * flush != 0 additionally performs flush() on every stream afterwards (SRC:318-350).  flush_mask (may be
  * NULL) restricts the flush to streams with a non-zero byte.  The H2D copies, the device pipeline and the
@@ -116,6 +118,23 @@ size_t mp3b_batch_output_total(const mp3b_batch *b);
 int mp3b_batch_xing_header(const mp3b_batch *b, int stream, uint8_t *out, size_t cap, size_t *written);
 uint32_t mp3b_batch_frame_count(const mp3b_batch *b, int stream);
 uint32_t mp3b_batch_byte_count(const mp3b_batch *b, int stream);
+
+/* ---- session pool: many threads, one step ------------------------------------------------------------- */
+/* n_sessions EncoderSessions (SRC:237-350) driven from concurrent threads — one blocking call per session at a time,
+ * like N reference sessions on N threads — and advanced on the GPU together: the calls that arrive within max_wait_us of
+ * each other (or all open sessions, whichever happens first) become one step of the batch plane.  BASELINE config 5. */
+typedef struct mp3b_pool mp3b_pool;
+int mp3b_pool_create(const mp3b_options *opts, int n_sessions, int device, int max_wait_us, mp3b_pool **out);
+void mp3b_pool_destroy(mp3b_pool *p);
+/* MP3Encoder.newSession(): claims a free session of the pool; *slot identifies it in the calls below. */
+int mp3b_pool_open(mp3b_pool *p, int *slot);
+/* EncoderSession.encode(samples:) / flush() of session `slot`.  Blocks until the step that contains the request has run.
+ * flush() closes the session (it no longer delays the steps of the others). */
+int mp3b_pool_encode(mp3b_pool *p, int slot, const float *pcm, size_t n_floats, uint8_t *out, size_t cap, size_t *written);
+int mp3b_pool_flush(mp3b_pool *p, int slot, uint8_t *out, size_t cap, size_t *written);
+/* Steps run so far and requests served by them (requests / steps = achieved coalescing). */
+int mp3b_pool_stats(mp3b_pool *p, uint64_t *steps, uint64_t *requests);
+const char *mp3b_pool_last_error(void);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost) so callers can stage PCM for full-speed H2D. */
 int mp3b_host_alloc(size_t bytes, void **out);

@@ -9,6 +9,6 @@ The package directory name contains a hyphen, so import it with
     importlib.import_module("swift-mp3_b200")
 """
 from .binding import (  # noqa: F401
-    ID3Tag, MP3Encoder, MP3EncoderOptions, EncoderSession, EncoderBatch, Mode, MP3BError, lib, library_path,
+    ID3Tag, MP3Encoder, MP3EncoderOptions, EncoderSession, EncoderBatch, SessionPool, Mode, MP3BError, lib, library_path,
     build_library, table, device_count, GC_RECORD, FRAME_RECORD, STAGES,
 )

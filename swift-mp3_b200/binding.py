@@ -94,6 +94,13 @@ def lib():
         "mp3b_table": (i32, [i32, vp, sz]),
         "mp3b_synth_fill": (i32, [i32, vp, sz, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint64]),
         "mp3b_selftest": (i32, [i32, C.POINTER(C.c_uint64)]),
+        "mp3b_batch_reset_stream": (i32, [vp, i32]),
+        "mp3b_pool_create": (i32, [C.POINTER(_Options), i32, i32, i32, C.POINTER(vp)]), "mp3b_pool_destroy": (None, [vp]),
+        "mp3b_pool_open": (i32, [vp, C.POINTER(i32)]),
+        "mp3b_pool_encode": (i32, [vp, i32, vp, sz, vp, sz, C.POINTER(sz)]),
+        "mp3b_pool_flush": (i32, [vp, i32, vp, sz, C.POINTER(sz)]),
+        "mp3b_pool_stats": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "mp3b_pool_last_error": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -346,6 +353,56 @@ class EncoderBatch:
         out = np.zeros((n, 576), dtype="<i4" if k == 1 else "<f4")
         _check(lib().mp3b_batch_trace_gc_array(self._h, stream, k, out.ctypes.data, n))
         return out
+
+
+class SessionPool:
+    """mp3b_pool: n_sessions EncoderSessions that may be driven from concurrent threads; the calls that arrive together
+    run as one step on the GPU (BASELINE config 5)."""
+
+    class Session:
+        def __init__(self, pool, slot, bound):
+            self._pool, self._slot, self._bound = pool, slot, bound
+
+        def _call(self, fn, *head):
+            cap = self._bound(head[1] if head else 0)
+            buf = (C.c_uint8 * cap)()
+            n = C.c_size_t(0)
+            rc = fn(self._pool._h, self._slot, *head, buf, cap, C.byref(n))
+            if rc != 0:
+                raise MP3BError(rc, (lib().mp3b_pool_last_error() or b"").decode())
+            return bytes(memoryview(buf)[:n.value])
+
+        def encode(self, samples):
+            a = _as_f32(samples)
+            return self._call(lib().mp3b_pool_encode, a.ctypes.data, a.size)
+
+        def flush(self):
+            return self._call(lib().mp3b_pool_flush)
+
+    def __init__(self, options, n_sessions, device=0, max_wait_us=200):
+        self.options = options
+        self._h = C.c_void_p()
+        o = options._c()
+        _check(lib().mp3b_pool_create(C.byref(o), n_sessions, device, max_wait_us, C.byref(self._h)))
+        self._frame_bytes = 1441 + 8
+
+    def newSession(self):
+        slot = C.c_int(-1)
+        _check(lib().mp3b_pool_open(self._h, C.byref(slot)))
+        fsc = 1152 * self.options.channels
+        return SessionPool.Session(self, slot.value, lambda n: (n // fsc + 3) * self._frame_bytes)
+
+    def stats(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().mp3b_pool_stats(self._h, C.byref(a), C.byref(b)))
+        return {"steps": a.value, "requests": b.value}
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().mp3b_pool_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
 
 
 class MP3Encoder:

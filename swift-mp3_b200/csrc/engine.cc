@@ -734,6 +734,18 @@ int mp3b_batch_reset(mp3b_batch *b) {
   b->out_total = 0; b->have_host_out = false; b->sticky = 0;
   return MP3B_OK;
 }
+int mp3b_batch_reset_stream(mp3b_batch *b, int stream) {
+  if (!b || stream < 0 || stream >= b->S) return fail(MP3B_ERR_BAD_ARG, "bad batch / stream");
+  CU(cudaSetDevice(b->device));
+  const size_t s = (size_t)stream, fsc2 = 2 * (size_t)b->cfg.fsc, ch = (size_t)b->cfg.channels;
+  CU(cudaMemsetAsync(b->pb.state + s, 0, sizeof(StreamState), b->st));
+  CU(cudaMemsetAsync(b->d_head[0] + s * fsc2, 0, fsc2 * sizeof(float), b->st));
+  CU(cudaMemsetAsync(b->d_head[1] + s * fsc2, 0, fsc2 * sizeof(float), b->st));
+  CU(cudaMemset2DAsync(b->pb.sub + s * ch * (size_t)b->pb.sub_rows * 32, (size_t)b->pb.sub_rows * 32 * sizeof(float), 0, 576 * sizeof(float), ch, b->st));
+  CU(cudaStreamSynchronize(b->st));
+  b->pending[s] = 0; b->out_len[s] = 0; b->frame_count[s] = 0; b->byte_count[s] = 0; b->frame_sizes[s].clear();
+  return MP3B_OK;
+}
 int mp3b_batch_set_trace(mp3b_batch *b, int flags) { if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch"); b->trace = flags ? (flags | 8) : 0; return MP3B_OK; }
 int mp3b_batch_trace_frames(const mp3b_batch *b, int stream) {
   if (!b || stream < 0 || stream >= b->S || (size_t)stream >= b->tr_frames.size()) return 0;

@@ -209,3 +209,45 @@ def test_wide_batch_short_streams(mp3, orc):
         ref = rs.encode(pcms[i][: pcms[i].size // 2]), rs.encode(pcms[i][pcms[i].size // 2:]) + rs.flush()
         assert first[i] == ref[0] and second[i] == ref[1], "stream %d" % i
     b.close()
+
+
+def test_session_pool_concurrent_threads(mp3, orc):
+    """BASELINE config 5 in small: 48 sessions on 48 threads, each feeding its own stream in 1152-sample chunks through a
+    blocking encode(samples:); the pool coalesces the calls into shared GPU steps.  Every session's bytes equal its own
+    oracle session fed the same chunks, and the steps really were shared."""
+    import threading
+    n, chunks = 48, 14
+    pool = mp3.SessionPool(_opts(mp3), n, 0, max_wait_us=2000)
+    pcms = [signals.sine_noise(chunks * 1152 / 44100.0 + 0.01, seed=500 + i, f_left=150.0 + 11 * i, f_right=260.0 + 5 * i) for i in range(n)]
+    got, errs = [None] * n, []
+
+    def client(i):
+        try:
+            s = pool.newSession()
+            out = []
+            for k in range(chunks):
+                out.append(s.encode(pcms[i][k * 2304:(k + 1) * 2304]))
+            out.append(s.encode(pcms[i][chunks * 2304:]))
+            out.append(s.flush())
+            got[i] = out
+        except Exception as e:  # pragma: no cover
+            errs.append((i, repr(e)))
+
+    threads = [threading.Thread(target=client, args=(i,)) for i in range(n)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errs, errs
+    for i in range(n):
+        rs = orc.Session()
+        ref = [rs.encode(pcms[i][k * 2304:(k + 1) * 2304]) for k in range(chunks)] + [rs.encode(pcms[i][chunks * 2304:]), rs.flush()]
+        assert got[i] == ref, "session %d" % i
+    st = pool.stats()
+    assert st["requests"] == n * (chunks + 2) and st["steps"] < st["requests"] / 4, st      # on average > 4 calls per step
+    # a flushed slot is a fresh session again
+    s = pool.newSession()
+    again = s.encode(pcms[0][:2304 * 3]) + s.flush()
+    rs = orc.Session()
+    assert again == rs.encode(pcms[0][:2304 * 3]) + rs.flush()
+    pool.close()
