@@ -105,6 +105,10 @@ int mp3b_batch_reset_stream(mp3b_batch *b, int stream);
  * NULL) restricts the flush to streams with a non-zero byte.  The H2D copies, the device pipeline and the
  * D2H copy of the produced frames all happen inside the call; results are read with mp3b_batch_output. */
 int mp3b_batch_encode(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, int flush, const uint8_t *flush_mask);
+/* Same for callers that stage every stream in one host arena: stream i = base + i * pitch_floats, n_floats[i] <= pitch_floats
+ * floats of it are new.  All rows being readable up to the pitch, the upload is a single strided copy even when only some of
+ * the streams have data (the session pool's case). */
+int mp3b_batch_encode_strided(mp3b_batch *b, const float *base, size_t pitch_floats, const size_t *n_floats, int flush, const uint8_t *flush_mask);
 /* Same, but pcm[i] are DEVICE pointers (same device, 4-byte aligned) and the produced frames stay in device
  * memory; only the per-stream byte counts come back.  download != 0 also copies the frames to the host. */
 int mp3b_batch_encode_device(mp3b_batch *b, const float *const *d_pcm, const size_t *n_floats, int flush, int download);

@@ -77,6 +77,7 @@ def lib():
         "mp3b_batch_destroy": (None, [vp]), "mp3b_batch_stream_count": (i32, [vp]),
         "mp3b_batch_encode": (i32, [vp, C.POINTER(vp), szp, i32, vp]),
         "mp3b_batch_encode_device": (i32, [vp, C.POINTER(vp), szp, i32, i32]),
+        "mp3b_batch_encode_strided": (i32, [vp, vp, sz, szp, i32, vp]),
         "mp3b_batch_output": (i32, [vp, i32, C.POINTER(vp), szp]),
         "mp3b_batch_output_device": (i32, [vp, i32, C.POINTER(vp), szp]),
         "mp3b_batch_output_total": (sz, [vp]),

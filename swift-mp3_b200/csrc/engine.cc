@@ -247,7 +247,7 @@ int ensure_trace(mp3b_batch *b) {
 
 // One API call = encode(samples:) on every stream (+ optional flush()), split into passes of at most Fc frames.
 int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, bool device_ptrs, int flush,
-             const uint8_t *flush_mask, bool download) {
+             const uint8_t *flush_mask, bool download, size_t row_floats = 0) {
   if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");
   if (b->sticky) return fail(b->sticky, "batch is in a failed state: %s", g_err.c_str());
   CU(cudaSetDevice(b->device));
@@ -315,7 +315,7 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
           if ((int)nfr < Fc) { nfr += 1; flags |= 3u; new_pending = 0; flushed[s] = 1; }
         } else { flags |= 2u; flushed[s] = 1; }
       }
-      src[slot][s] = n[s] ? pcm[s] + cursor[s] : nullptr;
+      src[slot][s] = (pcm && pcm[s]) ? pcm[s] + cursor[s] : nullptr;
       pl.cur = device_ptrs ? src[slot][s] : b->d_stage[slot] + (size_t)s * b->stage_stride;
       pl.cur_n = (uint32_t)cur_n; pl.n_frames = nfr; pl.flags = flags; pl.head_n = (uint32_t)(fsc + b->pending[s]);
       if (cur_n || nfr || (flags & 2u)) any = true;
@@ -331,11 +331,16 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
     CU(cudaEventRecord(b->ev_h2d[slot][0], stc));
     if (!device_ptrs) {
       CU(cudaStreamWaitEvent(stc, b->ev_consumed[slot], 0));       // the kernels that last read this staging buffer
-      // one strided copy when every stream hands over the same amount from equally spaced host buffers
-      bool uniform = S > 1 && hp[0].cur_n > 0;
-      const size_t cur0 = hp[0].cur_n; ptrdiff_t pitch = 0;
+      // one strided copy when every stream that hands over data hands over the same amount and all buffers are equally
+      // spaced (streams without data in this pass may sit in between: their rows are copied too and never read)
+      size_t cur0 = 0;
+      for (int s = 0; s < S; ++s) cur0 = std::max<size_t>(cur0, hp[s].cur_n);
+      bool uniform = S > 1 && cur0 > 0;
+      ptrdiff_t pitch = 0;
       for (int s = 0; s < S && uniform; ++s) {
-        if (hp[s].cur_n != cur0) { uniform = false; break; }
+        // a stream without data in this pass may only sit in the copy if its row is known to be readable that far
+        const bool idle_ok = row_floats && src[slot][s] && (size_t)(src[slot][s] - pcm[s]) + cur0 <= row_floats;
+        if (!src[slot][s] || (hp[s].cur_n != cur0 && !(hp[s].cur_n == 0 && idle_ok))) { uniform = false; break; }
         if (s >= 1) {
           ptrdiff_t d = (const char *)src[slot][s] - (const char *)src[slot][s - 1];
           if (s == 1) pitch = d; else if (d != pitch) uniform = false;
@@ -579,6 +584,15 @@ int mp3b_batch_frames_per_pass(const mp3b_batch *b) { return b ? b->Fc : 0; }
 
 int mp3b_batch_encode(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, int flush, const uint8_t *flush_mask) {
   return run_call(b, pcm, n_floats, false, flush, flush_mask, true);
+}
+int mp3b_batch_encode_strided(mp3b_batch *b, const float *base, size_t pitch_floats, const size_t *n_floats, int flush, const uint8_t *flush_mask) {
+  if (!b || !base || !n_floats) return fail(MP3B_ERR_BAD_ARG, "null batch / base / n_floats");
+  std::vector<const float *> rows((size_t)b->S);
+  for (int s = 0; s < b->S; ++s) {
+    if (n_floats[s] > pitch_floats) return fail(MP3B_ERR_BAD_ARG, "stream %d: n_floats exceeds the row pitch", s);
+    rows[(size_t)s] = base + (size_t)s * pitch_floats;
+  }
+  return run_call(b, rows.data(), n_floats, false, flush, flush_mask, true, pitch_floats);
 }
 int mp3b_batch_encode_device(mp3b_batch *b, const float *const *d_pcm, const size_t *n_floats, int flush, int download) {
   return run_call(b, d_pcm, n_floats, true, flush, nullptr, download != 0);

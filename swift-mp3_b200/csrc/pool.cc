@@ -9,6 +9,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -22,18 +23,23 @@ struct Slot {
   bool pending = false;      // request deposited, step not yet run
   bool done = false;         // result ready for the waiting client
   int flush = 0, rc = 0;
-  std::vector<float> pcm;    // request (copied: the caller's array may be reused after return, SRC:298)
+  size_t n = 0;              // request: n floats, copied into the slot's arena row (the caller's array may be reused
+                             // after return, SRC:298) or, when larger than a row, into `big`
+  std::vector<float> big;
   std::vector<uint8_t> out;  // response
   std::string err;
+  std::mutex m;              // guards `done`: the worker wakes exactly the members of a step, not every waiting client
+  std::condition_variable cv;
 };
 }  // namespace
 
 struct mp3b_pool {
   mp3b_batch *batch = nullptr;
   int n = 0, max_wait_us = 0;
-  std::vector<Slot> slots;
+  std::vector<std::unique_ptr<Slot>> slot_store;
+  std::vector<Slot *> slots;
   std::mutex mu;
-  std::condition_variable cv_worker, cv_client;
+  std::condition_variable cv_worker;
   std::thread worker;
   bool stop = false;
   int n_open = 0, n_pending = 0;
@@ -41,6 +47,8 @@ struct mp3b_pool {
   // statistics
   uint64_t steps = 0, requests = 0;
   // step scratch (worker only)
+  float *arena = nullptr;    // pinned [n][row] staging: one strided upload per step
+  size_t row = 0;
   std::vector<const float *> ptrs;
   std::vector<size_t> lens;
   std::vector<uint8_t> mask;
@@ -60,22 +68,24 @@ static void pool_worker(mp3b_pool *p) {
     if (p->stop) return;
     // take the step's members; requests that arrive from now on belong to the next step
     p->members.clear();
-    int any_flush = 0;
+    int any_flush = 0; bool in_arena = true;
     for (int i = 0; i < p->n; ++i) {
-      Slot &s = p->slots[i];
+      Slot &s = *p->slots[i];
       const bool in = s.pending;
-      p->ptrs[i] = in && !s.pcm.empty() ? s.pcm.data() : nullptr;
-      p->lens[i] = in ? s.pcm.size() : 0;
+      p->ptrs[i] = !in ? nullptr : s.n > p->row ? s.big.data() : p->arena + (size_t)i * p->row;
+      p->lens[i] = in ? s.n : 0;
+      if (in && s.n > p->row) in_arena = false;
       p->mask[i] = in && s.flush ? 1 : 0;
       any_flush |= p->mask[i];
       if (in) { p->members.push_back(i); s.pending = false; }
     }
     p->n_pending = 0;
     lk.unlock();
-    int rc = mp3b_batch_encode(p->batch, p->ptrs.data(), p->lens.data(), any_flush, any_flush ? p->mask.data() : nullptr);
+    int rc = in_arena ? mp3b_batch_encode_strided(p->batch, p->arena, p->row, p->lens.data(), any_flush, any_flush ? p->mask.data() : nullptr)
+                      : mp3b_batch_encode(p->batch, p->ptrs.data(), p->lens.data(), any_flush, any_flush ? p->mask.data() : nullptr);
     std::string err = rc ? mp3b_last_error() : "";
     for (int i : p->members) {
-      Slot &s = p->slots[i];                      // only this thread and the (blocked) owner touch a member slot now
+      Slot &s = *p->slots[i];                      // only this thread and the (blocked) owner touch a member slot now
       s.rc = rc; s.err = err; s.out.clear();
       if (rc == MP3B_OK) {
         const uint8_t *data = nullptr; size_t len = 0;
@@ -83,10 +93,13 @@ static void pool_worker(mp3b_pool *p) {
         if (s.flush) mp3b_batch_reset_stream(p->batch, i);           // the slot goes back to a fresh EncoderSession
       }
     }
+    for (int i : p->members) {
+      Slot &s = *p->slots[i];
+      { std::lock_guard<std::mutex> g(s.m); s.done = true; }
+      s.cv.notify_one();
+    }
     lk.lock();
-    for (int i : p->members) p->slots[i].done = true;
     p->steps += 1; p->requests += p->members.size();
-    p->cv_client.notify_all();
   }
 }
 
@@ -101,7 +114,13 @@ int mp3b_pool_create(const mp3b_options *opts, int n_sessions, int device, int m
   if (rc) return rc;
   mp3b_pool *p = new mp3b_pool();
   p->batch = b; p->n = n_sessions; p->max_wait_us = max_wait_us;
-  p->slots.resize(n_sessions); p->ptrs.resize(n_sessions); p->lens.resize(n_sessions); p->mask.resize(n_sessions);
+  for (int i = 0; i < n_sessions; ++i) { p->slot_store.emplace_back(new Slot()); p->slots.push_back(p->slot_store.back().get()); }
+  p->ptrs.resize(n_sessions); p->lens.resize(n_sessions); p->mask.resize(n_sessions);
+  p->row = 4 * 1152 * 2;                                               // four stereo frames per call fit a row
+  void *arena = nullptr;
+  rc = mp3b_host_alloc((size_t)n_sessions * p->row * sizeof(float), &arena);
+  if (rc) { mp3b_batch_destroy(b); delete p; return rc; }
+  p->arena = (float *)arena;
   p->worker = std::thread(pool_worker, p);
   *out = p;
   return MP3B_OK;
@@ -110,9 +129,11 @@ int mp3b_pool_create(const mp3b_options *opts, int n_sessions, int device, int m
 void mp3b_pool_destroy(mp3b_pool *p) {
   if (!p) return;
   { std::lock_guard<std::mutex> lk(p->mu); p->stop = true; }
-  p->cv_worker.notify_all(); p->cv_client.notify_all();
+  p->cv_worker.notify_all();
+  for (Slot *s : p->slots) { { std::lock_guard<std::mutex> g(s->m); s->done = true; s->rc = MP3B_ERR_INTERNAL; s->err = "pool destroyed"; } s->cv.notify_all(); }
   if (p->worker.joinable()) p->worker.join();
   mp3b_batch_destroy(p->batch);
+  mp3b_host_free(p->arena);
   delete p;
 }
 
@@ -120,24 +141,34 @@ int mp3b_pool_open(mp3b_pool *p, int *slot) {
   if (!p || !slot) return MP3B_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lk(p->mu);
   for (int i = 0; i < p->n; ++i)
-    if (!p->slots[i].open) { p->slots[i] = Slot(); p->slots[i].open = true; p->n_open += 1; *slot = i; return MP3B_OK; }
+    if (!p->slots[i]->open) { Slot &s = *p->slots[i]; s.pending = s.done = false; s.flush = s.rc = 0; s.n = 0; s.open = true; p->n_open += 1; *slot = i; return MP3B_OK; }
   return MP3B_ERR_BAD_ARG;                         // every session of the pool is in use
 }
 
 static int pool_call(mp3b_pool *p, int slot, const float *pcm, size_t n_floats, int flush, uint8_t *out, size_t cap, size_t *written) {
   if (written) *written = 0;
   if (!p || slot < 0 || slot >= p->n || (n_floats && !pcm)) return MP3B_ERR_BAD_ARG;
-  std::unique_lock<std::mutex> lk(p->mu);
-  Slot &s = p->slots[slot];
-  if (!s.open || s.pending) return MP3B_ERR_BAD_ARG;                  // one call per session at a time (README:207)
-  s.pcm.assign(pcm, pcm + n_floats);
-  s.flush = flush; s.done = false; s.pending = true;
-  if (p->n_pending++ == 0) p->first_pending = std::chrono::steady_clock::now();
-  p->cv_worker.notify_one();
-  p->cv_client.wait(lk, [&] { return s.done || p->stop; });
-  if (!s.done) return MP3B_ERR_INTERNAL;
-  s.done = false;
-  if (flush) { s.open = false; p->n_open -= 1; p->cv_worker.notify_one(); }   // a flushed session no longer holds steps back
+  Slot &s = *p->slots[slot];
+  {
+    std::unique_lock<std::mutex> lk(p->mu);
+    if (!s.open || s.pending || p->stop) return MP3B_ERR_BAD_ARG;      // one call per session at a time (README:207)
+    s.n = n_floats;
+    if (n_floats > p->row) s.big.assign(pcm, pcm + n_floats);
+    else if (n_floats) memcpy(p->arena + (size_t)slot * p->row, pcm, n_floats * sizeof(float));
+    s.flush = flush; s.pending = true;
+    { std::lock_guard<std::mutex> g(s.m); s.done = false; }
+    if (p->n_pending++ == 0) p->first_pending = std::chrono::steady_clock::now();
+    if (p->n_pending == 1 || p->n_pending >= p->n_open) p->cv_worker.notify_one();   // first arrival opens the window, the last closes it
+  }
+  {
+    std::unique_lock<std::mutex> g(s.m);
+    s.cv.wait(g, [&] { return s.done; });
+    s.done = false;
+  }
+  if (flush) {                                                        // a flushed session no longer holds steps back
+    std::lock_guard<std::mutex> lk(p->mu);
+    s.open = false; p->n_open -= 1; p->cv_worker.notify_one();
+  }
   if (s.rc) { t_pool_err = s.err; return s.rc; }
   if (written) *written = s.out.size();
   if (s.out.size() > cap) return MP3B_ERR_BUFFER_TOO_SMALL;
