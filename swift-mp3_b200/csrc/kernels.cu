@@ -330,29 +330,43 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
   // mid/side transform: one 4-byte cp.async per sample, nothing waits until the next tile starts.
   auto load_rows = [&](int ra, int rb, int slot0) {
     rb = min(rb, rows_total);
-    if (ra < rb) {
-      const int64_t rel = (int64_t)(n_start + 32 * ra + 1152) * ch - (int64_t)pv.head_n;
-      if (!joint && rel >= 0 && rel + (int64_t)(rb - ra) * 32 * ch <= (int64_t)pv.cur_n) {
-        const float *src = pv.cur + rel + (ch == 1 ? lane : 2 * lane + c) + (size_t)warp * 32 * ch;
-        uint32_t dst = (uint32_t)__cvta_generic_to_shared(P + (slot0 + warp) * 32 + lane);
-        const int step = kFbWarps * 32 * ch;
-        for (int r = warp; r < rb - ra; r += kFbWarps, src += step, dst += kFbWarps * 128)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src));
+    const int ra0 = ra;
+    const int lane_off = ch == 1 ? lane : 2 * lane + c;
+    const int64_t rel0 = (int64_t)(n_start + 32 * ra + 1152) * ch - (int64_t)pv.head_n;
+    if (!joint && ra < rb && rel0 >= 0 && rel0 + (int64_t)(rb - ra) * 32 * ch <= (int64_t)pv.cur_n) {
+      // the whole range is inside this pass's PCM (the common case): no per-row address arithmetic
+      const float *src = pv.cur + rel0 + lane_off + (size_t)warp * 32 * ch;
+      uint32_t dst = (uint32_t)__cvta_generic_to_shared(P + (slot0 + warp) * 32 + lane);
+      const int step = kFbWarps * 32 * ch;
+      for (int r = warp; r < rb - ra; r += kFbWarps, src += step, dst += kFbWarps * 128)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src));
+      ra = rb;
+    }
+    // otherwise row by row: a row (32 ch consecutive floats) that lies entirely in this pass's PCM or entirely in the
+    // carried head and needs no mid/side transform is still a cp.async; only straddling / zero-padded / mid-side rows are
+    // loaded synchronously
+    for (int r = ra + warp; r < rb; r += kFbWarps) {
+      const int nrow = n_start + 32 * r;
+      const int64_t q = (int64_t)(nrow + 1152) * ch, rel = q - (int64_t)pv.head_n;
+      float *dstp = P + (slot0 + r - ra0) * 32 + lane;
+      const float *src = nullptr;
+      if (!joint) {
+        if (rel >= 0 && rel + 32 * ch <= (int64_t)pv.cur_n) src = pv.cur + rel + lane_off;
+        else if (q >= 0 && q + 32 * ch <= (int64_t)pv.head_n) src = pv.head + q + lane_off;
+      }
+      if (src) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dstp)), "l"(src));
       } else {
-        for (int r = ra + warp; r < rb; r += kFbWarps) {
-          const int nrow = n_start + 32 * r;
-          const int64_t q = (int64_t)(nrow + 1152) * ch;
-          float v;
-          if (ch == 1) v = pv.at(q + lane);
-          else {
-            const float l = pv.at(q + 2 * lane), rr = pv.at(q + 2 * lane + 1);
-            const int fr = nrow >= 0 ? nrow / 1152 : -1;
-            const bool ms = joint && (fr < 0 ? ms_prev != 0 : msrow[1 + fr] != 0);
-            if (!ms) v = c == 0 ? l : rr;
-            else v = c == 0 ? __fmul_rn(__fadd_rn(l, rr), 0.5f) : __fmul_rn(__fsub_rn(l, rr), 0.5f);   // SRC:2148-2154
-          }
-          P[(slot0 + r - ra) * 32 + lane] = v;
+        float v;
+        if (ch == 1) v = pv.at(q + lane);
+        else {
+          const float l = pv.at(q + 2 * lane), rr = pv.at(q + 2 * lane + 1);
+          const int fr = nrow >= 0 ? nrow / 1152 : -1;
+          const bool ms = joint && (fr < 0 ? ms_prev != 0 : msrow[1 + fr] != 0);
+          if (!ms) v = c == 0 ? l : rr;
+          else v = c == 0 ? __fmul_rn(__fadd_rn(l, rr), 0.5f) : __fmul_rn(__fsub_rn(l, rr), 0.5f);   // SRC:2148-2154
         }
+        *dstp = v;
       }
     }
     asm volatile("cp.async.commit_group;");
