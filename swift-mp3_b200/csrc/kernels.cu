@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
       // ---- matrixing (SRC:1402-1408): S[k] = sum over ascending n of M[k][n] * Y[n], one fused multiply-add per term
       if (64 * warp < valid) {
         const float4 *mrow = reinterpret_cast<const float4 *>(sM + (32 * H) * 32 + kg * 16);
-#pragma unroll 1
+#pragma unroll 2
         for (int a = 0; a < 4; ++a) {
 #pragma unroll
           for (int b = 0; b < 8; ++b) {
