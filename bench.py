@@ -2,9 +2,10 @@
 """bench.py — headline benchmark of the B200-native MP3 encode path.
 
 Metric (BASELINE.json): encoded audio seconds per second (x realtime), whole job over all GPUs.
-Workload (BASELINE config 4, weak scaling): every GPU encodes its shard of the batch of independent 30 s 44.1 kHz
-stereo CBR 128 kbps streams — 512 streams per GPU, i.e. the named 4096-stream batch at N = 8.  One "step" = every
-stream of the shard through fresh EncoderSessions: encode(samples:) of the whole stream + flush().
+Workload (BASELINE config 4, strong scaling): the batch of 4096 independent 30 s 44.1 kHz stereo CBR 128 kbps streams,
+sharded by stream over the N GPUs (4096 / N streams each; at N = 1 the whole batch, 43 GB of PCM, sits on one B200).  One
+"step" = every stream of the shard through fresh EncoderSessions: encode(samples:) of the whole stream + flush().
+`--streams K` switches to K streams per GPU (weak scaling; reduced runs for profiling).
 
   value : PCM already resident in HBM, MP3 frames left in HBM (device plane of the C ABI), timed with CUDA events on
           the engine's own stream, max over ranks.
@@ -28,6 +29,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SR, CH, KBPS = 44100, 2, 128
+TOTAL_STREAMS = 4096                               # BASELINE config 4
 # Algorithmic bytes / flops per granule-channel (gc = 576 samples of one channel), DESIGN.md section 4
 ALGO_BYTES = {"prepass": 2304 + 8,                 # PCM in, decisions out
               "filterbank": 2304 + 2304,           # PCM in, 18 x 32 subband samples out
@@ -159,7 +161,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native")
-    ap.add_argument("--streams", type=int, default=512, help="streams per GPU")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="streams per GPU; 0 (default) = BASELINE config 4: 4096 streams in total, sharded over the GPUs (strong scaling)")
     ap.add_argument("--seconds", type=float, default=30.0)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -169,8 +172,11 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     metric = "encoded audio sec/sec (x realtime)"
-    workload = ("C4 shard: %d independent %.0f s 44.1 kHz stereo CBR 128 kbps streams per GPU (4096 x 30 s at 8 GPUs); "
-                "inputs %.1f GB per GPU > L2" % (a.streams, a.seconds, a.streams * a.seconds * SR * CH * 4 / 1e9))
+    strong = a.streams <= 0
+    if strong:
+        a.streams = TOTAL_STREAMS // world
+    workload = ("C4: batch of %d independent %.0f s 44.1 kHz stereo CBR 128 kbps streams sharded by stream over %d GPU(s), %d per "
+                "GPU; inputs %.1f GB per GPU > L2" % (a.streams * world, a.seconds, world, a.streams, a.streams * a.seconds * SR * CH * 4 / 1e9))
 
     if a.impl == "reference":
         if rank != 0:
@@ -178,7 +184,7 @@ def main():
         res, el, audio = cpu_reference(a.seconds, min_wall=max(5.0, 2.0 * a.steps), max_wall=120.0)
         line = {"impl": "reference", "metric": metric, "value": res["value"], "unit": "x realtime", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * el / max(a.steps, 1), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "reference": "C restatement of SwiftMP3 (oracle/); the Swift + Accelerate "
                            "original cannot be built on Linux"},
                 "cpu_baseline": res,
@@ -215,7 +221,7 @@ def main():
         rc = bench_c5(a, mp3, L, local, rank, world)
         sampler.stop()
         return rc
-    S = a.streams                                                  # weak scaling: a.streams per GPU
+    S = a.streams                                                  # streams of this rank
     shard_lo, shard_hi = sharding.shard_range(S * world, rank, world)
     assert shard_hi - shard_lo == S
     n_per = int(round(a.seconds * SR))
@@ -358,7 +364,7 @@ def main():
     total_launches = int(sum_over_ranks(launches))
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": "x realtime", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {"workload": workload, "streams_per_gpu": S, "seconds_per_stream": a.seconds,
                                                 "frames_per_pass": b.frames_per_pass, "l2": "inputs larger than L2",
                                                 "parity": parity, "output_bytes_per_step_per_gpu": int(out_bytes), "host_numa": numa},

@@ -11,7 +11,7 @@ python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.jso
 python bench.py --workload c5 --steps 300 > gpurun_out/c5.json 2> gpurun_out/c5.err; echo c5 rc=$?
 [ -x tools/pool_latency ] && ./tools/pool_latency 1024 200 300 > gpurun_out/c5_pool.json 2> gpurun_out/c5_pool.err
 KERN="regex:k_(prepass|bitrate|filterbank|granule|scan|pack|frames|carry|offsets|gather)"
-FULL="python bench.py --steps 2 --warmup 3 --e2e-steps 1 --no-cpu"
+FULL="python bench.py --steps 1 --warmup 3 --e2e-steps 1 --no-cpu"
 $FULL > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERN" -c 400 --csv --log-file gpurun_out/launches.csv $FULL > gpurun_out/ncu1.log 2>&1
 echo ncu1 rc=$?
