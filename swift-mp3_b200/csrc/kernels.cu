@@ -303,7 +303,8 @@ constexpr int kFbWarps = kFbThreads / 32;
 constexpr int kFbSmemFloats = 64 * 32 + kPRows * 32 + 32 * kTile;
 constexpr int kFbSmemBytes = kFbSmemFloats * 4;
 
-__global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBuffers pb, int R) {
+__global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBuffers pb, int Rdbg) {
+  const int R = Rdbg & 0xFFFF, dbg = Rdbg >> 16;     // dbg: timing experiments only (tools/stage_times.py), 0 in production
   extern __shared__ __align__(16) float sm[];
   float *sM = sm;                                  // [64 n][32 k] analysis matrix, transposed
   float *P = sM + 64 * 32;                         // [271][32] PCM rows of the tile
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
   // PCM rows [ra, rb) of the run -> P rows slot0 ...  Fast path: the rows are contiguous in this pass's PCM and need no
   // mid/side transform: one 4-byte cp.async per sample, nothing waits until the next tile starts.
   auto load_rows = [&](int ra, int rb, int slot0) {
-    rb = min(rb, rows_total);
+    rb = (dbg & 4) ? ra : min(rb, rows_total);
     const int ra0 = ra;
     const int lane_off = ch == 1 ? lane : 2 * lane + c;
     const int64_t rel0 = (int64_t)(n_start + 32 * ra + 1152) * ch - (int64_t)pv.head_n;
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
       // between the phases.  Block-wide barriers only guard P: its arrival here, its reuse after the last windowing.
       if (H == 0) __syncthreads(); else __syncwarp();
       // ---- windowing (SRC:1386-1399): X[n + 64 i] of step u = sample at tile row u + 15 - 2 i - H, column 31 - lane
-      if (64 * warp < valid) {                     // warp-uniform: a short last tile skips the steps beyond the run
+      if (64 * warp < valid && !(dbg & 1)) {                     // warp-uniform: a short last tile skips the steps beyond the run
         const float *Pc = P + (64 * warp + 1 - H) * 32 + (31 - lane);   // oldest row of the first step pair
         float2 q[8];
 #pragma unroll
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
         load_rows(kTile * (tile + 1) + kLook, kTile * (tile + 2) + kLook, kLook);     // lands during the matrixing
       }
       // ---- matrixing (SRC:1402-1408): S[k] = sum over ascending n of M[k][n] * Y[n], one fused multiply-add per term
-      if (64 * warp < valid) {
+      if (64 * warp < valid && !(dbg & 2)) {
         const float4 *mrow = reinterpret_cast<const float4 *>(sM + (32 * H) * 32 + kg * 16);
 #pragma unroll 2
         for (int a = 0; a < 4; ++a) {
@@ -463,16 +464,29 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
         }
       }
     }
-    // subband samples -> HBM: step row = 32 floats, this thread owns 16 of them for four consecutive steps
-    {
-      const int t0 = 64 * warp + 4 * tg;
-      float4 *dst = reinterpret_cast<float4 *>(out + (size_t)(kTile * tile + t0) * 32 + 16 * kg);
+    // subband samples -> HBM.  A thread owns 16 of the 32 subbands of four steps; written directly that is 32 scattered
+    // 16-byte pieces per store instruction.  The warp's own 8 KB of Y (it alone reads it, and is done with it) is used to
+    // transpose: 16-byte chunk c of step row t goes to slot t * 8 + (c ^ ((t >> 2) & 7)) — conflict-free both ways — and
+    // comes back as whole 128-byte rows, four rows per store instruction.
+    if (64 * warp < valid) {
+      __syncwarp();
+      auto slot = [&](int t, int cidx) {             // float offset of a chunk inside the warp's slice of Y
+        const int q = t * 8 + (cidx ^ ((t >> 2) & 7));
+        return (q >> 4) * kTile + ((16 * warp + (q & 15)) << 2);
+      };
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (t0 + j < valid) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dst[j * 8 + i] = make_float4(acc[j][2 * i].x, acc[j][2 * i].y, acc[j][2 * i + 1].x, acc[j][2 * i + 1].y);
-        }
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4 *>(Y + slot(4 * tg + j, 4 * kg + i)) = make_float4(acc[j][2 * i].x, acc[j][2 * i].y, acc[j][2 * i + 1].x, acc[j][2 * i + 1].y);
+      __syncwarp();
+      const int rows = min(64, valid - 64 * warp);
+      float4 *dst = reinterpret_cast<float4 *>(out + (size_t)(kTile * tile + 64 * warp) * 32);
+#pragma unroll 4
+      for (int it = 0; it < 16; ++it) {
+        const int t = 4 * it + (lane >> 3), cidx = lane & 7;
+        if (t < rows && !(dbg & 8)) dst[t * 8 + cidx] = *reinterpret_cast<const float4 *>(Y + slot(t, cidx));
+      }
     }
   }
 }
@@ -1137,7 +1151,9 @@ int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   while (R > 14 && (long long)cfg.n_streams * cfg.channels * ((ngr + R - 1) / R) < 148 * 6) R = R > 64 ? 64 : R > 28 ? 28 : 14;
   if (R > ngr) R = ngr;
   dim3 grid(cfg.channels, cfg.n_streams, (ngr + R - 1) / R);
-  k_filterbank<<<grid, kFbThreads, kFbSmemBytes, st>>>(cfg, pb, R);
+  static int dbg = -1;
+  if (dbg < 0) { const char *v = getenv("MP3B_FB_DEBUG"); dbg = v ? atoi(v) : 0; }
+  k_filterbank<<<grid, kFbThreads, kFbSmemBytes, st>>>(cfg, pb, R | dbg << 16);
   return check(1);
 }
 int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
