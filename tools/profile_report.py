@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Turn the outputs of tools/gpu_round.sh (gpurun_out/) into the committed evidence under profiles/ (round 1):
-  r01_launches.csv            ncu --metrics gpu__time_duration.sum launch list of `bench.py --steps 2 --warmup 3`
+  r01_launches.csv            ncu --metrics gpu__time_duration.sum launch list of `bench.py --steps 1 --warmup 3` (first 400 launches)
   r01_launch_shares.txt       per kernel and grid: launches, mean duration, share of the device-plane step
   r01_ncu_full_summary.txt    headline metrics + per-phase stall / opcode mix of the hot kernels (ncu --set full)
   r01_kernel_traffic.json     DRAM bytes and pipe utilisation per kernel (read by bench.py)
@@ -23,9 +23,9 @@ for (k, g), v in by.items():
         best[k] = (g, m, len(v))
 tot = sum(m for _, m, _ in best.values())
 with open(os.path.join(P, "r01_launch_shares.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 2 --warmup 3 --e2e-steps 1 --no-cpu`\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 400, `python bench.py --steps 1 --warmup 3 --e2e-steps 1 --no-cpu`\n")
     f.write("# (serialised, cold-cache launches: compare SHARES with bench.py's roofline.stages[*].share, not absolutes)\n")
-    f.write("# device-plane pass (512 streams x 512 frames) = per kernel the grid with the largest mean duration:\n")
+    f.write("# device-plane pass (4096 streams x 64 frames) = per kernel the grid with the largest mean duration; k_gather / k_offsets belong\n# to the (untimed) parity download, k_scan / k_carry have one grid for every pass size:\n")
     for k, (g, m, n) in sorted(best.items(), key=lambda kv: -kv[1][1]):
         f.write("%-14s grid %-18s launches %3d  mean %9.1f us  share of pass %5.1f %%\n" % (k, g, n, m, 100 * m / tot))
     f.write("\n# every (kernel, grid) group of the list:\n")
