@@ -393,6 +393,8 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
 #pragma unroll
   for (int b = 0; b < 8; ++b) yo[b] = b * kTile + (((16 * warp + tg) ^ b) << 2);
 
+  const float *pf_src = nullptr; uint32_t pf_dst = 0; int pf_left = 0;   // cp.async of the next tile still to be issued by this warp
+  const int pf_step = kFbWarps * 32 * ch;
   for (int tile = 0; tile < n_tiles; ++tile) {
     float2 acc[4][8];
 #pragma unroll
@@ -442,7 +444,18 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
         // look-back of the next tile = last 15 rows of this one; each warp moves the rows its own cp.async is about to
         // overwrite (program order inside the warp), so no barrier is needed in between
         for (int r = kTile + ((warp - (kTile - kLook)) & (kFbWarps - 1)); r < kPRows; r += kFbWarps) P[(r - kTile) * 32 + lane] = P[r * 32 + lane];
-        load_rows(kTile * (tile + 1) + kLook, kTile * (tile + 2) + kLook, kLook);     // lands during the matrixing
+        // Common case (the next tile's rows lie wholly in this pass's PCM): the 64 cp.async of this warp are not issued
+        // in one burst — which fills the memory-instruction queue that the matrixing's LDS.128 of all resident CTAs go
+        // through — but two per n inside the matrixing loop below.
+        const int ra = kTile * (tile + 1) + kLook, rb = min(kTile * (tile + 2) + kLook, rows_total);
+        const int64_t rel0 = (int64_t)(n_start + 32 * ra + 1152) * ch - (int64_t)pv.head_n;
+        if (!joint && ra < rb && rel0 >= 0 && rel0 + (int64_t)(rb - ra) * 32 * ch <= (int64_t)pv.cur_n) {
+          pf_src = pv.cur + rel0 + (ch == 1 ? lane : 2 * lane + c) + (size_t)warp * 32 * ch;
+          pf_dst = (uint32_t)__cvta_generic_to_shared(P + (kLook + warp) * 32 + lane);
+          pf_left = (rb - ra - warp + kFbWarps - 1) / kFbWarps;
+        } else {
+          load_rows(ra, rb, kLook);
+        }
       }
       // ---- matrixing (SRC:1402-1408): S[k] = sum over ascending n of M[k][n] * Y[n], one fused multiply-add per term
       if (64 * warp < valid && !(dbg & 2)) {
@@ -452,6 +465,14 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
 #pragma unroll
           for (int b = 0; b < 8; ++b) {
             const int nl = 8 * a + b;
+            if (H == 1) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u)
+                if (pf_left > 0) {
+                  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pf_dst), "l"(pf_src));
+                  pf_src += pf_step; pf_dst += kFbWarps * 128; --pf_left;
+                }
+            }
             const float4 m0 = mrow[nl * 8], m1 = mrow[nl * 8 + 1], m2 = mrow[nl * 8 + 2], m3 = mrow[nl * 8 + 3];
             const float4 y = *reinterpret_cast<const float4 *>(Y + a * 8 * kTile + yo[b]);
             const float yv[4] = {y.x, y.y, y.z, y.w};
@@ -464,6 +485,11 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
         }
       }
     }
+    while (pf_left > 0) {                           // (a warp that skipped the matrixing of a short tile)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pf_dst), "l"(pf_src));
+      pf_src += pf_step; pf_dst += kFbWarps * 128; --pf_left;
+    }
+    asm volatile("cp.async.commit_group;");
     // subband samples -> HBM.  A thread owns 16 of the 32 subbands of four steps; written directly that is 32 scattered
     // 16-byte pieces per store instruction.  The warp's own 8 KB of Y (it alone reads it, and is done with it) is used to
     // transpose: 16-byte chunk c of step row t goes to slot t * 8 + (c ^ ((t >> 2) & 7)) — conflict-free both ways — and
