@@ -201,7 +201,8 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   A(dalloc(p.gc_meta, S * GC)); A(dalloc(p.gc_bits, S * GC * kMaxEntries)); A(dalloc(p.gc_bv, S * GC * kMaxEntries));
   A(dalloc(p.gc_bitoff, S * GC)); A(dalloc(p.gc_sel, S * GC)); A(dalloc(p.fr_md, S * Fc * 2)); A(dalloc(p.rec, S * (Fc + 1))); A(dalloc(p.emit, S * (Fc + 1)));
   p.md_stride = round_up<size_t>(kMdCarryCap + (size_t)Fc * 2 * cfg.channels * 540, 16);
-  A(dalloc(p.md, S * p.md_stride, false)); A(dalloc(p.md_tail, S * 4)); A(dalloc(p.md_carry, S * kMdCarryCap));
+  A(dalloc(p.md, S * p.md_stride + 16, false));   // + one word: k_frames reads aligned word pairs
+  A(dalloc(p.md_tail, S * 4)); A(dalloc(p.md_carry, S * kMdCarryCap));
   A(dalloc(p.emit_size, S * (Fc + 1))); A(dalloc(p.emit_n, S));
   A(dalloc(b->d_offsets, S + 1));
   A(cudaHostAlloc((void **)&b->h_plan, 2 * S * sizeof(StreamPlan), cudaHostAllocDefault));

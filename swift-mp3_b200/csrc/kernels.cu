@@ -1005,10 +1005,33 @@ __global__ void __launch_bounds__(128) k_frames(Config cfg, PassBuffers pb) {
   dst += cfg.header_bytes;
   const uint32_t B0 = pb.md_tail[(size_t)s * 4 + 2];
   const uint8_t *carry = pb.md_carry + (size_t)s * kMdCarryCap, *md = pb.md + (size_t)s * pb.md_stride;
-  for (uint32_t i = lane; i < fr.slot; i += 32) {
-    uint8_t b = 0;
-    if (i < em.take) { uint32_t o = em.src_off + i; b = o < B0 ? carry[o] : md[o]; }
-    dst[i] = b;
+  // fillSlot: `take` bytes from the FIFO, zero padding up to the slot size.  When the bytes all come from this pass's part
+  // of the FIFO, the middle of the slot is copied as aligned words (two aligned source words funnel-shifted per word).
+  auto byte_at = [&](uint32_t i) -> uint8_t {
+    if (i >= em.take) return 0;
+    const uint32_t o = em.src_off + i;
+    return o < B0 ? carry[o] : md[o];
+  };
+  const uint32_t slot = fr.slot;
+  if (em.src_off >= B0 || em.take == 0) {
+    const uint32_t head = min((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u, slot), words = (slot - head) >> 2;
+    if (lane < head) dst[lane] = byte_at(lane);
+    for (uint32_t i = head + 4 * words + lane; i < slot; i += 32) dst[i] = byte_at(i);
+    uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+    const uint32_t *mw = reinterpret_cast<const uint32_t *>(md);
+    for (uint32_t k = lane; k < words; k += 32) {
+      const uint32_t i0 = head + 4 * k;
+      uint32_t w = 0;
+      if (i0 < em.take) {
+        const uint32_t o = em.src_off + i0;
+        w = __funnelshift_r(mw[o >> 2], mw[(o >> 2) + 1], 8 * (o & 3));
+        const uint32_t left = em.take - i0;                       // bytes of this word that exist
+        if (left < 4) w &= (1u << (8 * left)) - 1u;
+      }
+      dw[k] = w;
+    }
+  } else {
+    for (uint32_t i = lane; i < slot; i += 32) dst[i] = byte_at(i);
   }
 }
 
