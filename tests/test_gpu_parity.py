@@ -251,3 +251,51 @@ def test_session_pool_concurrent_threads(mp3, orc):
     rs = orc.Session()
     assert again == rs.encode(pcms[0][:2304 * 3]) + rs.flush()
     pool.close()
+
+
+def test_fuzz_against_oracle(mp3, orc):
+    """Seeded random walk over options, stream lengths, chunkings, pass sizes and batch widths: every stream of every case,
+    fed in ragged chunks through the batch plane, must equal its own oracle session fed the same chunks."""
+    import os
+    rng = np.random.default_rng(int(os.environ.get("MP3B_FUZZ_SEED", "20261018")))
+    rates = [(44100, [32, 64, 96, 128, 160, 192, 256, 320]), (48000, [64, 128, 192, 320]), (32000, [32, 64, 128, 320])]
+    for case in range(int(os.environ.get("MP3B_FUZZ_CASES", "28"))):   # soak: MP3B_FUZZ_CASES=400 MP3B_FUZZ_SEED=...
+        sr, brs = rates[rng.integers(len(rates))]
+        mode = ["mono", "stereo", "jointStereo"][rng.integers(3)]
+        cfg = dict(sample_rate=sr, bitrate_kbps=int(brs[rng.integers(len(brs))]), mode=mode, vbr=bool(rng.integers(2)),
+                   quality=int(rng.integers(10)), crc_protected=bool(rng.integers(2)))
+        ch = 1 if mode == "mono" else 2
+        S = int(rng.integers(1, 6))
+        fpp = int(rng.choice([0, 3, 8, 17, 40]))
+        pcms = []
+        for i in range(S):
+            secs = float(rng.uniform(0.0, 2.2)) if rng.integers(8) else 0.0
+            kind = rng.integers(3)
+            if kind == 0:
+                x = signals.sine_noise(secs, sr=sr, channels=ch, seed=int(rng.integers(1 << 30)), amp=float(rng.uniform(0.01, 0.9)),
+                                       noise=float(rng.uniform(0.0, 0.3)), f_left=float(rng.uniform(50, 8000)), f_right=float(rng.uniform(50, 8000)))
+            elif kind == 1:
+                x = signals.castanets(secs, sr=sr, seed=int(rng.integers(1 << 30)), period=float(rng.uniform(0.05, 0.4)))
+                x = x if ch == 2 else x[::2].copy()
+            else:
+                x = (rng.standard_normal(int(secs * sr) * ch) * float(rng.choice([1e-6, 1e-3, 0.2, 2.0]))).astype(np.float32)
+                x = np.clip(x, -1.0, 1.0)
+            pcms.append(np.ascontiguousarray(x[: (x.size // ch) * ch - int(rng.integers(0, 3)) * 0]))
+        n_calls = int(rng.integers(1, 5))
+        cuts = [sorted(int(c) for c in rng.integers(0, p.size + 1, n_calls - 1)) for p in pcms]
+        b = mp3.EncoderBatch(_opts(mp3, **cfg), S, 0, fpp)
+        refs = [orc.Session(**cfg) for _ in range(S)]
+        for k in range(n_calls):
+            chunks = []
+            for i, p in enumerate(pcms):
+                lo = cuts[i][k - 1] if k > 0 else 0
+                hi = cuts[i][k] if k < n_calls - 1 else p.size
+                chunks.append(p[lo:hi])
+            last = k == n_calls - 1
+            outs = b.encode(chunks, flush=last)
+            for i in range(S):
+                want = refs[i].encode(chunks[i]) + (refs[i].flush() if last else b"")
+                assert outs[i] == want, "case %d %s stream %d call %d" % (case, cfg, i, k)
+        for i in range(S):
+            assert b.frame_count(i) == refs[i].frame_count and b.byte_count(i) == refs[i].byte_count
+        b.close()
