@@ -122,7 +122,10 @@ int fill_config(const mp3b_options &o, int n_streams, Config &c) {
   if (c.vbr) {
     int lo = std::max(32, c.base_kbps - 64 + c.quality * 8), hi = std::min(320, c.base_kbps + 64 - c.quality * 4);
     lo_idx = 15; hi_idx = 0;
-    for (int k = std::min(lo, hi); k <= std::max(lo, hi); ++k) { lo_idx = std::min<int>(lo_idx, c.vbr_idx_of_kbps[k]); hi_idx = std::max<int>(hi_idx, c.vbr_idx_of_kbps[k]); }
+    for (int k = std::min(lo, hi); k <= std::max(lo, hi); ++k) {     // lo may exceed 320 (base 320, quality 9): k_bitrate clamps the same way
+      const int kk = std::min(std::max(k, 0), 320);
+      lo_idx = std::min<int>(lo_idx, c.vbr_idx_of_kbps[kk]); hi_idx = std::max<int>(hi_idx, c.vbr_idx_of_kbps[kk]);
+    }
   }
   for (int i = lo_idx; i <= hi_idx; ++i)
     if (c.frame_base[i] - c.header_bytes < 2 * c.channels || c.frame_base[i] + 1 > 65000)

@@ -188,6 +188,7 @@ def test_batch_shard_properties(mp3, orc):
                                  dict(sample_rate=44100, bitrate_kbps=32, mode="mono"),          # smallest budget
                                  dict(sample_rate=48000, bitrate_kbps=131),                      # off-table bitrate snaps (SRC:2519-2521)
                                  dict(sample_rate=44100, bitrate_kbps=160, vbr=True, quality=9, mode="mono"),
+                                 dict(sample_rate=44100, bitrate_kbps=320, vbr=True, quality=9),       # VBR floor 328 > ceiling 320 (found by the fuzz test)
                                  dict(sample_rate=44100, bitrate_kbps=96, vbr=True, quality=0, mode="jointStereo", crc_protected=True)])
 def test_unusual_configurations(mp3, orc, cfg):
     ch = 1 if cfg.get("mode") == "mono" else 2
