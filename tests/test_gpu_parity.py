@@ -293,7 +293,20 @@ def test_fuzz_against_oracle(mp3, orc):
                 hi = cuts[i][k] if k < n_calls - 1 else p.size
                 chunks.append(p[lo:hi])
             last = k == n_calls - 1
-            outs = b.encode(chunks, flush=last)
+            if case % 3 == 0:                            # device plane: PCM already in HBM, at 4-byte (not 8-byte) aligned addresses
+                import ctypes as C
+                import torch
+                keep, ptrs = [], []
+                for c_ in chunks:
+                    off = int(rng.integers(0, 4))
+                    t = torch.zeros(c_.size + off + 1, dtype=torch.float32, device="cuda")
+                    t[off:off + c_.size] = torch.from_numpy(np.ascontiguousarray(c_))
+                    keep.append(t); ptrs.append(t.data_ptr() + 4 * off)
+                torch.cuda.synchronize()
+                b.encode_device((C.c_void_p * S)(*ptrs), (C.c_size_t * S)(*[c_.size for c_ in chunks]), flush=last, download=True)
+                outs = b.outputs()
+            else:
+                outs = b.encode(chunks, flush=last)
             for i in range(S):
                 want = refs[i].encode(chunks[i]) + (refs[i].flush() if last else b"")
                 assert outs[i] == want, "case %d %s stream %d call %d" % (case, cfg, i, k)
