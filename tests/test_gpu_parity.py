@@ -313,3 +313,19 @@ def test_fuzz_against_oracle(mp3, orc):
         for i in range(S):
             assert b.frame_count(i) == refs[i].frame_count and b.byte_count(i) == refs[i].byte_count
         b.close()
+
+
+def test_joint_vbr_long_runs(mp3, orc):
+    """Joint stereo + VBR + transients with enough streams and audio that the filterbank uses its longest runs (128 granules,
+    nine 256-step tiles per CTA) together with the synchronous mid/side loader: four of the streams against the oracle."""
+    S, secs = 48, 20.0
+    cfg = dict(sample_rate=44100, bitrate_kbps=128, mode="jointStereo", vbr=True, quality=3)
+    base = [signals.castanets(secs, seed=40 + i, period=0.11 + 0.03 * i) for i in range(4)]
+    pcms = [base[i % 4] for i in range(S)]
+    b = mp3.EncoderBatch(_opts(mp3, **cfg), S, 0)
+    outs = b.encode(pcms, flush=True)
+    for i in range(4):
+        ref, rs = orc.encode_all(base[i], **cfg)
+        assert outs[i] == ref and outs[i + 44] == ref, "stream %d" % i
+        assert b.frame_count(i) == rs.frame_count
+    b.close()
