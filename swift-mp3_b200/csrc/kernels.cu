@@ -528,7 +528,7 @@ __device__ __forceinline__ int lo_bits_of(const Config &cfg, int bri) {
 }
 
 constexpr int kGranulePerWarp = 1;   // 4 measured slower (6.0 vs 5.7 ms): one granule-channel per warp keeps the tail short
-__global__ void __launch_bounds__(256) k_granule(Config cfg, PassBuffers pb) {
+template <bool TRACE> __global__ void __launch_bounds__(256) k_granule(Config cfg, PassBuffers pb) {   // TRACE: also leave the MDCT spectrum behind
   __shared__ uint8_t len15[256];                  // table-15 code length of a pair + its sign bits (SRC:828-853)
   __shared__ __align__(8) float smg[8][576];
   len15[threadIdx.x] = tab::kHuff15Len[threadIdx.x] + ((threadIdx.x >> 4) != 0) + ((threadIdx.x & 15) != 0);
@@ -604,13 +604,13 @@ __global__ void __launch_bounds__(256) k_granule(Config cfg, PassBuffers pb) {
   }
   // |x|^0.75 (SRC:805-813 [OD3]), peak -> g0 (SRC:989-1006), preflag (SRC:2042-2066); line i = lane + 32 j
   {
-    float *spec = pb.spec ? pb.spec + gslot * 576 : nullptr;   // trace plane only
+    float *spec = TRACE ? pb.spec + gslot * 576 : nullptr;       // trace plane only; no predicated-off stores otherwise
     float *smag = pb.smag + gslot * 576;
     float x[18];
 #pragma unroll
     for (int j = 0; j < 18; ++j) x[j] = smg[warp][lane + 32 * j];
     __syncwarp();
-    if (spec) {
+    if (TRACE) {
 #pragma unroll
       for (int j = 0; j < 18; ++j) spec[lane + 32 * j] = x[j];
     }
@@ -870,7 +870,7 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
 // per gc.  Lane L codes pairs 9L...9L+8, so a warp prefix sum of the lane bit counts gives every lane its bit
 // position; codes are OR-ed MSB-first into a shared bit buffer and the frame's bytes are written once.
 constexpr int kPackFramesPerCta = 4;
-__global__ void __launch_bounds__(128) k_pack(Config cfg, PassBuffers pb) {
+template <bool TRACE> __global__ void __launch_bounds__(128) k_pack(Config cfg, PassBuffers pb) {   // TRACE: also leave ix behind
   __shared__ uint32_t buf[548];
   __shared__ uint16_t tab15[256];                  // code | length << 8
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -888,14 +888,14 @@ __global__ void __launch_bounds__(128) k_pack(Config cfg, PassBuffers pb) {
     const int gain = sel & 255, bv = sel >> 8;
     const float inv = __fmul_rn(c_inv_step[gain], 2.0f);
     const float2 *sm2 = reinterpret_cast<const float2 *>(pb.smag + gslot * 576);
-    int32_t *trix = pb.tr_ix ? pb.tr_ix + gslot * 576 : nullptr;
+    int32_t *trix = TRACE ? pb.tr_ix + gslot * 576 : nullptr;
     uint32_t val[9]; int len[9]; int mine = 0;
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
       const int p = 9 * lane + j;
       float2 v = sm2[p];
       int qx = quant15(fabsf(v.x), inv), qy = quant15(fabsf(v.y), inv);
-      if (trix) { trix[2 * p] = v.x < 0.0f ? -qx : qx; trix[2 * p + 1] = v.y < 0.0f ? -qy : qy; }
+      if (TRACE) { trix[2 * p] = v.x < 0.0f ? -qx : qx; trix[2 * p + 1] = v.y < 0.0f ? -qy : qy; }
       const uint32_t t15 = tab15[qx * 16 + qy];
       uint32_t code = t15 & 255u; int l = (int)(t15 >> 8);
       if (qx) { code = code << 1 | (v.x < 0.0f ? 1u : 0u); ++l; }   // SRC:1729-1736
@@ -1208,7 +1208,7 @@ int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
 int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   if (pb.max_frames <= 0) return 0;
   dim3 grid(cfg.n_streams, (pb.max_frames * 2 * cfg.channels + 8 * kGranulePerWarp - 1) / (8 * kGranulePerWarp));
-  k_granule<<<grid, 256, 0, st>>>(cfg, pb);
+  if (pb.spec) k_granule<true><<<grid, 256, 0, st>>>(cfg, pb); else k_granule<false><<<grid, 256, 0, st>>>(cfg, pb);
   return check(1);
 }
 int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
@@ -1218,7 +1218,7 @@ int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
 int launch_pack(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   if (pb.max_frames <= 0) return 0;
   dim3 grid(cfg.n_streams, (pb.max_frames + kPackFramesPerCta - 1) / kPackFramesPerCta);
-  k_pack<<<grid, 128, 0, st>>>(cfg, pb);
+  if (pb.tr_ix) k_pack<true><<<grid, 128, 0, st>>>(cfg, pb); else k_pack<false><<<grid, 128, 0, st>>>(cfg, pb);
   return check(1);
 }
 int launch_frames(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
