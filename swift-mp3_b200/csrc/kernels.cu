@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
   __shared__ __align__(16) uint16_t sh_bits[32 * 4 * kMaxEntries];
   __shared__ uint32_t sh_meta[32 * 4];
   __shared__ uint8_t sh_bri[32];
-  __shared__ uint8_t sh_sel[32 * 4][4];       // chosen entry, gain_out, gain_used, iterations
+  __shared__ __align__(4) uint8_t sh_sel[32 * 4][4];       // chosen entry, gain_out, gain_used, iterations
   __shared__ ScanFrame sh_fr[32];
   __shared__ int sh_state[8];
   const int s = blockIdx.x, lane = threadIdx.x;
@@ -742,29 +742,32 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
         const int mdb = is_final ? 0 : (int)min(W - R, 511u);        // SRC:499, 2099-2101
         const int res_bits = is_final ? 0 : avail * 8;               // SRC:500
         const int bpg = (mds * 8 + (res_bits * 9) / 10) >> ngc_shift;  // SRC:647-650: / (2 * channels)
-        int total = 0;
-        if (lane < ngc) {
-          const int j = lane;
+        // every group of ngc lanes mirrors lanes 0..ngc-1 (lane L walks the curve of gc L mod ngc), so the butterfly below
+        // leaves the frame's bit total in every lane without a broadcast
+        int total;
+        {
+          const int j = lane & (ngc - 1);
           const uint32_t meta = sh_meta[l * ngc + j];
           const int g0 = meta & 255, n = (meta >> 8) & 255, restart = (meta >> 16) & 1;
           const uint16_t *cb = sh_bits + (l * ngc + j) * kMaxEntries;
-          int gain = g0, chosen = n - 1, gain_out = g0, gain_used = g0, iters = n;
+          int gain = g0, chosen = n - 1, gain_out = g0, gain_used = g0, iters = n, bits = -1;
           for (int e = 0; e < n; ++e) {                              // quantizeToFitBudget SRC:745-776
             gain_used = gain;
             if (e == 0 && restart) { gain = max(gain - 40, 0); continue; }
-            if ((int)cb[e] <= bpg) { chosen = e; gain_out = gain; iters = e + 1; break; }
+            const int be = cb[e];
+            if (be <= bpg) { chosen = e; gain_out = gain; iters = e + 1; bits = be; break; }
             int next = min(gain + 4, 255);
-            if (next >= 255 || e == kMaxEntries - 1) { chosen = e; gain_out = next; iters = e + 1; break; }
-            if (e == n - 1) { chosen = e; gain_out = next; err |= 1; break; }   // curve ended early: engine bug
+            if (next >= 255 || e == kMaxEntries - 1) { chosen = e; gain_out = next; iters = e + 1; bits = be; break; }
+            if (e == n - 1) { chosen = e; gain_out = next; err |= 1; bits = be; break; }   // curve ended early: engine bug
             gain = next;
           }
-          sh_sel[l * ngc + j][0] = (uint8_t)chosen; sh_sel[l * ngc + j][1] = (uint8_t)gain_out;
-          sh_sel[l * ngc + j][2] = (uint8_t)gain_used; sh_sel[l * ngc + j][3] = (uint8_t)iters;
-          total = cb[chosen];
+          if (bits < 0) bits = cb[chosen];
+          if (lane < ngc)
+            *reinterpret_cast<uint32_t *>(sh_sel[l * ngc + j]) = (uint32_t)chosen | (uint32_t)gain_out << 8 | (uint32_t)gain_used << 16 | (uint32_t)iters << 24;
+          total = bits;
         }
         total += __shfl_xor_sync(0xffffffffu, total, 1);
-        total += __shfl_xor_sync(0xffffffffu, total, 2);
-        total = __shfl_sync(0xffffffffu, total, 0);
+        if (ngc == 4) total += __shfl_xor_sync(0xffffffffu, total, 2);
         const int huff = (total + 7) >> 3;                           // padToByte SRC:729
         ScanFrame o;
         o.padding = padding; o.mdb = mdb; o.res_bits = res_bits; o.bpg = bpg; o.huff = huff; o.is_final = is_final;
