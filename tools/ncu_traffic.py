@@ -14,7 +14,7 @@ def num(r, k):
     except Exception: return None
 out = {}
 for r in rows[2:]:
-    name = r[col["Kernel Name"]].split("(")[0]
+    name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].strip()      # "void k_granule<0>(...)" -> k_granule
     if name not in stage_of or stage_of[name] in out: continue
     unit = rows[1][col["dram__bytes_read.sum"]]
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)

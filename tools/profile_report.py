@@ -13,7 +13,7 @@ shutil.copy(os.path.join(G, "launches.csv"), os.path.join(P, "r01_launches.csv")
 rows = [r for r in csv.reader(open(os.path.join(G, "launches.csv"))) if len(r) > 10 and r[0].isdigit()]
 by = collections.OrderedDict()
 for r in rows:
-    key = (r[4].split("(")[0], r[8])
+    key = (r[4].split("(")[0].replace("void ", "").split("<")[0].strip(), r[8])
     by.setdefault(key, []).append(float(r[-1]) / 1e3)
 # device-plane passes = for each kernel the grid with the largest mean duration
 best = {}
