@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=30.0)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--i16", action="store_true", help="also time the 16-bit-input extension end to end (reported as e2e_i16, not the headline)")
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
                     help="c4 (default, the headline): batch of 30 s streams; c5: streaming latency, 1024 sessions x 1152-sample chunks")
     a = ap.parse_args()
@@ -358,6 +359,38 @@ def main():
         assert b.output(1) == ref, "e2e output differs from the oracle"
     L.mp3b_host_free(hp)
 
+    # ---- optional: the same end-to-end step from 16-bit PCM (mp3b_batch_encode_i16: half the PCIe bytes); an extension of
+    # the reference API, so it is reported beside e2e, never instead of it
+    e2e_i16 = None
+    if a.i16:
+        pcm16 = (pcm * 32767.0).round().to(torch.int16)
+        hp16 = C.c_void_p()
+        assert L.mp3b_host_alloc(S * n_floats * 2, C.byref(hp16)) == 0, L.mp3b_last_error()
+        assert L.mp3b_device_copy(local, hp16, pcm16.data_ptr(), S * n_floats * 2, 1) == 0
+        hptrs16 = (C.c_void_p * S)(*[hp16.value + i * n_floats * 2 for i in range(S)])
+
+        def step_host16():
+            b.reset()
+            b.encode_i16_ptrs(hptrs16, ns, flush=True)
+
+        step_host16()
+        barrier()
+        t16 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host16()
+        barrier()
+        s16 = max_over_ranks(time.perf_counter() - t16) / e2e_steps
+        e2e_i16 = {"value": world * audio_per_step / s16, "unit": "x realtime", "h2d_bytes_per_step": S * n_floats * 2,
+                   "d2h_bytes_per_step": int(b.output_total), "ms_per_step": 1000.0 * s16, "steps": e2e_steps,
+                   "note": "extension: int16 PCM in, widened on the device to Float(s) / 32768"}
+        if rank == 0:
+            import oracle_binding as orc
+            f = (pcm16[1].cpu().numpy().astype(np.float32) / np.float32(32768.0))
+            ref, _ = orc.encode_all(f, sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")
+            assert b.output(1) == ref, "int16 e2e output differs from the oracle"
+        L.mp3b_host_free(hp16)
+        del pcm16
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
         cpu, _, _ = cpu_reference(a.seconds, min_wall=10.0, max_wall=30.0)
@@ -371,6 +404,8 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if e2e_i16 is not None:
+            line["e2e_i16"] = e2e_i16
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -109,6 +109,9 @@ int mp3b_batch_encode(mp3b_batch *b, const float *const *pcm, const size_t *n_fl
  * floats of it are new.  All rows being readable up to the pitch, the upload is a single strided copy even when only some of
  * the streams have data (the session pool's case). */
 int mp3b_batch_encode_strided(mp3b_batch *b, const float *base, size_t pitch_floats, const size_t *n_floats, int flush, const uint8_t *flush_mask);
+/* Extension for 16-bit sources (not in the reference, whose input is [Float]): pcm[i] = n_samples[i] interleaved int16 values.
+ * Exactly mp3b_batch_encode on Float(pcm[i][k]) / 32768 — the widening runs on the device, so half the bytes cross PCIe. */
+int mp3b_batch_encode_i16(mp3b_batch *b, const int16_t *const *pcm, const size_t *n_samples, int flush, const uint8_t *flush_mask);
 /* Same, but pcm[i] are DEVICE pointers (same device, 4-byte aligned) and the produced frames stay in device
  * memory; only the per-stream byte counts come back.  download != 0 also copies the frames to the host. */
 int mp3b_batch_encode_device(mp3b_batch *b, const float *const *d_pcm, const size_t *n_floats, int flush, int download);

@@ -78,6 +78,7 @@ def lib():
         "mp3b_batch_encode": (i32, [vp, C.POINTER(vp), szp, i32, vp]),
         "mp3b_batch_encode_device": (i32, [vp, C.POINTER(vp), szp, i32, i32]),
         "mp3b_batch_encode_strided": (i32, [vp, vp, sz, szp, i32, vp]),
+        "mp3b_batch_encode_i16": (i32, [vp, C.POINTER(vp), szp, i32, vp]),
         "mp3b_batch_output": (i32, [vp, i32, C.POINTER(vp), szp]),
         "mp3b_batch_output_device": (i32, [vp, i32, C.POINTER(vp), szp]),
         "mp3b_batch_output_total": (sz, [vp]),
@@ -277,6 +278,17 @@ class EncoderBatch:
     def encode_ptrs(self, host_ptrs, n_floats, flush=False):
         """Raw variant: host_ptrs / n_floats are ctypes arrays (c_void_p / c_size_t) prepared by the caller."""
         _check(lib().mp3b_batch_encode(self._h, host_ptrs, n_floats, int(flush), None))
+
+    def encode_i16(self, chunks, flush=False):
+        """Extension: one interleaved int16 array per stream; equals encode([c.astype(float32) / 32768 for c in chunks])."""
+        arrs = [np.ascontiguousarray(c, dtype=np.int16).reshape(-1) for c in chunks]
+        ptrs = (C.c_void_p * self.n_streams)(*[a.ctypes.data if a.size else None for a in arrs])
+        ns = (C.c_size_t * self.n_streams)(*[a.size for a in arrs])
+        _check(lib().mp3b_batch_encode_i16(self._h, ptrs, ns, int(flush), None))
+        return self.outputs()
+
+    def encode_i16_ptrs(self, host_ptrs, n_samples, flush=False):
+        _check(lib().mp3b_batch_encode_i16(self._h, host_ptrs, n_samples, int(flush), None))
 
     def encode_device(self, dev_ptrs, n_floats, flush=False, download=False):
         _check(lib().mp3b_batch_encode_device(self._h, dev_ptrs, n_floats, int(flush), int(download)))

@@ -57,6 +57,7 @@ struct mp3b_batch {
   float *d_head[2] = {nullptr, nullptr};
   int head_sel = 0;
   float *d_stage[2] = {nullptr, nullptr}; size_t stage_stride = 0;   // double-buffered PCM staging, floats per stream
+  int16_t *d_stage16[2] = {nullptr, nullptr};                        // the same for 16-bit input (converted into d_stage on the device)
   StreamPlan *h_plan = nullptr;                          // pinned [2][S]
   StreamPlan *d_plan[2] = {nullptr, nullptr};
   cudaStream_t st_copy = nullptr, st_d2h = nullptr;
@@ -147,7 +148,7 @@ void free_batch(mp3b_batch *b) {
   PassBuffers &p = b->pb;
   void *dev[] = {p.plan, p.state, b->d_head[0], b->d_head[1], p.ms, p.frame_energy, p.gc_energy, p.gc_bt, p.frame_br, p.spec, p.sub, p.smag,
                  p.gc_meta, p.gc_bits, p.gc_bv, p.gc_bitoff, p.gc_sel, p.fr_md, p.rec, p.emit, p.md, p.md_tail, p.md_carry, p.out,
-                 p.emit_size, p.emit_n, p.tr_ix, p.tr_thr, b->d_stage[0], b->d_stage[1], b->d_plan[1], b->d_offsets, b->d_compact};
+                 p.emit_size, p.emit_n, p.tr_ix, p.tr_thr, b->d_stage[0], b->d_stage[1], b->d_stage16[0], b->d_stage16[1], b->d_plan[1], b->d_offsets, b->d_compact};
   for (void *q : dev) if (q) cudaFree(q);
   void *host[] = {b->h_plan, b->h_state, b->h_emit_size, b->h_emit_n, b->h_offsets, b->h_out};
   for (void *q : host) if (q) cudaFreeHost(q);
@@ -251,7 +252,8 @@ int ensure_trace(mp3b_batch *b) {
 
 // One API call = encode(samples:) on every stream (+ optional flush()), split into passes of at most Fc frames.
 int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, bool device_ptrs, int flush,
-             const uint8_t *flush_mask, bool download, size_t row_floats = 0) {
+             const uint8_t *flush_mask, bool download, size_t row_floats = 0, int elem_bytes = 4) {
+  // elem_bytes = 2: pcm[] really are const int16_t * (mp3b_batch_encode_i16); sample i means Float(pcm[i]) / 32768
   if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");
   if (b->sticky) return fail(b->sticky, "batch is in a failed state: %s", g_err.c_str());
   CU(cudaSetDevice(b->device));
@@ -292,6 +294,10 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
     CU(cudaMalloc((void **)&b->d_stage[0], (size_t)S * b->stage_stride * sizeof(float)));
     CU(cudaMalloc((void **)&b->d_stage[1], (size_t)S * b->stage_stride * sizeof(float)));
   }
+  if (elem_bytes == 2 && !b->d_stage16[0]) {
+    CU(cudaMalloc((void **)&b->d_stage16[0], (size_t)S * b->stage_stride * sizeof(int16_t)));
+    CU(cudaMalloc((void **)&b->d_stage16[1], (size_t)S * b->stage_stride * sizeof(int16_t)));
+  }
   for (auto &m : b->stage_ms) m = 0.0f;
   b->launches = 0; b->passes = 0;
   b->have_host_out = false;
@@ -319,7 +325,7 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
           if ((int)nfr < Fc) { nfr += 1; flags |= 3u; new_pending = 0; flushed[s] = 1; }
         } else { flags |= 2u; flushed[s] = 1; }
       }
-      src[slot][s] = (pcm && pcm[s]) ? pcm[s] + cursor[s] : nullptr;
+      src[slot][s] = (pcm && pcm[s]) ? (const float *)((const char *)pcm[s] + cursor[s] * (size_t)elem_bytes) : nullptr;
       pl.cur = device_ptrs ? src[slot][s] : b->d_stage[slot] + (size_t)s * b->stage_stride;
       pl.cur_n = (uint32_t)cur_n; pl.n_frames = nfr; pl.flags = flags; pl.head_n = (uint32_t)(fsc + b->pending[s]);
       if (cur_n || nfr || (flags & 2u)) any = true;
@@ -343,23 +349,28 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
       ptrdiff_t pitch = 0;
       for (int s = 0; s < S && uniform; ++s) {
         // a stream without data in this pass may only sit in the copy if its row is known to be readable that far
-        const bool idle_ok = row_floats && src[slot][s] && (size_t)(src[slot][s] - pcm[s]) + cur0 <= row_floats;
+        const bool idle_ok = row_floats && src[slot][s] && (size_t)((const char *)src[slot][s] - (const char *)pcm[s]) / elem_bytes + cur0 <= row_floats;
         if (!src[slot][s] || (hp[s].cur_n != cur0 && !(hp[s].cur_n == 0 && idle_ok))) { uniform = false; break; }
         if (s >= 1) {
           ptrdiff_t d = (const char *)src[slot][s] - (const char *)src[slot][s - 1];
           if (s == 1) pitch = d; else if (d != pitch) uniform = false;
         }
       }
-      if (uniform && pitch >= (ptrdiff_t)(cur0 * sizeof(float))) {
-        CU(cudaMemcpy2DAsync(b->d_stage[slot], b->stage_stride * sizeof(float), src[slot][0], (size_t)pitch, cur0 * sizeof(float), S,
-                             cudaMemcpyHostToDevice, stc));
+      char *stage = elem_bytes == 2 ? (char *)b->d_stage16[slot] : (char *)b->d_stage[slot];
+      const size_t eb = (size_t)elem_bytes;
+      if (uniform && pitch >= (ptrdiff_t)(cur0 * eb)) {
+        CU(cudaMemcpy2DAsync(stage, b->stage_stride * eb, src[slot][0], (size_t)pitch, cur0 * eb, S, cudaMemcpyHostToDevice, stc));
       } else {
         for (int s = 0; s < S; ++s)
-          if (hp[s].cur_n) CU(cudaMemcpyAsync(b->d_stage[slot] + (size_t)s * b->stage_stride, src[slot][s], hp[s].cur_n * sizeof(float),
-                                              cudaMemcpyHostToDevice, stc));
+          if (hp[s].cur_n) CU(cudaMemcpyAsync(stage + (size_t)s * b->stage_stride * eb, src[slot][s], hp[s].cur_n * eb, cudaMemcpyHostToDevice, stc));
       }
     }
     CU(cudaMemcpyAsync(b->d_plan[slot], hp, (size_t)S * sizeof(StreamPlan), cudaMemcpyHostToDevice, stc));
+    if (!device_ptrs && elem_bytes == 2) {                             // widen on the copy stream, behind the previous pass's kernels
+      int k = launch_widen_i16(b->d_stage16[slot], b->d_stage[slot], b->stage_stride, b->d_plan[slot], S, stc);
+      if (k < 0) return fail(MP3B_ERR_CUDA, "launch_widen_i16: %s", cudaGetErrorString((cudaError_t)(-k)));
+      b->launches += k;
+    }
     CU(cudaEventRecord(b->ev_h2d[slot][1], stc));
     return MP3B_OK;
   };
@@ -597,6 +608,9 @@ int mp3b_batch_encode_strided(mp3b_batch *b, const float *base, size_t pitch_flo
     rows[(size_t)s] = base + (size_t)s * pitch_floats;
   }
   return run_call(b, rows.data(), n_floats, false, flush, flush_mask, true, pitch_floats);
+}
+int mp3b_batch_encode_i16(mp3b_batch *b, const int16_t *const *pcm, const size_t *n_samples, int flush, const uint8_t *flush_mask) {
+  return run_call(b, reinterpret_cast<const float *const *>(pcm), n_samples, false, flush, flush_mask, true, 0, 2);
 }
 int mp3b_batch_encode_device(mp3b_batch *b, const float *const *d_pcm, const size_t *n_floats, int flush, int download) {
   return run_call(b, d_pcm, n_floats, true, flush, nullptr, download != 0);

@@ -1152,6 +1152,31 @@ __global__ void k_synth(float *pcm, size_t n, int channels, int sample_rate, flo
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// 16-bit PCM input (mp3b_batch_encode_i16): sample = Float(s) / 32768, exact in FP32.  Runs on the copy stream right after
+// the upload of a pass, so the PCIe traffic of 16-bit sources is halved and nothing else changes.
+__global__ void __launch_bounds__(256) k_widen_i16(const int16_t *in, float *out, size_t stride, const StreamPlan *plan) {
+  const int s = blockIdx.y;
+  const uint32_t n = plan[s].cur_n;
+  const short4 *in4 = reinterpret_cast<const short4 *>(in + (size_t)s * stride);
+  float4 *out4 = reinterpret_cast<float4 *>(out + (size_t)s * stride);
+  const float k = 1.0f / 32768.0f;
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n / 4; i += gridDim.x * 256) {
+    const short4 v = in4[i];
+    out4[i] = make_float4(__fmul_rn((float)v.x, k), __fmul_rn((float)v.y, k), __fmul_rn((float)v.z, k), __fmul_rn((float)v.w, k));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) {
+    const size_t i = (size_t)s * stride + (n & ~3u) + threadIdx.x;
+    out[i] = __fmul_rn((float)in[i], k);
+  }
+}
+int launch_widen_i16(const int16_t *in, float *out, size_t stride, const StreamPlan *d_plan, int n_streams, cudaStream_t st) {
+  dim3 grid(64, n_streams);
+  k_widen_i16<<<grid, 256, 0, st>>>(in, out, stride, d_plan);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 1 : -(int)e;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Self-test (tests only): pow34 against its definition on every float in [1e-10, 65536), div_exact against the IEEE
 // division for every finite float.  mismatch[0] / [1] / [2] count pow34, /9 and /3 disagreements.
 __global__ void k_selftest(unsigned long long *mismatch) {

@@ -126,5 +126,6 @@ int launch_synth(float *d_pcm, size_t n_per_channel, int channels, int sample_ra
                  float amp, float noise, uint64_t seed, cudaStream_t st);
 int launch_table_dump(int which, void *d_out, cudaStream_t st);
 int launch_selftest(unsigned long long *d_mismatch /* [3] */, cudaStream_t st);
+int launch_widen_i16(const int16_t *in, float *out, size_t stride, const StreamPlan *d_plan, int n_streams, cudaStream_t st);
 
 }  // namespace mp3b

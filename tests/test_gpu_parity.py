@@ -329,3 +329,22 @@ def test_joint_vbr_long_runs(mp3, orc):
         assert outs[i] == ref and outs[i + 44] == ref, "stream %d" % i
         assert b.frame_count(i) == rs.frame_count
     b.close()
+
+
+def test_int16_input_extension(mp3, orc):
+    """mp3b_batch_encode_i16 (16-bit PCM widened on the device) == encode(Float(sample) / 32768), multi-pass and chunked."""
+    rng = np.random.default_rng(77)
+    S = 5
+    pcms = [(np.clip(signals.sine_noise(0.3 + 0.4 * i, seed=60 + i), -1, 1) * 32767).astype(np.int16) for i in range(S)]
+    pcms[2] = pcms[2][:-1]                                   # odd number of values
+    b = mp3.EncoderBatch(_opts(mp3), S, 0, 9)
+    refs = [orc.Session() for _ in range(S)]
+    cuts = [sorted(int(c) for c in rng.integers(0, p.size + 1, 2)) for p in pcms]
+    for k in range(3):
+        chunks = [p[(cuts[i][k - 1] if k else 0):(cuts[i][k] if k < 2 else p.size)] for i, p in enumerate(pcms)]
+        outs = b.encode_i16(chunks, flush=(k == 2))
+        for i in range(S):
+            f = chunks[i].astype(np.float32) / np.float32(32768.0)
+            want = refs[i].encode(f) + (refs[i].flush() if k == 2 else b"")
+            assert outs[i] == want, "stream %d call %d" % (i, k)
+    b.close()
