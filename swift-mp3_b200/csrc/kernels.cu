@@ -151,11 +151,12 @@ template <int MODE, bool JOINT, int CH> __device__ __forceinline__ void prepass_
                                                                   int s, int f, int lane) {
   constexpr int ch = CH;
   constexpr int NV = JOINT ? 4 : CH;               // signal variants: L, R (or mono), mid, side
-  // frame energy over the interleaved frame (SRC:477), lane = float index mod 32 [OD1b]
+  // Frame energy over the interleaved frame (SRC:477) [OD1b]: partial p sums the floats at interleaved positions = p mod 32,
+  // ascending.  Mono: lane = partial.  Stereo: position 2 n + c, so partial 2 q + c walks n = q, q + 16, q + 32, ... — values
+  // that lanes q and q + 16 of the pair loop below hold alternately.  Lane q (< 16) therefore accumulates partial 2 q from its
+  // own left sample and lane q + 16's, lane q + 16 accumulates partial 2 q + 1 from lane q's right sample and its own: one
+  // shuffle per pair instead of a second pass over the frame.
   float pf = 0.0f;
-#pragma unroll 8
-  for (int i = lane; i < cfg.fsc; i += 32) { float x = ld.one(i); pf = __fmaf_rn(x, x, pf); }
-  const float frame_energy = __fdiv_rn(lane_tree(pf), (float)cfg.fsc);
 
   // per-channel signals; variant 0/1 = L/R (or mono), 2/3 = mid/side
   constexpr bool joint = JOINT;
@@ -176,6 +177,12 @@ template <int MODE, bool JOINT, int CH> __device__ __forceinline__ void prepass_
 #pragma unroll
       for (int jj = 0; jj < 6; ++jj) {
         float v[4] = {lr[jj].x, lr[jj].y, 0.0f, 0.0f};
+        if (ch == 1) pf = __fmaf_rn(v[0], v[0], pf);
+        else {
+          const float got = __shfl_xor_sync(0xffffffffu, lane < 16 ? v[1] : v[0], 16);
+          const float first = lane < 16 ? v[0] : got, second = lane < 16 ? got : v[1];
+          pf = __fmaf_rn(first, first, pf); pf = __fmaf_rn(second, second, pf);
+        }
         if (joint) {
           v[2] = __fmul_rn(__fadd_rn(v[0], v[1]), 0.5f);       // SRC:2148-2150
           v[3] = __fmul_rn(__fsub_rn(v[0], v[1]), 0.5f);       // SRC:2153-2154
@@ -190,6 +197,14 @@ template <int MODE, bool JOINT, int CH> __device__ __forceinline__ void prepass_
 #pragma unroll
     for (int k = 0; k < NV; ++k) eg[k][gr] = __fdiv_rn(lane_tree(ag[k]), 576.0f);
   }
+  // butterfly tree over the partials in partial-index order 16, 8, 4, 2, 1; stereo lane L holds partial 2 (L & 15) + (L >> 4),
+  // so those are lane distances 8, 4, 2, 1, 16
+  if (ch == 2) {
+#pragma unroll
+    for (int m = 8; m >= 1; m >>= 1) pf = __fadd_rn(pf, __shfl_xor_sync(0xffffffffu, pf, m));
+    pf = __fadd_rn(pf, __shfl_xor_sync(0xffffffffu, pf, 16));
+  } else pf = lane_tree(pf);
+  const float frame_energy = __fdiv_rn(pf, (float)cfg.fsc);
   int ms = 0;
   if (joint) {
     float me = __fdiv_rn(lane_tree(pm), 1152.0f), se = __fdiv_rn(lane_tree(ps), 1152.0f);
