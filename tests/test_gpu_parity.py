@@ -348,3 +348,35 @@ def test_int16_input_extension(mp3, orc):
             want = refs[i].encode(f) + (refs[i].flush() if k == 2 else b"")
             assert outs[i] == want, "stream %d call %d" % (i, k)
     b.close()
+
+
+def test_fuzz_wide_and_long(mp3, orc):
+    """The fuzz walk at shapes that reach the filterbank's long runs and multi-pass carries: 16-48 streams of 4-12 s, random
+    options and pass sizes; three streams of every case against the oracle.  MP3B_FUZZ_LONG_CASES (default 3) cases."""
+    import os
+    rng = np.random.default_rng(int(os.environ.get("MP3B_FUZZ_SEED", "20261018")) + 1)
+    rates = [(44100, [64, 128, 192, 320]), (48000, [128, 320]), (32000, [64, 128])]
+    for case in range(int(os.environ.get("MP3B_FUZZ_LONG_CASES", "3"))):
+        sr, brs = rates[rng.integers(len(rates))]
+        mode = ["mono", "stereo", "jointStereo"][rng.integers(3)]
+        cfg = dict(sample_rate=sr, bitrate_kbps=int(brs[rng.integers(len(brs))]), mode=mode, vbr=bool(rng.integers(2)), quality=int(rng.integers(10)))
+        ch = 1 if mode == "mono" else 2
+        S = int(rng.integers(16, 49))
+        fpp = int(rng.choice([0, 0, 64, 150]))
+        base = []
+        for i in range(3):
+            secs = float(rng.uniform(4.0, 12.0))
+            if rng.integers(2):
+                x = signals.sine_noise(secs, sr=sr, channels=ch, seed=int(rng.integers(1 << 30)), amp=float(rng.uniform(0.05, 0.8)), noise=float(rng.uniform(0.0, 0.2)))
+            else:
+                x = signals.castanets(secs, sr=sr, seed=int(rng.integers(1 << 30)), period=float(rng.uniform(0.07, 0.3)))
+                x = x if ch == 2 else x[::2].copy()
+            base.append(x)
+        pcms = [base[i % 3] for i in range(S)]
+        b = mp3.EncoderBatch(_opts(mp3, **cfg), S, 0, fpp)
+        outs = b.encode(pcms, flush=True)
+        for i in range(3):
+            ref, rs = orc.encode_all(base[i], **cfg)
+            assert outs[i] == ref and outs[S - 3 + ((i - S) % 3)] == ref, "case %d %s stream %d" % (case, cfg, i)
+            assert b.frame_count(i) == rs.frame_count
+        b.close()
