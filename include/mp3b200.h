@@ -70,6 +70,9 @@ int mp3b_device_count(int *count);
 /* MP3Encoder.newSession(), SRC:143-145 / EncoderSession.init, SRC:268-282.  device = CUDA ordinal. */
 int mp3b_session_create(const mp3b_options *opts, int device, mp3b_session **out);
 void mp3b_session_destroy(mp3b_session *s);
+/* `var copy = session` — EncoderSession is a struct of values (SRC:237-258), so a copy is a complete, independent snapshot of the
+ * encoder (checkpoint / fork).  The clone continues bit-identically to the original when fed the same samples. */
+int mp3b_session_clone(const mp3b_session *s, mp3b_session **out);
 /* EncoderSession.encode(samples:), SRC:297-310.  pcm = interleaved f32 in [-1, 1], any length (0 allowed).
  * Writes 0...k whole MP3 frames to out; the first full frame of a session yields 0 bytes (one-frame delay,
  * SRC:546-562).  If cap is too small: MP3B_ERR_BUFFER_TOO_SMALL, *written = bytes needed, and the frames
@@ -97,6 +100,8 @@ int mp3b_batch_frames_per_pass(const mp3b_batch *b);
 void mp3b_batch_destroy(mp3b_batch *b);
 int mp3b_batch_stream_count(const mp3b_batch *b);
 /* Every stream back to a fresh EncoderSession (SRC:268-282) without reallocating anything. */
+/* Snapshot of all n_streams sessions (see mp3b_session_clone). */
+int mp3b_batch_clone(const mp3b_batch *b, mp3b_batch **out);
 int mp3b_batch_reset(mp3b_batch *b);
 /* The same for one stream (a session slot handed to a new caller). */
 int mp3b_batch_reset_stream(mp3b_batch *b, int stream);

@@ -97,6 +97,7 @@ def lib():
         "mp3b_synth_fill": (i32, [i32, vp, sz, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint64]),
         "mp3b_selftest": (i32, [i32, C.POINTER(C.c_uint64)]),
         "mp3b_batch_reset_stream": (i32, [vp, i32]),
+        "mp3b_session_clone": (i32, [vp, C.POINTER(vp)]), "mp3b_batch_clone": (i32, [vp, C.POINTER(vp)]),
         "mp3b_pool_create": (i32, [C.POINTER(_Options), i32, i32, i32, C.POINTER(vp)]), "mp3b_pool_destroy": (None, [vp]),
         "mp3b_pool_open": (i32, [vp, C.POINTER(i32)]),
         "mp3b_pool_encode": (i32, [vp, i32, vp, sz, vp, sz, C.POINTER(sz)]),
@@ -216,6 +217,14 @@ class EncoderSession:
         n = C.c_size_t(0)
         _check(fn(self._h, *head, buf, cap, C.byref(n)))
         return bytes(memoryview(buf)[:n.value])
+
+    def clone(self):
+        """`var copy = session`: an independent snapshot (the reference's EncoderSession is a value type)."""
+        c = object.__new__(EncoderSession)
+        c.options = self.options
+        c._h = C.c_void_p()
+        _check(lib().mp3b_session_clone(self._h, C.byref(c._h)))
+        return c
 
     def encode(self, samples):
         """encode(samples:), SRC:297-310: interleaved float32 in [-1, 1]; returns 0...k whole frames."""

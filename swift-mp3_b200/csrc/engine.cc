@@ -766,6 +766,40 @@ int mp3b_batch_reset(mp3b_batch *b) {
   b->out_total = 0; b->have_host_out = false; b->sticky = 0;
   return MP3B_OK;
 }
+// EncoderSession is a value type in the reference (SRC:237-258: every field is a value): copying the struct is a full
+// snapshot of the encoder.  The same here: a new batch with the same options and a copy of everything that crosses a call
+// boundary — per-stream device state (reservoir, padding remainder, counters, VBR history, buffered frame), the carried PCM
+// frame, the MDCT overlap rows, the main-data backlog — and of the host-side counters.
+int mp3b_batch_clone(const mp3b_batch *src, mp3b_batch **out) {
+  if (!src || !out) return fail(MP3B_ERR_BAD_ARG, "null batch / out");
+  if (src->sticky) return fail(src->sticky, "cannot clone a batch in a failed state");
+  mp3b_batch *b = nullptr;
+  int rc = create_batch(&src->opt, src->S, src->device, src->Fc, &b);
+  if (rc) return rc;
+  const size_t S = (size_t)src->S, fsc2 = 2 * (size_t)src->cfg.fsc, ch = (size_t)src->cfg.channels;
+  cudaError_t e = cudaStreamSynchronize(src->st);
+  auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  A(cudaMemcpy(b->pb.state, src->pb.state, S * sizeof(StreamState), cudaMemcpyDeviceToDevice));
+  A(cudaMemcpy(b->d_head[0], src->d_head[0], S * fsc2 * sizeof(float), cudaMemcpyDeviceToDevice));
+  A(cudaMemcpy(b->d_head[1], src->d_head[1], S * fsc2 * sizeof(float), cudaMemcpyDeviceToDevice));
+  A(cudaMemcpy2D(b->pb.sub, (size_t)b->pb.sub_rows * 32 * sizeof(float), src->pb.sub, (size_t)src->pb.sub_rows * 32 * sizeof(float),
+                 576 * sizeof(float), S * ch, cudaMemcpyDeviceToDevice));
+  A(cudaMemcpy(b->pb.md_carry, src->pb.md_carry, S * kMdCarryCap, cudaMemcpyDeviceToDevice));
+  if (e != cudaSuccess) { free_batch(b); return fail(MP3B_ERR_CUDA, "clone failed: %s", cudaGetErrorString(e)); }
+  b->head_sel = src->head_sel;
+  b->pending = src->pending; b->frame_count = src->frame_count; b->byte_count = src->byte_count; b->frame_sizes = src->frame_sizes;
+  b->trace = src->trace;
+  *out = b;
+  return MP3B_OK;
+}
+int mp3b_session_clone(const mp3b_session *s, mp3b_session **out) {
+  if (!s || !out) return fail(MP3B_ERR_BAD_ARG, "null session / out");
+  mp3b_batch *b = nullptr;
+  int rc = mp3b_batch_clone(s->b, &b);
+  if (rc) return rc;
+  mp3b_session *c = new mp3b_session(); c->b = b; c->pending_out = s->pending_out; *out = c;
+  return MP3B_OK;
+}
 int mp3b_batch_reset_stream(mp3b_batch *b, int stream) {
   if (!b || stream < 0 || stream >= b->S) return fail(MP3B_ERR_BAD_ARG, "bad batch / stream");
   CU(cudaSetDevice(b->device));

@@ -380,3 +380,20 @@ def test_fuzz_wide_and_long(mp3, orc):
             assert outs[i] == ref and outs[S - 3 + ((i - S) % 3)] == ref, "case %d %s stream %d" % (case, cfg, i)
             assert b.frame_count(i) == rs.frame_count
         b.close()
+
+
+def test_session_clone_is_a_snapshot(mp3, orc):
+    """Copying the reference's EncoderSession struct forks the encoder; mp3b_session_clone does the same: clone mid-stream
+    (with a partial frame pending, reservoir in use), then the original and the clone, fed different continuations, each
+    equal an oracle session that was cloned at the same point."""
+    x = signals.sine_noise(1.3, seed=91, amp=0.1)
+    y = signals.castanets(0.8, seed=92)
+    s = mp3.MP3Encoder(_opts(mp3, vbr=True, quality=4)).newSession()
+    r = orc.Session(vbr=True, quality=4)
+    cut = 2304 * 17 + 1001
+    assert s.encode(x[:cut]) == r.encode(x[:cut])
+    s2, r2 = s.clone(), r.clone()
+    assert s.encode(x[cut:]) + s.flush() == r.encode(x[cut:]) + r.flush()
+    assert s2.encode(y) + s2.flush() == r2.encode(y) + r2.flush()
+    assert s2.encodedFrameCount == r2.frame_count and s.encodedFrameCount == r.frame_count
+    s.close(); s2.close()
