@@ -64,7 +64,7 @@ struct mp3b_batch {
   size_t h_pitch = 0;                                    // > 0: h_out is [S][h_pitch] (progressive download), else compact at h_offsets
   cudaEvent_t ev_h2d[2][2] = {}, ev_consumed[2] = {};
   StreamState *h_state = nullptr;                        // pinned [S]
-  uint16_t *h_emit_size = nullptr; uint32_t *h_emit_n = nullptr;
+  uint16_t *h_emit_size = nullptr; uint32_t *h_emit_n = nullptr;   // pinned [2][...]: one copy per pass in flight
   uint64_t *d_offsets = nullptr, *h_offsets = nullptr;
   uint8_t *d_compact = nullptr; size_t compact_cap = 0;
   uint8_t *h_out = nullptr; size_t h_out_cap = 0;
@@ -81,6 +81,7 @@ struct mp3b_batch {
   float stage_ms[MP3B_STAGE_COUNT] = {};
   int launches = 0, passes = 0;
   cudaEvent_t ev[MP3B_STAGE_COUNT + 1] = {};
+  cudaEvent_t evp[2][9] = {};                            // per-pass stage boundaries ([8] = the pass's results are on the host)
   // trace
   int trace = 0;
   std::vector<std::vector<mp3b_frame_record>> tr_frames;
@@ -154,6 +155,7 @@ void free_batch(mp3b_batch *b) {
   for (void *q : host) if (q) cudaFreeHost(q);
   for (auto &e : b->ev) if (e) cudaEventDestroy(e);
   for (auto &e : b->ev_consumed) if (e) cudaEventDestroy(e);
+  for (auto &r : b->evp) for (auto &e : r) if (e) cudaEventDestroy(e);
   for (auto &r : b->ev_h2d) for (auto &e : r) if (e) cudaEventDestroy(e);
   if (b->st) cudaStreamDestroy(b->st);
   if (b->st_copy) cudaStreamDestroy(b->st_copy);
@@ -211,11 +213,12 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   A(dalloc(b->d_offsets, S + 1));
   A(cudaHostAlloc((void **)&b->h_plan, 2 * S * sizeof(StreamPlan), cudaHostAllocDefault));
   A(cudaHostAlloc((void **)&b->h_state, S * sizeof(StreamState), cudaHostAllocDefault));
-  A(cudaHostAlloc((void **)&b->h_emit_size, S * (Fc + 1) * sizeof(uint16_t), cudaHostAllocDefault));
-  A(cudaHostAlloc((void **)&b->h_emit_n, S * sizeof(uint32_t), cudaHostAllocDefault));
+  A(cudaHostAlloc((void **)&b->h_emit_size, 2 * S * (Fc + 1) * sizeof(uint16_t), cudaHostAllocDefault));
+  A(cudaHostAlloc((void **)&b->h_emit_n, 2 * S * sizeof(uint32_t), cudaHostAllocDefault));
   A(cudaHostAlloc((void **)&b->h_offsets, (S + 1) * sizeof(uint64_t), cudaHostAllocDefault));
   for (auto &ev : b->ev) A(cudaEventCreate(&ev));
   for (auto &ev : b->ev_consumed) A(cudaEventCreate(&ev));
+  for (auto &r : b->evp) for (auto &ev : r) A(cudaEventCreate(&ev));
   for (auto &r : b->ev_h2d) for (auto &ev : r) A(cudaEventCreate(&ev));
   if (e != cudaSuccess) {
     free_batch(b);
@@ -374,66 +377,26 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
     CU(cudaEventRecord(b->ev_h2d[slot][1], stc));
     return MP3B_OK;
   };
-  int slot = 0;
-  bool have = plan_pass(slot);
-  if (have) { rc = issue_h2d(slot); if (rc) return rc; }
-  while (have) {
+  // A pass's host-side work (frame sizes for the Xing TOC, the progressive download of its bytes, stage times) needs its
+  // results on the host, but the next pass does not: the kernels of pass p + 1 are queued before the host waits for
+  // pass p, so the device never idles between passes.  Only the trace plane (which reads per-pass device buffers with
+  // synchronous copies) finishes every pass before the next one starts.
+  auto finish_pass = [&](int slot, int par) -> int {
     const StreamPlan *hplan = b->h_plan + (size_t)slot * S;
-    // look ahead: plan + start the transfer of the next pass before this one's kernels are queued
-    bool more = false;
-    for (int s = 0; s < S && !more; ++s) more = cursor[s] < n[s] || (want_flush[s] && !flushed[s]);
-    bool have_next = false;
-    if (more) { have_next = plan_pass(slot ^ 1); if (have_next) { rc = issue_h2d(slot ^ 1); if (rc) return rc; } }
-    CU(cudaStreamWaitEvent(st, b->ev_h2d[slot][1], 0));
-    CU(cudaEventRecord(b->ev[0], st));
-    CU(cudaEventRecord(b->ev[1], st));
-    // ---- device pipeline
-    PassBuffers pb = b->pb;
-    pb.plan = b->d_plan[slot];
-    pb.max_frames = 0;
-    for (int s = 0; s < S; ++s) pb.max_frames = std::max<int>(pb.max_frames, (int)hplan[s].n_frames);
-    pb.head_in = b->d_head[b->head_sel]; pb.head_out = b->d_head[b->head_sel ^ 1];
-#define LAUNCH(expr)                                                                                        \
-  do {                                                                                                      \
-    int k = (expr);                                                                                             \
-    if (k < 0) { b->sticky = MP3B_ERR_CUDA; return fail(MP3B_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString((cudaError_t)(-k))); } \
-    b->launches += k;                                                                                       \
-  } while (0)
-    LAUNCH(launch_prepass(cfg, pb, st));
-    CU(cudaEventRecord(b->ev[2], st));
-    LAUNCH(launch_spectrum(cfg, pb, st));
-    CU(cudaEventRecord(b->ev[3], st));
-    LAUNCH(launch_curve(cfg, pb, st));
-    if (b->trace & 4) LAUNCH(launch_thresholds(cfg, pb, st));
-    CU(cudaEventRecord(b->ev[4], st));
-    LAUNCH(launch_scan(cfg, pb, st));
-    CU(cudaEventRecord(b->ev[5], st));
-    LAUNCH(launch_pack(cfg, pb, st));
-    CU(cudaEventRecord(b->ev[6], st));
-    LAUNCH(launch_frames(cfg, pb, st));
-    LAUNCH(launch_carry(cfg, pb, st));
-    CU(cudaEventRecord(b->ev[7], st));
-    CU(cudaEventRecord(b->ev_consumed[slot], st));
-    b->passes += 1;
-    b->head_sel ^= 1;
-    CU(cudaMemcpyAsync(b->h_emit_n, pb.emit_n, (size_t)S * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(b->h_emit_size, pb.emit_size, (size_t)S * (Fc + 1) * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
-    if (b->trace) {
-      b->h_rec.resize((size_t)S * (Fc + 1));
-      CU(cudaMemcpyAsync(b->h_rec.data(), pb.rec, b->h_rec.size() * sizeof(FrameRec), cudaMemcpyDeviceToHost, st));
-    }
-    cudaError_t se = cudaStreamSynchronize(st);
+    cudaError_t se = cudaEventSynchronize(b->evp[par][8]);
     if (se != cudaSuccess) { b->sticky = MP3B_ERR_CUDA; return fail(MP3B_ERR_CUDA, "device pipeline failed: %s", cudaGetErrorString(se)); }
     {
       static const int stage_of[7] = {MP3B_STAGE_H2D, MP3B_STAGE_PREPASS, MP3B_STAGE_SPECTRUM, MP3B_STAGE_CURVE, MP3B_STAGE_SCAN, MP3B_STAGE_PACK, MP3B_STAGE_FRAMES};
-      for (int i = 1; i < 7; ++i) { float ms = 0; cudaEventElapsedTime(&ms, b->ev[i], b->ev[i + 1]); b->stage_ms[stage_of[i]] += ms; }
+      for (int i = 1; i < 7; ++i) { float ms = 0; cudaEventElapsedTime(&ms, b->evp[par][i], b->evp[par][i + 1]); b->stage_ms[stage_of[i]] += ms; }
       { float ms = 0; cudaEventElapsedTime(&ms, b->ev_h2d[slot][0], b->ev_h2d[slot][1]); b->stage_ms[MP3B_STAGE_H2D] += ms; }
-      float ms = 0; cudaEventElapsedTime(&ms, b->ev[0], b->ev[7]); b->stage_ms[MP3B_STAGE_TOTAL] += ms;
+      float ms = 0; cudaEventElapsedTime(&ms, b->evp[par][0], b->evp[par][7]); b->stage_ms[MP3B_STAGE_TOTAL] += ms;
     }
+    const uint32_t *h_emit_n = b->h_emit_n + (size_t)par * S;
+    const uint16_t *h_emit_size = b->h_emit_size + (size_t)par * S * (Fc + 1);
     size_t cmin = SIZE_MAX, cmax = 0, useful = 0;
     for (int s = 0; s < S; ++s) {
-      uint32_t ne = b->h_emit_n[s];
-      const uint16_t *sz = b->h_emit_size + (size_t)s * (Fc + 1);
+      uint32_t ne = h_emit_n[s];
+      const uint16_t *sz = h_emit_size + (size_t)s * (Fc + 1);
       if (ne) b->frame_sizes[s].insert(b->frame_sizes[s].end(), sz, sz + ne);
       if (progressive && ne) {
         uint32_t add = 0;
@@ -442,13 +405,13 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
       }
     }
     if (progressive && useful) {
-      cmin &= ~(size_t)15; cmax = std::min(round_up<size_t>(cmax, 16), pb.out_stride);
+      cmin &= ~(size_t)15; cmax = std::min(round_up<size_t>(cmax, 16), b->pb.out_stride);
       if ((cmax - cmin) * (size_t)S > 3 * useful + (1u << 20)) progressive = false;   // ragged batch: one compact copy at the end instead
-      else CU(cudaMemcpy2DAsync(b->h_out + cmin, pb.out_stride, pb.out + cmin, pb.out_stride, cmax - cmin, S, cudaMemcpyDeviceToHost, b->st_d2h));
+      else CU(cudaMemcpy2DAsync(b->h_out + cmin, b->pb.out_stride, b->pb.out + cmin, b->pb.out_stride, cmax - cmin, S, cudaMemcpyDeviceToHost, b->st_d2h));
     }
     if (b->trace) {
+      const PassBuffers &pb = b->pb;
       const int ngc = 2 * cfg.channels;
-      std::vector<float> tmpf; std::vector<int32_t> tmpi;
       for (int s = 0; s < S; ++s) {
         const uint32_t nf = hplan[s].n_frames;
         for (uint32_t f = 0; f < nf; ++f) {
@@ -476,9 +439,67 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
         }
       }
     }
+    return MP3B_OK;
+  };
+  int slot = 0, par = 0;
+  int open_slot = -1, open_par = 0;                              // the pass whose host-side work is still outstanding
+  bool have = plan_pass(slot);
+  if (have) { rc = issue_h2d(slot); if (rc) return rc; }
+  while (have) {
+    const StreamPlan *hplan = b->h_plan + (size_t)slot * S;
+    CU(cudaStreamWaitEvent(st, b->ev_h2d[slot][1], 0));
+    cudaEvent_t *ev = b->evp[par];
+    CU(cudaEventRecord(ev[0], st));
+    CU(cudaEventRecord(ev[1], st));
+    // ---- device pipeline
+    PassBuffers pb = b->pb;
+    pb.plan = b->d_plan[slot];
+    pb.max_frames = 0;
+    for (int s = 0; s < S; ++s) pb.max_frames = std::max<int>(pb.max_frames, (int)hplan[s].n_frames);
+    pb.head_in = b->d_head[b->head_sel]; pb.head_out = b->d_head[b->head_sel ^ 1];
+#define LAUNCH(expr)                                                                                        \
+  do {                                                                                                      \
+    int k = (expr);                                                                                             \
+    if (k < 0) { b->sticky = MP3B_ERR_CUDA; return fail(MP3B_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString((cudaError_t)(-k))); } \
+    b->launches += k;                                                                                       \
+  } while (0)
+    LAUNCH(launch_prepass(cfg, pb, st));
+    CU(cudaEventRecord(ev[2], st));
+    LAUNCH(launch_spectrum(cfg, pb, st));
+    CU(cudaEventRecord(ev[3], st));
+    LAUNCH(launch_curve(cfg, pb, st));
+    if (b->trace & 4) LAUNCH(launch_thresholds(cfg, pb, st));
+    CU(cudaEventRecord(ev[4], st));
+    LAUNCH(launch_scan(cfg, pb, st));
+    CU(cudaEventRecord(ev[5], st));
+    LAUNCH(launch_pack(cfg, pb, st));
+    CU(cudaEventRecord(ev[6], st));
+    LAUNCH(launch_frames(cfg, pb, st));
+    LAUNCH(launch_carry(cfg, pb, st));
+    CU(cudaEventRecord(ev[7], st));
+    CU(cudaEventRecord(b->ev_consumed[slot], st));
+    b->passes += 1;
+    b->head_sel ^= 1;
+    CU(cudaMemcpyAsync(b->h_emit_n + (size_t)par * S, pb.emit_n, (size_t)S * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(b->h_emit_size + (size_t)par * S * (Fc + 1), pb.emit_size, (size_t)S * (Fc + 1) * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    if (b->trace) {
+      b->h_rec.resize((size_t)S * (Fc + 1));
+      CU(cudaMemcpyAsync(b->h_rec.data(), pb.rec, b->h_rec.size() * sizeof(FrameRec), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaEventRecord(ev[8], st));
+    // the previous pass: its kernels finished before this one's started, so this wait is short and the device stays busy
+    if (open_slot >= 0) { rc = finish_pass(open_slot, open_par); open_slot = -1; if (rc) return rc; }
+    open_slot = slot; open_par = par;
+    if (b->trace) { rc = finish_pass(open_slot, open_par); open_slot = -1; if (rc) return rc; }
+    // plan the next pass and start its transfer (its plan / staging slot belonged to the pass that was just finished)
+    bool more = false;
+    for (int s = 0; s < S && !more; ++s) more = cursor[s] < n[s] || (want_flush[s] && !flushed[s]);
+    bool have_next = false;
+    if (more) { have_next = plan_pass(slot ^ 1); if (have_next) { rc = issue_h2d(slot ^ 1); if (rc) return rc; } }
     have = have_next;
-    slot ^= 1;
+    slot ^= 1; par ^= 1;
   }
+  if (open_slot >= 0) { rc = finish_pass(open_slot, open_par); if (rc) return rc; }
   // ---- results: counters, lengths, optional download
   CU(cudaEventRecord(b->ev[0], st));
   LAUNCH(launch_compact(cfg, b->pb, b->d_offsets, nullptr, 0, st));
