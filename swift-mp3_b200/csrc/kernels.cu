@@ -311,6 +311,15 @@ __device__ __forceinline__ int gain_from_peak(float peak) {      // computeGloba
 //     three CTAs fit an SM;
 //   * the PCM rows of tile j+1 are fetched with cp.async while tile j is in its second matrixing half.
 // The MDCT lives in k_granule: it is warp-local work that wants many resident warps, this kernel wants shared memory.
+// compile-time loop: f(integral_constant<int, 0>) ... f(integral_constant<int, N - 1>)
+template <int V> struct IntC { static constexpr int value = V; };
+template <int I, int N, class F> __device__ __forceinline__ void static_for(F &&f) {
+  if constexpr (I < N) { f(IntC<I>{}); static_for<I + 1, N>(f); }
+}
+// one 4-byte cp.async with both offsets as instruction immediates
+template <int DST_OFF, int SRC_OFF> __device__ __forceinline__ void cp_async4_imm(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 4;" ::"r"(dst), "l"(src), "n"(DST_OFF), "n"(SRC_OFF));
+}
 constexpr int kTile = 256;                        // filterbank steps per tile
 constexpr int kPRows = kTile + kLook;             // 271 PCM rows of 32 samples: 15 rows of look-back + 256 new
 constexpr int kFbThreads = 128;
@@ -472,32 +481,47 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
           load_rows(ra, rb, kLook);
         }
       }
-      // ---- matrixing (SRC:1402-1408): S[k] = sum over ascending n of M[k][n] * Y[n], one fused multiply-add per term
+      // ---- matrixing (SRC:1402-1408): S[k] = sum over ascending n of M[k][n] * Y[n], one fused multiply-add per term.
+      // PFM = how the next tile's PCM rows are fetched from inside the loop (second half only): 0 nothing, 1 / 2 the
+      // whole tile is contiguous stereo / mono PCM of this pass (64 rows per warp: two cp.async per n whose addresses are
+      // instruction immediates — no pointer arithmetic, no branches), 3 whatever is left, one predicated copy at a time.
       if (64 * warp < valid && !(dbg & 2)) {
-        const float4 *mrow = reinterpret_cast<const float4 *>(sM + (32 * H) * 32 + kg * 16);
+        auto matrixing = [&](auto Mc) {
+          constexpr int PFM = decltype(Mc)::value;
+          const float4 *mrow = reinterpret_cast<const float4 *>(sM + (32 * H) * 32 + kg * 16);
 #pragma unroll 2
-        for (int a = 0; a < 4; ++a) {
+          for (int a = 0; a < 4; ++a) {
+            static_for<0, 8>([&](auto bc) {
+              constexpr int b = decltype(bc)::value;
+              const int nl = 8 * a + b;
+              if constexpr (PFM == 1 || PFM == 2) {
+                constexpr int SB = kFbWarps * 32 * 4 * (PFM == 1 ? 2 : 1);   // bytes between the rows of one warp
+                cp_async4_imm<(2 * b) * kFbWarps * 128, (2 * b) * SB>(pf_dst, pf_src);
+                cp_async4_imm<(2 * b + 1) * kFbWarps * 128, (2 * b + 1) * SB>(pf_dst, pf_src);
+              } else if constexpr (PFM == 3) {
 #pragma unroll
-          for (int b = 0; b < 8; ++b) {
-            const int nl = 8 * a + b;
-            if (H == 1) {
+                for (int u = 0; u < 2; ++u)
+                  if (pf_left > 0) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pf_dst), "l"(pf_src));
+                    pf_src += pf_step; pf_dst += kFbWarps * 128; --pf_left;
+                  }
+              }
+              const float4 m0 = mrow[nl * 8], m1 = mrow[nl * 8 + 1], m2 = mrow[nl * 8 + 2], m3 = mrow[nl * 8 + 3];
+              const float4 y = *reinterpret_cast<const float4 *>(Y + a * 8 * kTile + yo[b]);
+              const float yv[4] = {y.x, y.y, y.z, y.w};
+              const float mv[16] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w, m3.x, m3.y, m3.z, m3.w};
 #pragma unroll
-              for (int u = 0; u < 2; ++u)
-                if (pf_left > 0) {
-                  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pf_dst), "l"(pf_src));
-                  pf_src += pf_step; pf_dst += kFbWarps * 128; --pf_left;
-                }
-            }
-            const float4 m0 = mrow[nl * 8], m1 = mrow[nl * 8 + 1], m2 = mrow[nl * 8 + 2], m3 = mrow[nl * 8 + 3];
-            const float4 y = *reinterpret_cast<const float4 *>(Y + a * 8 * kTile + yo[b]);
-            const float yv[4] = {y.x, y.y, y.z, y.w};
-            const float mv[16] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w, m3.x, m3.y, m3.z, m3.w};
+              for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) acc[j][i] = __ffma2_rn(make_float2(yv[j], yv[j]), make_float2(mv[2 * i], mv[2 * i + 1]), acc[j][i]);
+                for (int i = 0; i < 8; ++i) acc[j][i] = __ffma2_rn(make_float2(yv[j], yv[j]), make_float2(mv[2 * i], mv[2 * i + 1]), acc[j][i]);
+            });
+            if constexpr (PFM == 1 || PFM == 2) { pf_src += 16 * pf_step; pf_dst += 16 * kFbWarps * 128; }
           }
-        }
+          if constexpr (PFM == 1 || PFM == 2) pf_left = 0;
+        };
+        if (H == 0 || pf_left == 0) matrixing(IntC<0>{});
+        else if (pf_left == kTile / kFbWarps) { if (ch == 2) matrixing(IntC<1>{}); else matrixing(IntC<2>{}); }
+        else matrixing(IntC<3>{});
       }
     }
     while (pf_left > 0) {                           // (a warp that skipped the matrixing of a short tile)
@@ -522,12 +546,13 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
           *reinterpret_cast<float4 *>(Y + slot(4 * tg + j, 4 * kg + i)) = make_float4(acc[j][2 * i].x, acc[j][2 * i].y, acc[j][2 * i + 1].x, acc[j][2 * i + 1].y);
       __syncwarp();
       const int rows = min(64, valid - 64 * warp);
-      float4 *dst = reinterpret_cast<float4 *>(out + (size_t)(kTile * tile + 64 * warp) * 32);
-#pragma unroll 4
-      for (int it = 0; it < 16; ++it) {
-        const int t = 4 * it + (lane >> 3), cidx = lane & 7;
-        if (t < rows && !(dbg & 8)) dst[t * 8 + cidx] = *reinterpret_cast<const float4 *>(Y + slot(t, cidx));
-      }
+      // row t = 4 it + (lane >> 3), chunk lane & 7: slot(t, chunk) = fixed per lane + it * 2 kTile + ((chunk ^ (it & 7)) << 2)
+      const int l3 = lane >> 3, cidx = lane & 7;
+      float4 *dst = reinterpret_cast<float4 *>(out + (size_t)(kTile * tile + 64 * warp) * 32) + l3 * 8 + cidx;
+      const float *ysrc = Y + (l3 >> 1) * kTile + ((16 * warp + 8 * (l3 & 1)) << 2);
+#pragma unroll
+      for (int it = 0; it < 16; ++it)
+        if (4 * it + l3 < rows && !(dbg & 8)) dst[it * 32] = *reinterpret_cast<const float4 *>(ysrc + it * 2 * kTile + ((cidx ^ (it & 7)) << 2));
     }
   }
 }
