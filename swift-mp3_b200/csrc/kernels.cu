@@ -564,36 +564,43 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
 // budget the frame can have (no reservoir, no padding) or the loop's own exits fire; the serial scan (K_scan) then
 // only looks entries up.
 __device__ __forceinline__ int lo_bits_of(const Config &cfg, int bri) {
-  return ((cfg.frame_base[bri] - cfg.header_bytes) * 8) / (2 * cfg.channels);
+  return ((cfg.frame_base[bri] - cfg.header_bytes) * 8) >> cfg.channels;     // / (2 * channels), channels = 1 or 2; the dividend is positive
 }
 
 constexpr int kGranulePerWarp = 1;   // 4 measured slower (6.0 vs 5.7 ms): one granule-channel per warp keeps the tail short
 template <bool TRACE> __global__ void __launch_bounds__(256) k_granule(Config cfg, PassBuffers pb) {   // TRACE: also leave the MDCT spectrum behind
   __shared__ uint8_t len15[256];                  // table-15 code length of a pair + its sign bits (SRC:828-853)
   __shared__ __align__(8) float smg[8][576];
-  len15[threadIdx.x] = tab::kHuff15Len[threadIdx.x] + ((threadIdx.x >> 4) != 0) + ((threadIdx.x & 15) != 0);
-  __syncthreads();
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ch = cfg.channels;
-  // a warp walks kGranulePerWarp granule-channels: the table staging above and the CTA start-up are paid once for all
+  const int ch = cfg.channels, chs = ch - 1;         // channels = 1 or 2: / ch is >> chs
+  // a warp walks kGranulePerWarp granule-channels: the table staging below and the CTA start-up are paid once for all
   for (int rep = 0; rep < kGranulePerWarp; ++rep) {
   const int gci = (blockIdx.y * kGranulePerWarp + rep) * 8 + warp;
+  // ---- MDCT (SRC:1512-1565): lane = subband; the 36 time samples are the previous and the current granule's rows of
+  // the subband array (row 18 (g + 1) + t = step t of granule g; rows 0..17 = last granule of the previous pass).
+  // They are requested before anything else — their addresses need nothing from memory — so that the frame count, the
+  // block type and the bitrate index arrive under their latency instead of in front of it.
+  float v[36];
+  {
+    const int gcl = min(gci, pb.GC - 1);             // the grid is rounded up to whole CTAs: stay inside the array
+    const int g = gcl >> chs, c = gcl & chs;
+    const float *prev = pb.sub + ((size_t)(s * ch + c) * pb.sub_rows + 18 * g) * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < 36; ++k) v[k] = __ldg(prev + k * 32);
+  }
+  if (rep == 0) {
+    len15[threadIdx.x] = tab::kHuff15Len[threadIdx.x] + ((threadIdx.x >> 4) != 0) + ((threadIdx.x & 15) != 0);
+    __syncthreads();
+  }
   if (gci >= (int)pb.plan[s].n_frames * 2 * ch) return;
   const size_t gslot = (size_t)s * pb.GC + gci;
-  const int f = gci / (2 * ch);
+  const int f = gci >> (chs + 1);
   const int lo_bits = lo_bits_of(cfg, pb.frame_br[(size_t)s * pb.Fc + f]);
-  // ---- MDCT (SRC:1512-1565): lane = subband; the 36 time samples are the previous and the current granule's rows of
-  // the subband array (row 18 (g + 1) + t = step t of granule g; rows 0..17 = last granule of the previous pass)
   {
-    const int g = gci / ch, c = gci - g * ch;
     const int bt = pb.gc_bt[gslot] & 3;
-    const float *prev = pb.sub + ((size_t)(s * ch + c) * pb.sub_rows + 18 * g) * 32 + lane;
     float *X = smg[warp];
     const int sb = lane;
     const bool flip = sb & 1;
-    float v[36];
-#pragma unroll
-    for (int k = 0; k < 36; ++k) v[k] = __ldg(prev + k * 32);
     const bool use_long = bt == 0 || (bt == 1 && sb < 2);      // SRC:1542-1553
     if (use_long) {                                             // mdctLong SRC:1619-1636
       float a[18];
@@ -643,6 +650,7 @@ template <bool TRACE> __global__ void __launch_bounds__(256) k_granule(Config cf
     __syncwarp();
   }
   // |x|^0.75 (SRC:805-813 [OD3]), peak -> g0 (SRC:989-1006), preflag (SRC:2042-2066); line i = lane + 32 j
+  uint32_t meta;
   {
     float *spec = TRACE ? pb.spec + gslot * 576 : nullptr;       // trace plane only; no predicated-off stores otherwise
     float *smag = pb.smag + gslot * 576;
@@ -669,17 +677,13 @@ template <bool TRACE> __global__ void __launch_bounds__(256) k_granule(Config cf
     }
     peak = warp_max(peak);
     const float low = lane_tree(plo), high = lane_tree(phi);
-    if (lane == 0) {
-      const int g0 = gain_from_peak(peak);
-      const int pre = high > __fmul_rn(low, 1.5f) ? 1 : 0;
-      pb.gc_meta[gslot] = (uint32_t)g0 | (uint32_t)pre << 17;
-    }
+    // every lane holds the same peak and energies: all of them derive g0 / preflag (no broadcast, no read-back)
+    meta = (uint32_t)gain_from_peak(peak) | (uint32_t)(high > __fmul_rn(low, 1.5f) ? 1 : 0) << 17;
     __syncwarp();
   }
   float mx[9], my[9];
 #pragma unroll
   for (int j = 0; j < 9; ++j) { float2 v = reinterpret_cast<const float2 *>(smg[warp])[lane + 32 * j]; mx[j] = v.x; my[j] = v.y; }
-  const uint32_t meta = __shfl_sync(0xffffffffu, lane == 0 ? pb.gc_meta[gslot] : 0u, 0);
   const int g0 = meta & 255;
   int gain = g0, n = 0, restart = 0;
   uint16_t *bits_out = pb.gc_bits + gslot * kMaxEntries, *bv_out = pb.gc_bv + gslot * kMaxEntries;
@@ -702,7 +706,7 @@ template <bool TRACE> __global__ void __launch_bounds__(256) k_granule(Config cf
     if (next >= 255) break;
     gain = next;
   }
-  if (lane == 0) pb.gc_meta[gslot] = (meta & 0xFFFE00FFu) | (uint32_t)n << 8 | (uint32_t)restart << 16;
+  if (lane == 0) pb.gc_meta[gslot] = meta | (uint32_t)n << 8 | (uint32_t)restart << 16;
   __syncwarp();
   }
 }
