@@ -669,7 +669,7 @@ template <bool TRACE> __global__ void __launch_bounds__(256) k_granule(Config cf
       // the butterfly tree is invariant under.
       if (i < 432) plo = __fmaf_rn(x[j], x[j], plo); else phi = __fmaf_rn(x[j], x[j], phi);
       const float mag = pow34(fmaxf(ax, 1e-10f));
-      smag[i] = x[j] < 0.0f ? -mag : mag;
+      smag[i] = __uint_as_float(__float_as_uint(mag) | (__float_as_uint(x[j]) & 0x80000000u));   // sign of x on mag > 0 (a -0 line quantizes to 0 either way: no sign bit is coded)
       smg[warp][i] = mag;
     }
     peak = warp_max(peak);
@@ -952,8 +952,8 @@ template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta, 
       if (TRACE) { const int ax = (qx + 1) >> 1, ay = (qy + 1) >> 1; trix[2 * p] = v.x < 0.0f ? -ax : ax; trix[2 * p + 1] = v.y < 0.0f ? -ay : ay; }
       const uint32_t t15 = tab31[qx * 32 + qy];
       uint32_t code = t15 & 255u; int l = (int)(t15 >> 8);
-      if (qx) { code = code << 1 | (v.x < 0.0f ? 1u : 0u); ++l; }   // SRC:1729-1736
-      if (qy) { code = code << 1 | (v.y < 0.0f ? 1u : 0u); ++l; }
+      if (qx) { code = code << 1 | __float_as_uint(v.x) >> 31; ++l; }   // SRC:1729-1736 (the magnitude carries the line's sign)
+      if (qy) { code = code << 1 | __float_as_uint(v.y) >> 31; ++l; }
       if (p >= bv) l = 0;
       val[j] = code; len[j] = l; mine += l;
     }
