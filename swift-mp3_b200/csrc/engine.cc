@@ -224,6 +224,7 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
     free_batch(b);
     return fail(e == cudaErrorMemoryAllocation ? MP3B_ERR_OOM : MP3B_ERR_CUDA, "batch allocation failed: %s", cudaGetErrorString(e));
   }
+  if (!cfg.vbr && cudaMemset(p.frame_br, cfg.cbr_index, S * Fc) != cudaSuccess) { free_batch(b); return fail(MP3B_ERR_CUDA, "batch initialisation failed"); }   // constant for CBR: the pre-pass may be skipped
   b->pending.assign(S, 0); b->out_len.assign(S, 0); b->frame_count.assign(S, 0); b->byte_count.assign(S, 0);
   b->frame_sizes.resize(S);
   b->d_plan[0] = p.plan;
@@ -463,11 +464,14 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
     if (k < 0) { b->sticky = MP3B_ERR_CUDA; return fail(MP3B_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString((cudaError_t)(-k))); } \
     b->launches += k;                                                                                       \
   } while (0)
-    LAUNCH(launch_prepass(cfg, pb, st));
+    // CBR without joint stereo needs nothing from the pre-pass but the block type, which k_granule then derives from the PCM
+    // itself (one pass less over the input); the trace plane keeps the pre-pass for its energy records
+    const bool fused_prepass = !cfg.vbr && cfg.mode != 2 && !b->trace;
+    if (!fused_prepass) LAUNCH(launch_prepass(cfg, pb, st));
     CU(cudaEventRecord(ev[2], st));
     LAUNCH(launch_spectrum(cfg, pb, st));
     CU(cudaEventRecord(ev[3], st));
-    LAUNCH(launch_curve(cfg, pb, st));
+    LAUNCH(launch_curve(cfg, pb, st, fused_prepass));
     if (b->trace & 4) LAUNCH(launch_thresholds(cfg, pb, st));
     CU(cudaEventRecord(ev[4], st));
     LAUNCH(launch_scan(cfg, pb, st));

@@ -565,7 +565,9 @@ __device__ __forceinline__ int lo_bits_of(const Config &cfg, int bri) {
 }
 
 constexpr int kGranulePerWarp = 1;   // 4 measured slower (6.0 vs 5.7 ms): one granule-channel per warp keeps the tail short
-template <bool TRACE> __global__ void __launch_bounds__(256) k_granule(Config cfg, PassBuffers pb) {   // TRACE: also leave the MDCT spectrum behind
+// TRACE: also leave the MDCT spectrum behind.  PRE: no k_prepass ran (CBR, not joint stereo, no trace: nothing but the block
+// type is needed from the PCM) — the warp reads its granule's 576 samples itself and decides the block type (SRC:1944-1968).
+template <bool TRACE, bool PRE> __global__ void __launch_bounds__(256, 4) k_granule(Config cfg, PassBuffers pb) {
   __shared__ __align__(16) uint8_t len31[31 * 32];   // table-15 code length of a pair + its sign bits (SRC:828-853), indexed by quant30
   __shared__ __align__(8) float smg[8][576];
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -585,6 +587,21 @@ template <bool TRACE> __global__ void __launch_bounds__(256) k_granule(Config cf
 #pragma unroll
     for (int k = 0; k < 36; ++k) v[k] = __ldg(prev + k * 32);
   }
+  float pc[PRE ? 18 : 1];                            // PRE: sample 32 k + lane of the granule-channel
+  if (PRE) {
+    const PcmView pv = pcm_view(cfg, pb, s);
+    const int f = gci >> (chs + 1), gr = (gci >> chs) & 1, c = gci & chs;
+    const int64_t q0 = (int64_t)(1 + f) * cfg.fsc + (int64_t)(gr * 576 + lane) * ch + c;   // element of sample `lane`
+    const int64_t rel = q0 - (int64_t)pv.head_n;
+    if (rel >= 0 && rel + (int64_t)(17 * 32 * ch) < (int64_t)pv.cur_n) {                     // the usual case: all of it in this pass's PCM
+      const float *p = pv.cur + rel;
+#pragma unroll
+      for (int k = 0; k < 18; ++k) pc[k] = __ldg(p + k * 32 * ch);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 18; ++k) pc[k] = pv.at(q0 + (int64_t)k * 32 * ch);
+    }
+  }
   if (rep == 0) {
     if (threadIdx.x < 31 * 32 / 4) reinterpret_cast<uint32_t *>(len31)[threadIdx.x] = reinterpret_cast<const uint32_t *>(tab::kLen31s)[threadIdx.x];
     __syncthreads();
@@ -594,7 +611,20 @@ template <bool TRACE> __global__ void __launch_bounds__(256) k_granule(Config cf
   const int f = gci >> (chs + 1);
   const int lo_bits = lo_bits_of(cfg, pb.frame_br[(size_t)s * pb.Fc + f]);
   {
-    const int bt = pb.gc_bt[gslot] & 3;
+    int bt;
+    if (PRE) {
+      // TransientDetector.analyze: thirds of 192 samples = 6 rows of 32; [OD1b] partial = lane, ascending rows, butterfly tree
+      float e3[3]; int sbg[3];
+#pragma unroll
+      for (int th = 0; th < 3; ++th) {
+        float a = 0.0f;
+#pragma unroll
+        for (int jj = 0; jj < 6; ++jj) a = __fmaf_rn(pc[6 * th + jj], pc[6 * th + jj], a);
+        e3[th] = __fdiv_rn(lane_tree(a), 192.0f);
+      }
+      transient_decide(e3, bt, sbg);
+      if (lane == 0) pb.gc_bt[gslot] = (uint16_t)(bt | sbg[0] << 2 | sbg[1] << 5 | sbg[2] << 8);
+    } else bt = pb.gc_bt[gslot] & 3;
     float *X = smg[warp];
     const int sb = lane;
     const bool flip = sb & 1;
@@ -1284,10 +1314,12 @@ int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   k_filterbank<<<grid, kFbThreads, kFbSmemBytes, st>>>(cfg, pb, R | dbg << 16);
   return check(1);
 }
-int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st, bool fused_prepass) {
   if (pb.max_frames <= 0) return 0;
   dim3 grid(cfg.n_streams, (pb.max_frames * 2 * cfg.channels + 8 * kGranulePerWarp - 1) / (8 * kGranulePerWarp));
-  if (pb.spec) k_granule<true><<<grid, 256, 0, st>>>(cfg, pb); else k_granule<false><<<grid, 256, 0, st>>>(cfg, pb);
+  if (pb.spec) k_granule<true, false><<<grid, 256, 0, st>>>(cfg, pb);
+  else if (fused_prepass) k_granule<false, true><<<grid, 256, 0, st>>>(cfg, pb);
+  else k_granule<false, false><<<grid, 256, 0, st>>>(cfg, pb);
   return check(1);
 }
 int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {

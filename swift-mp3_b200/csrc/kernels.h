@@ -113,7 +113,7 @@ cudaError_t upload_tables();   // __constant__ tables for the current device
 // launchers; each returns the number of kernels launched (negative cudaError on failure)
 int launch_prepass(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
-int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
+int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st, bool fused_prepass);   // fused_prepass: launch_prepass did not run
 int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_pack(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_frames(const Config &cfg, const PassBuffers &pb, cudaStream_t st);

@@ -70,6 +70,31 @@ def test_c3_joint_vbr_transients(mp3, orc):
     _compare(mp3, orc, pcm, frames_per_pass=5, arrays=False, sample_rate=44100, bitrate_kbps=128, mode="jointStereo", vbr=True, quality=2)
 
 
+def test_cbr_transients_without_prepass(mp3, orc):
+    """CBR without joint stereo and without the trace plane skips k_prepass: k_granule decides the block types from the PCM
+    itself.  Castanet bursts (short and mixed blocks), stereo and mono, one pass and 5-frame passes with a ragged tail,
+    plus a stream fed in odd chunks; bytes against the oracle, and the oracle must really have switched blocks."""
+    pcm = signals.castanets(3.0)
+    for o in (dict(mode="stereo"), dict(mode="mono", bitrate_kbps=96, sample_rate=48000), dict(mode="stereo", crc_protected=True, bitrate_kbps=192, sample_rate=32000)):
+        x = pcm if o["mode"] == "stereo" else np.ascontiguousarray(pcm[0::2])
+        x = x[: len(x) - 1001 * (2 if o["mode"] == "stereo" else 1)]
+        ref, rs = orc.encode_all(x, trace=True, **o)
+        bts = rs.gc_trace()["block_type"]
+        assert (bts == 2).any() and (bts == 1).any()
+        for fpp in (0, 5):
+            b = mp3.EncoderBatch(_opts(mp3, **o), 1, 0, fpp)
+            assert b.encode([x], flush=True)[0] == ref
+            b.close()
+        s = mp3.MP3Encoder(_opts(mp3, **o)).newSession(0)
+        out, pos, k = b"", 0, 0
+        while pos < len(x):
+            n = (977, 2304, 5000, 1, 40000)[k % 5]; k += 1
+            out += s.encode(x[pos:pos + n]); pos += n
+        out += s.flush()
+        assert out == ref
+        s.close()
+
+
 def test_silence_and_ragged_tail(mp3, orc):
     _compare(mp3, orc, np.zeros(2304 * 3 + 777, np.float32))
     _compare(mp3, orc, signals.sine440(3)[: 2304 * 2 + 10], crc_protected=True, copyright=True, original=False)
