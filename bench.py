@@ -301,7 +301,14 @@ def main():
     except Exception:
         pass
     stage_table = {}
+    fused_prepass = stages["prepass"] / max(passes, 1) < 0.02     # CBR without joint stereo: k_prepass is not launched at all
+    if fused_prepass:
+        algo["granule"] += 2304                                   # k_granule then reads the granule's PCM itself (block-type decision)
     for k in algo:
+        if k == "prepass" and fused_prepass:
+            stage_table[k] = {"ms_per_step": 0.0, "share": 0.0, "skipped": "CBR without joint stereo: the block types are decided inside k_granule, "
+                                                                            "k_prepass (energies for VBR / mid-side / the trace plane) is not launched"}
+            continue
         sec = stages[k] / a.steps / 1000.0
         row = {"ms_per_step": 1000.0 * sec, "share": stages[k] / max(stages["total"], 1e-9), "algo_bytes_per_gc": algo[k],
                "achieved_GBps": gc_per_step * algo[k] / sec / 1e9, "hbm_frac": gc_per_step * algo[k] / sec / 1e9 / hbm_peak}
