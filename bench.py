@@ -146,14 +146,35 @@ def bench_c5(a, mp3, L, local, rank, world):
         ref = b"".join(rs.encode(host[(k % n_chunks) * chunk:(k % n_chunks + 1) * chunk]) for k in range(steps + 20))
         assert b.byte_count(3) == len(ref) and b.output(3) == ref[-len(b.output(3)):], "streaming output differs from the oracle"
         p50, p99 = float(np.percentile(lat, 50)), float(np.percentile(lat, 99))
-        print(json.dumps({"metric": "per-frame latency, 1024 concurrent sessions (config 5)", "value": p50, "unit": "ms (p50)",
+        emit({"metric": "per-frame latency, 1024 concurrent sessions (config 5)", "value": p50, "unit": "ms (p50)",
                           "p99_ms": p99, "mean_ms": float(lat.mean()), "n_gpus": 1, "steps": steps, "higher_is_better": False,
                           "frame_period_ms": 1152 / SR * 1e3, "realtime_factor_p50": S * 1152 / SR * 1e3 / p50,
                           "data": "synthetic", "config": {"workload": "C5: 1024 sessions x 1152-sample stereo chunks, host buffers in, bytes out"},
                           "stage_ms_last_call": b.stage_ms(), "gpu_launches_per_call": b.launch_count,
-                          "parity": "session 3 byte-identical to the oracle over %d chunks" % (steps + 20)}))
+                          "parity": "session 3 byte-identical to the oracle over %d chunks" % (steps + 20)})
     L.mp3b_host_free(hp)
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line from C), so file
+    descriptor 1 points at stderr while the bench runs and emit() puts it back for the one line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line))
+    sys.stdout.flush()
 
 
 def main():
@@ -171,6 +192,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
                     help="c4 (default, the headline): batch of 30 s streams; c5: streaming latency, 1024 sessions x 1152-sample chunks")
     a = ap.parse_args()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     metric = "encoded audio sec/sec (x realtime)"
@@ -191,7 +213,7 @@ def main():
                            "original cannot be built on Linux"},
                 "cpu_baseline": res,
                 "e2e": {"value": res["value"], "unit": "x realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import numpy as np
@@ -417,7 +439,7 @@ def main():
             line["cpu_baseline"] = cpu
         if e2e_i16 is not None:
             line["e2e_i16"] = e2e_i16
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
