@@ -193,7 +193,9 @@ int mp3b_batch_trace_gc_array(const mp3b_batch *b, int stream, int kind, void *o
 /* Product tables for cross-checks against the oracle / the reference literals.
  * which: 0 window[512] f32, 1 analysis[32*64] f32, 2 mdct_long[18*36] f32, 3 mdct_short[6*12] f32,
  * 4 win_long[36] f32, 5 win_short[12] f32, 6 inv_step[256] f32, 7 len15[256] u8, 8 code15[256] u8,
- * 9 gain_threshold[256] f64, 10 alias_cs[8] f32, 11 alias_ca[8] f32, 12 sfb_cum[3*21] i32.
+ * 9 gain_threshold[256] f64, 10 alias_cs[8] f32, 11 alias_ca[8] f32, 12 sfb_cum[3*21] i32,
+ * 13 len31s[31*32] u8, 14 tab31[31*32] u16: table 15 indexed by the kernels' unclamped quantizer value (u = min(floor(2t), 30),
+ * q = (u+1)>>1, row stride 32): pair length incl. sign bits, and code | length << 8.
  * Returns the element count, or a negative status. */
 int mp3b_table(int which, void *out, size_t cap_bytes);
 /* Deterministic synthetic PCM written straight into device memory (bench / tests): stream `seed` of the

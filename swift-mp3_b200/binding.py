@@ -131,7 +131,7 @@ def device_count():
 _TABLES = {"window": (0, "<f4"), "analysis": (1, "<f4"), "mdct_long": (2, "<f4"), "mdct_short": (3, "<f4"),
            "win_long": (4, "<f4"), "win_short": (5, "<f4"), "inv_step": (6, "<f4"), "len15": (7, "u1"),
            "code15": (8, "u1"), "gain_thr": (9, "<f8"), "alias_cs": (10, "<f4"), "alias_ca": (11, "<f4"),
-           "sfb_cum": (12, "<i4")}
+           "sfb_cum": (12, "<i4"), "len31s": (13, "u1"), "tab31": (14, "<u2")}
 
 
 def table(name):

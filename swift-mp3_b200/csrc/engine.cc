@@ -883,6 +883,8 @@ int mp3b_table(int which, void *out, size_t cap_bytes) {
     case 10: src = tab::kAliasCs; n = 8; break;
     case 11: src = tab::kAliasCa; n = 8; break;
     case 12: src = host_sfb_cum(); n = 63; break;
+    case 13: src = tab::kLen31s; n = 31 * 32; es = 1; break;
+    case 14: src = tab::kTab31; n = 31 * 32; es = 2; break;
     default: return fail(MP3B_ERR_BAD_ARG, "unknown table %d", which);
   }
   if (n * es > cap_bytes) return fail(MP3B_ERR_BUFFER_TOO_SMALL, "table %d needs %zu bytes", which, n * es);

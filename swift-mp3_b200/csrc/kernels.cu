@@ -16,22 +16,16 @@ namespace mp3b {
 
 __constant__ float c_inv_step[256];     // 1 / Float(max(2^((g-210)/4), 1e-4)), SRC:798-800
 __constant__ double c_gain_thr[256];    // 2^((g-210)/4) in double: replaces log2 in computeGlobalGain, SRC:1004
-__constant__ uint8_t c_len15[256];      // SRC:2457-2473
-__constant__ uint8_t c_code15[256];     // SRC:2476-2493
 __constant__ int c_sfb_cum[3][21];      // cumulative long sfb widths, SRC:1814-1820
 
 extern const float *host_inv_step();    // tables.cc
 extern const double *host_gain_thr();
 extern const int *host_sfb_cum();
-extern const uint8_t *host_len15();
-extern const uint8_t *host_code15();
 
 cudaError_t upload_tables() {
   cudaError_t e;
   if ((e = cudaMemcpyToSymbol(c_inv_step, host_inv_step(), sizeof(float) * 256))) return e;
   if ((e = cudaMemcpyToSymbol(c_gain_thr, host_gain_thr(), sizeof(double) * 256))) return e;
-  if ((e = cudaMemcpyToSymbol(c_len15, host_len15(), 256))) return e;
-  if ((e = cudaMemcpyToSymbol(c_code15, host_code15(), 256))) return e;
   if ((e = cudaMemcpyToSymbol(c_sfb_cum, host_sfb_cum(), sizeof(int) * 63))) return e;
   return cudaSuccess;
 }
@@ -96,15 +90,10 @@ __device__ __forceinline__ float pow34_reference(float a) {      // the same wit
   return __double2float_rn(__dmul_rn(r, __dsqrt_rn(r)));
 }
 
-// quantizeWithGain SRC:816-821: min(Int32(roundf(mag * inv)), 15); roundf = ties away from zero [OD4].
+// quantizeWithGain SRC:816-821: q = min(Int32(roundf(mag * inv)), 15); roundf = ties away from zero [OD4].
 // inv2 = 2 * inv: scaling by two commutes with the rounding of the product (no overflow / underflow at these
 // magnitudes), so floor(RN(mag * inv2)) = floor(2 t) with t = RN(mag * inv), and roundf(t) = (floor(2 t) + 1) >> 1, t >= 0.
-__device__ __forceinline__ int quant15(float mag, float inv2) {
-  const int q = (__float2int_rd(__fmul_rn(mag, inv2)) + 1) >> 1;
-  return q > 15 ? 15 : q;
-}
-
-// The same quantizer as an index: u = min(floor(RN(mag * inv2)), 30), and q = (u + 1) >> 1 = quant15 (u = 29, 30 -> 15).  The
+// The kernels keep the quantizer as an index: u = min(floor(2 t), 30), and q = (u + 1) >> 1 (u = 29, 30 -> 15).  The
 // Huffman tables indexed by (ux, uy) (tab::kLen31s, tab::kTab31, row stride 32) save the increment, shift and clamp per value;
 // q != 0 <=> u != 0.
 __device__ __forceinline__ int quant30(float mag, float inv2) { return min(__float2int_rd(__fmul_rn(mag, inv2)), 30); }

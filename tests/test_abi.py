@@ -56,6 +56,14 @@ def test_product_tables_equal_oracle(mp3, orc):
     assert np.array_equal(mp3.table("win_long"), orc.table("win_long"))
     assert np.array_equal(mp3.table("win_short"), orc.table("win_short"))
     assert np.array_equal(mp3.table("len15"), orc.table("len15")) and np.array_equal(mp3.table("code15"), orc.table("code15"))
+    # the quantizer-indexed views the kernels use: u = min(floor(2 t), 30) per value, q = (u + 1) >> 1 (kernels.cu quant30)
+    len15, code15 = orc.table("len15").astype(int), orc.table("code15").astype(int)
+    len31, tab31 = mp3.table("len31s").reshape(31, 32), mp3.table("tab31").reshape(31, 32)
+    for ux in range(31):
+        for uy in range(31):
+            qx, qy = (ux + 1) >> 1, (uy + 1) >> 1
+            assert len31[ux, uy] == len15[qx * 16 + qy] + (qx != 0) + (qy != 0)
+            assert tab31[ux, uy] == code15[qx * 16 + qy] | len15[qx * 16 + qy] << 8
     inv = np.array([orc.lib().orc_inv_step(g) for g in range(256)], np.float32)
     assert np.array_equal(mp3.table("inv_step"), inv)
     thr = mp3.table("gain_thr")
