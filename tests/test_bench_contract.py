@@ -28,3 +28,12 @@ def test_numa_cpulist_parser():
     assert sh._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
     assert sh._parse_cpulist("") == set()
     assert sh.shard_range(4096, 3, 8) == (1536, 2048)
+
+
+def test_stdout_carries_only_the_json_line():
+    """Libraries print to file descriptor 1 from C (NCCL's version line): bench.py parks it on stderr until emit()."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.quiet_stdout(); os.write(1, b'NCCL version x\\n'); "
+            "print('python noise'); bench.emit({'a': 1})" % ROOT)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert p.stdout == '{"a": 1}\n' and "NCCL version x" in p.stderr and "python noise" in p.stderr
