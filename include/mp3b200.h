@@ -205,7 +205,7 @@ int mp3b_synth_fill(int device, float *d_pcm, size_t n_samples_per_channel, int 
                     float f_left, float f_right, float amp, float noise, uint64_t seed);
 
 /* Exhaustive on-device check of the two exact-arithmetic shortcuts of the kernels (tests only): mismatches[0] = floats in
- * [1e-10, 65536) where the fast |x|^0.75 differs from its IEEE-double definition, [1] / [2] = finite floats where the
+ * [1e-10, FLT_MAX] where the fast |x|^0.75 differs from its IEEE-double definition, [1] / [2] = finite floats where the
  * FMA-based division by 9 / 3 differs from the IEEE division.  All three must be 0. */
 int mp3b_selftest(int device, uint64_t mismatches[3]);
 

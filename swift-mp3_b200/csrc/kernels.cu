@@ -65,24 +65,24 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ int warp_max_i(int v) { return __reduce_max_sync(0xffffffffu, v); }   // REDUX: one instruction
 __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
-// Correctly rounded double square root for arguments in the normal range (no zero / subnormal / huge inputs, which is
-// all this file ever feeds it): reciprocal-square-root seed, one third-order Newton step, then the Markstein correction
-// g + (d - g * g) * h with h = 1 / (2 sqrt d), which rounds correctly.  Same steps as the library's sqrt.rn.f64 without
-// its range guard and slow-path call; mp3b_selftest compares the two on every float of the encoder's range.
-__device__ __forceinline__ double dsqrt_normal(double d) {
+// Double square root for arguments in the normal range (no zero / subnormal / huge inputs, which is all this file ever
+// feeds it): reciprocal-square-root seed, one third-order Newton step, d * y.  Not always the correctly rounded root — the
+// library's sqrt.rn.f64 adds the correction g + (d - g * g) * (y / 2), a range guard and a slow-path call — but its last-bit
+// error never survives the rounding of the product to FP32: mp3b_selftest compares pow34 below with the IEEE definition on
+// EVERY finite float >= 1e-10 (0 differences; with a second-order step instead it counts 5052, so the test has teeth).
+__device__ __forceinline__ double dsqrt_fast(double d) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
   const double e = __fma_rn(d, -__dmul_rn(y, y), 1.0);             // 1 - d y^2
   const double p = __fma_rn(e, 0.375, 0.5);
   y = __fma_rn(p, __dmul_rn(y, e), y);                             // y (1 + e / 2 + 3 e^2 / 8)
-  const double g = __dmul_rn(d, y), h = __dmul_rn(y, 0.5);
-  return __fma_rn(__fma_rn(-g, g, d), h, g);
+  return __dmul_rn(d, y);
 }
 
 // [OD3] |x|^0.75 = (float)(sqrt(d) * sqrt(sqrt(d))) in IEEE double; a >= 1e-10f.
 __device__ __forceinline__ float pow34(float a) {
-  const double r = dsqrt_normal((double)a);
-  return __double2float_rn(__dmul_rn(r, dsqrt_normal(r)));
+  const double r = dsqrt_fast((double)a);
+  return __double2float_rn(__dmul_rn(r, dsqrt_fast(r)));
 }
 __device__ __forceinline__ float pow34_reference(float a) {      // the same with the library's IEEE square root
   double d = (double)a;
@@ -1247,14 +1247,14 @@ int launch_widen_i16(const int16_t *in, float *out, size_t stride, const StreamP
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Self-test (tests only): pow34 against its definition on every float in [1e-10, 65536), div_exact against the IEEE
+// Self-test (tests only): pow34 against its definition on every finite float >= 1e-10, div_exact against the IEEE
 // division for every finite float.  mismatch[0] / [1] / [2] count pow34, /9 and /3 disagreements.
 __global__ void k_selftest(unsigned long long *mismatch) {
   const uint32_t stride = gridDim.x * blockDim.x;
   unsigned long long bad0 = 0, bad1 = 0, bad2 = 0;
   for (uint64_t u = blockIdx.x * blockDim.x + threadIdx.x; u < (1ull << 32); u += stride) {
     const float a = __uint_as_float((uint32_t)u);
-    if (a >= 1e-10f && a < 65536.0f) bad0 += __float_as_uint(pow34(a)) != __float_as_uint(pow34_reference(a));
+    if (a >= 1e-10f && a <= 3.402823466e38f) bad0 += __float_as_uint(pow34(a)) != __float_as_uint(pow34_reference(a));
     if ((((uint32_t)u >> 23) & 255) != 255) {
       bad1 += __float_as_uint(div_exact(a, 9.0f, 1.0f / 9.0f)) != __float_as_uint(__fdiv_rn(a, 9.0f));
       bad2 += __float_as_uint(div_exact(a, 3.0f, 1.0f / 3.0f)) != __float_as_uint(__fdiv_rn(a, 3.0f));

@@ -144,7 +144,7 @@ def test_batch_of_independent_streams(mp3, orc):
 
 def test_exact_arithmetic_shortcuts(mp3):
     """The kernels' two shortcuts are exact: |x|^0.75 with the guard-free double square root equals its IEEE definition
-    ([OD3]) on every float of [1e-10, 65536), and the FMA-based division by 9 / 3 (MDCT scaling, SRC:1633 / 1658) equals
+    ([OD3]) on every finite float >= 1e-10, and the FMA-based division by 9 / 3 (MDCT scaling, SRC:1633 / 1658) equals
     the IEEE division on every finite float.  Exhaustive, on the device."""
     import ctypes as C
     bad = (C.c_uint64 * 3)()
