@@ -65,24 +65,25 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ int warp_max_i(int v) { return __reduce_max_sync(0xffffffffu, v); }   // REDUX: one instruction
 __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
-// Double square root for arguments in the normal range (no zero / subnormal / huge inputs, which is all this file ever
-// feeds it): reciprocal-square-root seed, one third-order Newton step, d * y.  Not always the correctly rounded root — the
-// library's sqrt.rn.f64 adds the correction g + (d - g * g) * (y / 2), a range guard and a slow-path call — but its last-bit
-// error never survives the rounding of the product to FP32: mp3b_selftest compares pow34 below with the IEEE definition on
-// EVERY finite float >= 1e-10 (0 differences; with a second-order step instead it counts 5052, so the test has teeth).
-__device__ __forceinline__ double dsqrt_fast(double d) {
+// d^-1/2 in double for arguments in the normal range (no zero / subnormal / huge inputs, which is all this file ever feeds
+// it): reciprocal-square-root seed and one third-order Newton step.  The library's sqrt.rn.f64 continues with d * y, the
+// correction g + (d - g * g) * (y / 2), a range guard and a slow-path call to deliver the correctly rounded root; pow34
+// needs none of that, because the last-bit error never survives the rounding of the result to FP32: mp3b_selftest
+// compares pow34 with the IEEE definition on EVERY finite float >= 1e-10 (0 of 2.3e9 differ; with a second-order step
+// instead it counts 5052, so the test has teeth).
+__device__ __forceinline__ double drsqrt_fast(double d) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
   const double e = __fma_rn(d, -__dmul_rn(y, y), 1.0);             // 1 - d y^2
   const double p = __fma_rn(e, 0.375, 0.5);
-  y = __fma_rn(p, __dmul_rn(y, e), y);                             // y (1 + e / 2 + 3 e^2 / 8)
-  return __dmul_rn(d, y);
+  return __fma_rn(p, __dmul_rn(y, e), y);                          // y (1 + e / 2 + 3 e^2 / 8)
 }
 
-// [OD3] |x|^0.75 = (float)(sqrt(d) * sqrt(sqrt(d))) in IEEE double; a >= 1e-10f.
+// [OD3] |x|^0.75 = (float)(sqrt(d) * sqrt(sqrt(d))) in IEEE double, a >= 1e-10f; evaluated as d * (d^1/2)^-1/2.
 __device__ __forceinline__ float pow34(float a) {
-  const double r = dsqrt_fast((double)a);
-  return __double2float_rn(__dmul_rn(r, dsqrt_fast(r)));
+  const double d = (double)a;
+  const double r = __dmul_rn(d, drsqrt_fast(d));                   // d^1/2
+  return __double2float_rn(__dmul_rn(d, drsqrt_fast(r)));          // d * d^-1/4
 }
 __device__ __forceinline__ float pow34_reference(float a) {      // the same with the library's IEEE square root
   double d = (double)a;
