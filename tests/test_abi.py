@@ -114,3 +114,11 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(root, f)).read()
                 assert "oracle_binding" not in text and "libmp3oracle" not in text and "dlopen" not in text, f
                 assert not re.search(r'#include\s+"[^"]*oracle', text) and not re.search(r"^\s*(import|from)\s+\S*oracle", text, re.M), f
+
+
+def test_generated_tables_are_current(tmp_path):
+    """swift-mp3_b200/csrc/tables_gen.h is what tools/gen_device_tables.py writes today (no hand edits, no drift)."""
+    import subprocess, sys
+    out = tmp_path / "tables_gen.h"
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_device_tables.py"), str(out)], check=True, capture_output=True, timeout=120)
+    assert out.read_text() == open(os.path.join(ROOT, "swift-mp3_b200", "csrc", "tables_gen.h")).read()
