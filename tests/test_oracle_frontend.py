@@ -1,0 +1,105 @@
+"""An independent restatement of the spectral front end, in float64 numpy and in matrix form, against the oracle's traces.
+
+The oracle (oracle/mp3_oracle.c) walks the reference's loops one sample at a time in float32; this file states the same
+mathematics the other way round — whole-signal matrix products in float64, written from the formulas of
+Sources/SwiftMP3/MP3Encoder.swift (SRC) and not from the oracle's code — so that a transcription slip in either shows up
+as a disagreement.  The two differ only by float32 rounding, which is what north_star's tiers allow:
+  tier 1  subband samples and MDCT spectra within 1e-5 of the granule's peak;
+  tier 2  the quantizer's ix identical on (nearly) every line at the gain the oracle used.
+Block types and gains are taken from the oracle's trace (the transient detector and the gain loop have their own
+known-answer tests); everything between the PCM and ix is recomputed here."""
+import numpy as np
+import pytest
+
+import signals
+
+# ISO 11172-3 table B.9 as printed in SRC:1568-1575
+CS = np.array([0.857492926, 0.881741997, 0.949628649, 0.983314592, 0.995517816, 0.999160558, 0.999899195, 0.999993155])
+CA = np.array([-0.514495755, -0.471731969, -0.313377454, -0.181913200, -0.094574193, -0.040965583, -0.014198569, -0.003699975])
+
+
+def _subbands(x, window):
+    """PolyphaseFilterbank.analyze SRC:1367-1411 for a whole channel: returns S[step, subband]."""
+    n_steps = len(x) // 32
+    xp = np.concatenate([np.zeros(480), x.astype(np.float64)])               # the 512-buffer starts as zeros (SRC:275)
+    idx = 32 * np.arange(n_steps)[:, None] + (511 - np.arange(512))[None, :]  # reversed buffer: newest sample first (SRC:1386-1387)
+    z = xp[idx] * window[None, :]                                             # SRC:1389
+    y = z.reshape(n_steps, 8, 64).sum(axis=1)                                 # Y[j] = sum_i Z[j + 64 i], SRC:1392-1399
+    k, n = np.arange(32)[:, None], np.arange(64)[None, :]
+    m = np.cos(np.pi / 64.0 * (2 * k + 1) * (n - 16))                         # SRC:1197-1206
+    return y @ m.T
+
+
+def _mdct(sub, block_types):
+    """MDCT.apply SRC:1512-1565 (+ mdctLong 1619-1636, mdctShort 1639-1662, alias reduction 1581-1616) for a whole channel."""
+    n_gr = sub.shape[0] // 18
+    s = sub.reshape(n_gr, 18, 32).transpose(0, 2, 1).copy()                   # [granule, subband, t]
+    s[:, 1::2, 1::2] *= -1.0                                                  # frequency inversion, SRC:1520-1524
+    prev = np.concatenate([np.zeros((1, 32, 18)), s[:-1]])                    # overlap = the previous granule's (flipped) samples
+    comb = np.concatenate([prev, s], axis=2)                                  # [granule, subband, 36]
+    kk, mm = np.arange(36)[None, :], np.arange(18)[:, None]
+    long_m = np.cos(np.pi / 72.0 * (2 * kk + 1 + 18) * (2 * mm + 1))          # SRC:1422-1433
+    long_w = np.sin(np.pi / 36.0 * (np.arange(36) + 0.5))                     # SRC:1450-1457
+    k2, m2 = np.arange(12)[None, :], np.arange(6)[:, None]
+    short_m = np.cos(np.pi / 24.0 * (2 * k2 + 1 + 6) * (2 * m2 + 1))          # SRC:1436-1447
+    short_w = np.sin(np.pi / 12.0 * (np.arange(12) + 0.5))                    # SRC:1460-1467
+    out_long = (comb * long_w) @ long_m.T / 9.0                               # [granule, subband, 18]
+    out_short = np.zeros_like(out_long)
+    for w in range(3):                                                        # SRC:1645-1659: window w at offset 6 w + 6, out[w + 3 m]
+        seg = comb[:, :, 6 * w + 6: 6 * w + 18] * short_w
+        out_short[:, :, w::3] = seg @ short_m.T / 3.0
+    bt = np.asarray(block_types)
+    use_long = (bt == 0)[:, None] | ((bt == 1)[:, None] & (np.arange(32) < 2)[None, :])   # SRC:1542-1553 (mixed = raw value 1)
+    spec = np.where(use_long[:, :, None], out_long, out_short).reshape(n_gr, 576)
+    for g in np.nonzero(bt == 0)[0]:                                          # alias reduction, long blocks only (SRC:1560-1562)
+        x = spec[g]
+        sb = np.arange(31)[:, None]
+        iu, il = sb * 18 + 17 - np.arange(8)[None, :], (sb + 1) * 18 + np.arange(8)[None, :]
+        upper, lower = x[iu].copy(), x[il].copy()
+        x[iu] = lower * CA + upper * CS
+        x[il] = lower * CS - upper * CA
+    return spec
+
+
+def _quantize(spec, gains):
+    """quantizeWithGain SRC:797-825 at the gain the oracle's loop ended on."""
+    step = np.maximum(2.0 ** ((np.asarray(gains, dtype=np.float64) - 210.0) / 4.0), 1e-4)[:, None]
+    scaled = np.maximum(np.abs(spec), 1e-10) ** 0.75 / step
+    q = np.minimum(np.floor(scaled + 0.5), 15).astype(np.int64)               # .rounded(): ties away from zero (scaled >= 0)
+    return np.where(spec < 0, -q, q)
+
+
+@pytest.mark.parametrize("name", ["sine_noise_stereo", "white_mono_48k", "castanets_stereo"])
+def test_front_end_against_float64_restatement(orc, name):
+    if name == "sine_noise_stereo":
+        pcm, opts, ch = signals.sine_noise(1.0), dict(mode="stereo"), 2
+    elif name == "white_mono_48k":
+        pcm, opts, ch = signals.white(1.0), dict(mode="mono", sample_rate=48000, bitrate_kbps=320), 1
+    else:
+        pcm, opts, ch = signals.castanets(2.0), dict(mode="stereo", bitrate_kbps=128), 2
+    n_frames = len(pcm) // (1152 * ch)
+    pcm = pcm[: n_frames * 1152 * ch]                                         # whole frames: no flush padding to model
+    _, rs = orc.encode_all(pcm, trace=True, **opts)
+    gt = rs.gc_trace()
+    assert len(gt) == n_frames * 2 * ch
+    window = orc.table("window").astype(np.float64)
+    worst_sub = worst_spec = 0.0
+    lines = same = 0
+    for c in range(ch):
+        x = pcm[c::ch]
+        tr = gt[c::ch]                                                        # gc order is (granule, channel)
+        sub = _subbands(x, window)
+        ref_sub = tr["subband"].reshape(-1, 32, 18).transpose(0, 2, 1).reshape(-1, 32)   # oracle layout [sb][t] per granule
+        peak = np.abs(ref_sub).reshape(-1, 18 * 32).max(axis=1).repeat(18)[:, None]
+        worst_sub = max(worst_sub, float((np.abs(sub - ref_sub) / np.maximum(peak, 1e-12)).max()))
+        spec = _mdct(sub, tr["block_type"])
+        gpeak = np.abs(tr["spectrum"]).max(axis=1)[:, None]
+        worst_spec = max(worst_spec, float((np.abs(spec - tr["spectrum"]) / np.maximum(gpeak, 1e-12)).max()))
+        ix = _quantize(spec, tr["gain_used"])
+        lines += ix.size
+        same += int((ix == tr["ix"]).sum())
+        if name == "castanets_stereo":
+            assert (tr["block_type"] == 2).any() and (tr["block_type"] == 1).any()      # short and mixed blocks are exercised
+    assert worst_sub < 2e-6, worst_sub                                        # tier 1 asks for 1e-5; measured 4e-7 (float32 rounding)
+    assert worst_spec < 2e-6, worst_spec
+    assert same / lines > 0.9999, (same, lines)                               # tier 2, per line; measured: every line identical
