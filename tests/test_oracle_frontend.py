@@ -103,3 +103,72 @@ def test_front_end_against_float64_restatement(orc, name):
     assert worst_sub < 2e-6, worst_sub                                        # tier 1 asks for 1e-5; measured 4e-7 (float32 rounding)
     assert worst_spec < 2e-6, worst_spec
     assert same / lines > 0.9999, (same, lines)                               # tier 2, per line; measured: every line identical
+
+
+SFB_LONG = {44100: [4, 4, 4, 4, 4, 4, 6, 6, 8, 8, 10, 12, 16, 20, 24, 28, 34, 42, 50, 54, 76],          # SRC:1814
+            48000: [4, 4, 4, 4, 4, 4, 6, 6, 6, 8, 10, 12, 16, 18, 22, 28, 34, 40, 46, 54, 54],          # SRC:1817
+            32000: [4, 4, 4, 4, 4, 4, 6, 6, 8, 10, 12, 16, 20, 24, 30, 38, 46, 56, 68, 84, 102]}        # SRC:1820
+
+
+@pytest.mark.parametrize("name", ["sine_noise_stereo", "white_mono_48k", "castanets_stereo", "sine_32k"])
+def test_decisions_and_side_fields_against_restatement(orc, name):
+    """The per-granule decisions and side-info fields, restated from SRC in numpy on the oracle's own spectrum / ix:
+    block type + subblock_gain (SRC:1944-1968), initial gain (989-1006), big_values (692-700), the table-15 bit count
+    (828-853) = part2_3_length, preflag (2042-2066), region counts (856-887), and the gain loop's outcome (734-794): the
+    count fits the budget unless the loop ran out of iterations, and the gain before it did not fit."""
+    sr = 44100
+    if name == "sine_noise_stereo":
+        pcm, opts, ch = signals.sine_noise(1.0), dict(mode="stereo"), 2
+    elif name == "white_mono_48k":
+        pcm, opts, ch, sr = signals.white(1.0), dict(mode="mono", sample_rate=48000, bitrate_kbps=320), 1, 48000
+    elif name == "castanets_stereo":
+        pcm, opts, ch = signals.castanets(2.0), dict(mode="stereo", bitrate_kbps=128), 2
+    else:
+        pcm, opts, ch, sr = signals.sine_noise(1.0, sr=32000), dict(mode="stereo", sample_rate=32000, bitrate_kbps=64), 2, 32000
+    n_frames = len(pcm) // (1152 * ch)
+    pcm = pcm[: n_frames * 1152 * ch]
+    _, rs = orc.encode_all(pcm, trace=True, **opts)
+    gt = rs.gc_trace()
+    len15 = orc.table("len15").astype(int).reshape(16, 16)
+    bounds = np.cumsum(SFB_LONG[sr])
+    bt_same = 0
+    for i, t in enumerate(gt):
+        c, g = i % ch, i // ch
+        x = pcm[c::ch][576 * g: 576 * (g + 1)].astype(np.float64)
+        e3 = (x.reshape(3, 192) ** 2).sum(axis=1) / 192.0
+        mx, mn = e3.max(), e3.min()
+        ratio = mx / max(mn, 1e-4)
+        bt = (1 if int(np.argmax(e3)) == 0 else 2) if ratio > 6.0 else 0
+        sbg = [int((1.0 - min(max(e / max(mx, 1e-4), 0.0), 1.0)) * 7.0) for e in e3]
+        bt_same += int(bt == t["block_type"] and sbg == list(t["subblock_gain"]))
+        spec = t["spectrum"].astype(np.float64)
+        peak = np.abs(spec).max()
+        g0 = 210 if peak <= 0 else min(max(210 + int(4.0 * np.log2(peak ** 0.75 / 15.0)), 0), 255)
+        assert abs(g0 - t["g0"]) <= 1, (i, g0, t["g0"])                        # float32 powf against float64 at a truncation edge
+        ix = t["ix"]
+        nz = np.nonzero(ix)[0]
+        last = int(nz[-1]) + 1 if nz.size else 0
+        bv = min(((last + 1) & ~1) // 2, 288)
+        assert bv == t["big_values"]
+        a = np.minimum(np.abs(ix[: 2 * bv]), 15).reshape(-1, 2)
+        bits = int(len15[a[:, 0], a[:, 1]].sum() + np.count_nonzero(a))
+        assert bits == t["bits"], (i, bits, t["bits"])
+        assert int((spec[432:] ** 2).sum() > 1.5 * (spec[:432] ** 2).sum()) == t["preflag"] or \
+            abs((spec[432:] ** 2).sum() - 1.5 * (spec[:432] ** 2).sum()) < 1e-6 * (spec ** 2).sum()
+        r0 = 0
+        for k in range(15):
+            if bounds[k] <= 2 * bv:
+                r0 = k
+            else:
+                break
+        r1 = 0
+        for k in range(r0 + 1, min(r0 + 8, 21)):
+            if bounds[k] <= 2 * bv:
+                r1 = k - r0 - 1
+            else:
+                break
+        assert (min(r0, 15), min(r1, 7)) == (t["region0"], t["region1"])
+        # the loop's outcome: it stopped because the count fits, or it ran out of iterations / hit gain 255
+        assert t["bits"] <= t["max_bits"] or t["iterations"] == 20 or t["gain_out"] >= 255, (i, t["bits"], t["max_bits"])
+        assert t["gain_used"] <= t["gain_out"] <= 255
+    assert bt_same >= 0.995 * len(gt), (bt_same, len(gt))                      # float64 sums against float32 at the ratio / truncation edges
