@@ -172,3 +172,45 @@ def test_decisions_and_side_fields_against_restatement(orc, name):
         assert t["bits"] <= t["max_bits"] or t["iterations"] == 20 or t["gain_out"] >= 255, (i, t["bits"], t["max_bits"])
         assert t["gain_used"] <= t["gain_out"] <= 255
     assert bt_same >= 0.995 * len(gt), (bt_same, len(gt))                      # float64 sums against float32 at the ratio / truncation edges
+
+
+@pytest.mark.parametrize("cfg", [dict(mode="stereo"), dict(mode="mono", bitrate_kbps=64), dict(mode="stereo", crc_protected=True, bitrate_kbps=320, sample_rate=48000),
+                                 dict(mode="jointStereo", vbr=True, quality=2), dict(mode="stereo", sample_rate=32000, bitrate_kbps=96)])
+def test_frame_chain_against_restatement(orc, cfg):
+    """encodeFrame's serial chain (SRC:475-568: padding accumulator, frame / slot sizes, reservoir snapshot, per-granule
+    budget, stream FIFO, updateReservoir) replayed in Python from the oracle's own per-frame bitrate and per-granule bit
+    counts; every frame field and every granule's max_bits must come out the same."""
+    ch = 1 if cfg["mode"] == "mono" else 2
+    sr = cfg.get("sample_rate", 44100)
+    pcm = signals.castanets(2.0, sr=sr) if cfg.get("vbr") else signals.sine_noise(1.3, sr=sr)
+    if ch == 1:
+        pcm = np.ascontiguousarray(pcm[0::2])
+    pcm = pcm[: len(pcm) - 333 * ch]                                          # ragged: the last frame is flush()'s padded one
+    _, rs = orc.encode_all(pcm, trace=True, **cfg)
+    ft, gt = rs.frame_trace(), rs.gc_trace()
+    side, crc = (17 if ch == 1 else 32), (2 if cfg.get("crc_protected") else 0)
+    pad_rem = avail = backlog = 0
+    prev_slot = None
+    for f, t in enumerate(ft):
+        num = 144 * int(t["bitrate_kbps"]) * 1000
+        pad_rem += num % sr                                                   # shouldPad SRC:456-463
+        padding = 0
+        if pad_rem >= sr:
+            pad_rem -= sr; padding = 1
+        frame_size = num // sr + padding
+        mds = frame_size - 4 - crc - side
+        final = f == len(ft) - 1                                              # the ragged tail: encodeFrame(isFinal: true) from flush()
+        mdb = 0 if final else min(backlog, 511)                               # SRC:499, 2099-2101
+        res_bits = 0 if final else avail * 8                                  # SRC:500
+        bpg = (mds * 8 + res_bits * 9 // 10) // (2 * ch)                      # SRC:647-650
+        gcs = gt[f * 2 * ch: (f + 1) * 2 * ch]
+        huff = (int(gcs["bits"].sum()) + 7) // 8                              # one byte pad per frame, SRC:729
+        assert (padding, frame_size, mds, mdb, res_bits, huff, int(final)) == \
+            (t["padding"], t["frame_size"], t["main_data_size"], t["main_data_begin"], t["reservoir_bits"], t["huff_bytes"], t["is_final"]), f
+        assert (gcs["max_bits"] == bpg).all(), f
+        backlog += huff                                                       # appendHuffmanData SRC:511
+        if prev_slot is not None:
+            backlog -= min(prev_slot, backlog)                                # fillSlot of the buffered frame SRC:548-556, 2110-2121
+        prev_slot = mds
+        avail = min(max(avail + mds - huff, 0), 511)                          # updateReservoir SRC:2125-2128
+    assert rs.frame_count == len(ft)
