@@ -214,3 +214,42 @@ def test_frame_chain_against_restatement(orc, cfg):
         prev_slot = mds
         avail = min(max(avail + mds - huff, 0), 511)                          # updateReservoir SRC:2125-2128
     assert rs.frame_count == len(ft)
+
+
+@pytest.mark.parametrize("cfg", [dict(mode="jointStereo", vbr=True, quality=2), dict(mode="mono", vbr=True, quality=7, bitrate_kbps=96),
+                                 dict(mode="stereo", vbr=True, quality=0, bitrate_kbps=256, sample_rate=48000)])
+def test_vbr_bitrate_choice_against_restatement(orc, cfg):
+    """VBRState.chooseBitrate (SRC:1177-1189) + VBRState.update (1144-1153) + MP3Tables.bitrateIndex (2509-2523) replayed in
+    float32 numpy from the oracle's own frame / granule energies: the bitrate of every frame must come out the same."""
+    f32 = np.float32
+    ch = 1 if cfg["mode"] == "mono" else 2
+    sr, base, q = cfg.get("sample_rate", 44100), cfg.get("bitrate_kbps", 128), cfg["quality"]
+    pcm = signals.castanets(3.0, sr=sr)
+    if ch == 1:
+        pcm = np.ascontiguousarray(pcm[0::2])
+    _, rs = orc.encode_all(pcm, trace=True, **cfg)
+    ft, gt = rs.frame_trace(), rs.gc_trace()
+    table = [0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, 0]             # SRC:2511
+    hist, seen = [], set()
+    for f, t in enumerate(ft):
+        e = f32(t["frame_energy"])
+        if hist:
+            s = f32(0.0)
+            for h in hist:
+                s = f32(s + h)
+            average = f32(s / f32(len(hist)))
+        else:
+            average = e
+        ratio = min(max(f32(e / max(average, f32(0.0001))), f32(0.5)), f32(2.0))
+        qf = f32(f32(9 - q) / f32(9.0))
+        max_adj = int(f32(f32(32.0) + f32(f32(32.0) * qf)))
+        adj = int(f32(f32(ratio - f32(1.0)) * f32(max_adj)))
+        lo, hi = max(32, base - 64 + q * 8), min(320, base + 64 - q * 4)
+        want = max(lo, min(base + adj, hi))
+        idx = table.index(want) if want in table else min(range(16), key=lambda i: abs(table[i] - want))   # first minimum, like min(by:)
+        assert (idx, table[idx]) == (t["bitrate_index"], t["bitrate_kbps"]), (f, want)
+        seen.add(int(t["bitrate_kbps"]))
+        for g in gt[f * 2 * ch: (f + 1) * 2 * ch]:                            # VBRState.update: ten most recent granule energies
+            hist.append(f32(g["energy"]))
+        hist = hist[-10:]
+    assert len(seen) >= 2                                                     # the bitrate really moves on this signal
