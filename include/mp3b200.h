@@ -144,6 +144,9 @@ int mp3b_pool_open(mp3b_pool *p, int *slot);
  * flush() closes the session (it no longer delays the steps of the others). */
 int mp3b_pool_encode(mp3b_pool *p, int slot, const float *pcm, size_t n_floats, uint8_t *out, size_t cap, size_t *written);
 int mp3b_pool_flush(mp3b_pool *p, int slot, uint8_t *out, size_t cap, size_t *written);
+/* When encode / flush returned MP3B_ERR_BUFFER_TOO_SMALL (*written = the size needed) the bytes are kept: fetch them here
+ * before the session's next call (which is refused until then).  Same contract as mp3b_session_take_output. */
+int mp3b_pool_take_output(mp3b_pool *p, int slot, uint8_t *out, size_t cap, size_t *written);
 /* Steps run so far and requests served by them (requests / steps = achieved coalescing). */
 int mp3b_pool_stats(mp3b_pool *p, uint64_t *steps, uint64_t *requests);
 const char *mp3b_pool_last_error(void);

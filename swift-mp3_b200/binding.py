@@ -14,6 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libmp3b200.so")
 
 
+ERR_BUFFER_TOO_SMALL = -4      # mp3b_status, include/mp3b200.h
+
+
 class MP3BError(RuntimeError):
     def __init__(self, code, message):
         super().__init__("mp3b200 error %d: %s" % (code, message))
@@ -102,6 +105,7 @@ def lib():
         "mp3b_pool_open": (i32, [vp, C.POINTER(i32)]),
         "mp3b_pool_encode": (i32, [vp, i32, vp, sz, vp, sz, C.POINTER(sz)]),
         "mp3b_pool_flush": (i32, [vp, i32, vp, sz, C.POINTER(sz)]),
+        "mp3b_pool_take_output": (i32, [vp, i32, vp, sz, C.POINTER(sz)]),
         "mp3b_pool_stats": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "mp3b_pool_last_error": (C.c_char_p, []),
     }
@@ -390,6 +394,10 @@ class SessionPool:
             buf = (C.c_uint8 * cap)()
             n = C.c_size_t(0)
             rc = fn(self._pool._h, self._slot, *head, buf, cap, C.byref(n))
+            if rc == ERR_BUFFER_TOO_SMALL:                       # the bytes are kept by the pool: fetch them with a buffer that fits
+                cap = n.value
+                buf = (C.c_uint8 * cap)()
+                rc = lib().mp3b_pool_take_output(self._pool._h, self._slot, buf, cap, C.byref(n))
             if rc != 0:
                 raise MP3BError(rc, (lib().mp3b_pool_last_error() or b"").decode())
             return bytes(memoryview(buf)[:n.value])

@@ -22,6 +22,7 @@ struct Slot {
   bool open = false;         // acquired by a client
   bool pending = false;      // request deposited, step not yet run
   bool done = false;         // result ready for the waiting client
+  bool undelivered = false;  // the caller's buffer was too small: `out` waits for mp3b_pool_take_output
   int flush = 0, rc = 0;
   size_t n = 0;              // request: n floats, copied into the slot's arena row (the caller's array may be reused
                              // after return, SRC:298) or, when larger than a row, into `big`
@@ -141,7 +142,7 @@ int mp3b_pool_open(mp3b_pool *p, int *slot) {
   if (!p || !slot) return MP3B_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lk(p->mu);
   for (int i = 0; i < p->n; ++i)
-    if (!p->slots[i]->open) { Slot &s = *p->slots[i]; s.pending = s.done = false; s.flush = s.rc = 0; s.n = 0; s.open = true; p->n_open += 1; *slot = i; return MP3B_OK; }
+    if (!p->slots[i]->open && !p->slots[i]->undelivered) { Slot &s = *p->slots[i]; s.pending = s.done = false; s.flush = s.rc = 0; s.n = 0; s.open = true; p->n_open += 1; *slot = i; return MP3B_OK; }
   return MP3B_ERR_BAD_ARG;                         // every session of the pool is in use
 }
 
@@ -151,6 +152,7 @@ static int pool_call(mp3b_pool *p, int slot, const float *pcm, size_t n_floats, 
   Slot &s = *p->slots[slot];
   {
     std::unique_lock<std::mutex> lk(p->mu);
+    if (s.undelivered) { t_pool_err = "output of the previous call is still pending: call mp3b_pool_take_output"; return MP3B_ERR_BAD_ARG; }
     if (!s.open || s.pending || p->stop) return MP3B_ERR_BAD_ARG;      // one call per session at a time (README:207)
     s.n = n_floats;
     if (n_floats > p->row) s.big.assign(pcm, pcm + n_floats);
@@ -171,7 +173,11 @@ static int pool_call(mp3b_pool *p, int slot, const float *pcm, size_t n_floats, 
   }
   if (s.rc) { t_pool_err = s.err; return s.rc; }
   if (written) *written = s.out.size();
-  if (s.out.size() > cap) return MP3B_ERR_BUFFER_TOO_SMALL;
+  if (s.out.size() > cap || (!s.out.empty() && !out)) {               // nothing is lost: the bytes wait for mp3b_pool_take_output
+    std::lock_guard<std::mutex> lk(p->mu);
+    s.undelivered = true;
+    return MP3B_ERR_BUFFER_TOO_SMALL;
+  }
   if (!s.out.empty()) memcpy(out, s.out.data(), s.out.size());
   return MP3B_OK;
 }
@@ -181,6 +187,17 @@ int mp3b_pool_encode(mp3b_pool *p, int slot, const float *pcm, size_t n_floats, 
 }
 int mp3b_pool_flush(mp3b_pool *p, int slot, uint8_t *out, size_t cap, size_t *written) {
   return pool_call(p, slot, nullptr, 0, 1, out, cap, written);
+}
+int mp3b_pool_take_output(mp3b_pool *p, int slot, uint8_t *out, size_t cap, size_t *written) {
+  if (!p || slot < 0 || slot >= p->n) return MP3B_ERR_BAD_ARG;
+  Slot &s = *p->slots[slot];
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (!s.undelivered) { if (written) *written = 0; return MP3B_OK; }
+  if (written) *written = s.out.size();
+  if (s.out.size() > cap || !out) return MP3B_ERR_BUFFER_TOO_SMALL;
+  memcpy(out, s.out.data(), s.out.size());
+  s.undelivered = false;
+  return MP3B_OK;
 }
 int mp3b_pool_stats(mp3b_pool *p, uint64_t *steps, uint64_t *requests) {
   if (!p) return MP3B_ERR_BAD_ARG;

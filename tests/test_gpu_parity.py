@@ -271,6 +271,17 @@ def test_session_pool_concurrent_threads(mp3, orc):
         assert got[i] == ref, "session %d" % i
     st = pool.stats()
     assert st["requests"] == n * (chunks + 2) and st["steps"] < st["requests"] / 4, st      # on average > 4 calls per step
+    # a buffer that is too small loses nothing: the size comes back, the next call is refused, take_output delivers
+    import ctypes as C
+    L, s2 = mp3.lib(), pool.newSession()
+    x = np.ascontiguousarray(pcms[1][:2304 * 3])
+    n, small, big = C.c_size_t(0), (C.c_uint8 * 8)(), (C.c_uint8 * 4096)()
+    assert L.mp3b_pool_encode(pool._h, s2._slot, x.ctypes.data, x.size, small, 8, C.byref(n)) == -4 and n.value > 8
+    need = n.value
+    assert L.mp3b_pool_encode(pool._h, s2._slot, x.ctypes.data, x.size, big, 4096, C.byref(n)) == -1      # refused: output pending
+    assert L.mp3b_pool_take_output(pool._h, s2._slot, big, 4096, C.byref(n)) == 0 and n.value == need
+    rs = orc.Session()
+    assert bytes(big[:need]) == rs.encode(x) and s2.flush() == rs.flush()
     # a flushed slot is a fresh session again
     s = pool.newSession()
     again = s.encode(pcms[0][:2304 * 3]) + s.flush()
