@@ -175,6 +175,8 @@ def emit(line):
         os.dup2(_REAL_STDOUT, 1)
     print(json.dumps(line))
     sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)                  # whatever a library still prints while shutting down goes to stderr again
 
 
 def main():
