@@ -85,6 +85,9 @@ int mp3b_session_take_output(mp3b_session *s, uint8_t *out, size_t cap, size_t *
 size_t mp3b_session_output_bound(const mp3b_session *s, size_t n_floats);
 /* EncoderSession.generateXingHeader(), SRC:367-449 (uses the counters as of now). */
 int mp3b_session_xing_header(const mp3b_session *s, uint8_t *out, size_t cap, size_t *written);
+/* Size of the Xing placeholder MP3Encoder.encode(_:to:) reserves before the first audio frame, SRC:198-200:
+ * 144 * bitrateValue(bitrateIndex(bitrate_kbps)) * 1000 / sample_rate, i.e. from the SNAPPED bitrate.  Host only. */
+int mp3b_xing_frame_size(const mp3b_options *opts);
 /* EncoderSession.encodedFrameCount / encodedByteCount, SRC:261-264. */
 uint32_t mp3b_session_frame_count(const mp3b_session *s);
 uint32_t mp3b_session_byte_count(const mp3b_session *s);

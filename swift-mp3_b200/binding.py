@@ -71,7 +71,7 @@ def lib():
         "mp3b_session_create": (i32, [C.POINTER(_Options), i32, C.POINTER(vp)]), "mp3b_session_destroy": (None, [vp]),
         "mp3b_session_encode": (i32, [vp, vp, sz, vp, sz, szp]), "mp3b_session_flush": (i32, [vp, vp, sz, szp]),
         "mp3b_session_take_output": (i32, [vp, vp, sz, szp]), "mp3b_session_output_bound": (sz, [vp, sz]),
-        "mp3b_session_xing_header": (i32, [vp, vp, sz, szp]),
+        "mp3b_session_xing_header": (i32, [vp, vp, sz, szp]), "mp3b_xing_frame_size": (i32, [C.POINTER(_Options)]),
         "mp3b_session_frame_count": (C.c_uint32, [vp]), "mp3b_session_byte_count": (C.c_uint32, [vp]),
         "mp3b_id3_build": (i32, [C.POINTER(_ID3), vp, sz, szp]),
         "mp3b_batch_create": (i32, [C.POINTER(_Options), i32, i32, C.POINTER(vp)]),
@@ -467,10 +467,10 @@ class MP3Encoder:
         s = self.newSession(device)
         try:
             id3 = s.generateID3Tag()
-            o = self.options
+            o = self.options._c()
             with open(path, "wb") as f:
                 f.write(id3)
-                f.write(bytes(144 * o.bitrateKbps * 1000 // o.sampleRate))      # SRC:198-205
+                f.write(bytes(_check(lib().mp3b_xing_frame_size(C.byref(o)))))   # SRC:198-205: from the snapped bitrate
                 for c in chunks:
                     f.write(s.encode(c))
                 f.write(s.flush())

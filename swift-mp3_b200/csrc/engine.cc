@@ -36,6 +36,7 @@ int fail(int code, const char *fmt, ...) {
   } while (0)
 
 template <class T> inline T round_up(T v, T a) { return (v + a - 1) / a * a; }
+constexpr int kMaxStreams = 65535;      // streams of one device batch: the stream index is gridDim.y in several launches
 
 std::mutex g_dev_mu;
 bool g_tables_uploaded[64] = {};
@@ -77,6 +78,7 @@ struct mp3b_batch {
   std::vector<std::vector<uint16_t>> frame_sizes;       // SRC:258
   int max_frame_bytes = 0;
   int sticky = 0;
+  bool planned = false;                                  // the current call has started to mutate the host bookkeeping
   // measurement
   float stage_ms[MP3B_STAGE_COUNT] = {};
   int launches = 0, passes = 0;
@@ -172,6 +174,7 @@ template <class T> cudaError_t dalloc(T *&p, size_t n, bool zero = true) {
 
 int create_batch(const mp3b_options *opts, int n_streams, int device, int frames_per_pass, mp3b_batch **out) {
   if (!opts || !out || n_streams <= 0) return fail(MP3B_ERR_BAD_ARG, "null options / out or n_streams <= 0");
+  if (n_streams > kMaxStreams) return fail(MP3B_ERR_BAD_ARG, "n_streams %d exceeds the per-device limit of %d (the stream index is a grid y dimension); split the batch or use mp3b_batch_create_multi", n_streams, kMaxStreams);
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return fail(MP3B_ERR_CUDA, "no CUDA device: the engine has no CPU fallback"); }
   if (device < 0 || device >= count) return fail(MP3B_ERR_BAD_ARG, "device %d out of range (%d devices)", device, count);
@@ -225,6 +228,9 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
     return fail(e == cudaErrorMemoryAllocation ? MP3B_ERR_OOM : MP3B_ERR_CUDA, "batch allocation failed: %s", cudaGetErrorString(e));
   }
   if (!cfg.vbr && cudaMemset(p.frame_br, cfg.cbr_index, S * Fc) != cudaSuccess) { free_batch(b); return fail(MP3B_ERR_CUDA, "batch initialisation failed"); }   // constant for CBR: the pre-pass may be skipped
+  // The zero fills above ran on the legacy default stream; the engine's own streams are non-blocking and never synchronise
+  // with it, so the batch is handed out only when they have landed.
+  if (cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { free_batch(b); return fail(MP3B_ERR_CUDA, "batch initialisation failed"); }
   b->pending.assign(S, 0); b->out_len.assign(S, 0); b->frame_count.assign(S, 0); b->byte_count.assign(S, 0);
   b->frame_sizes.resize(S);
   b->d_plan[0] = p.plan;
@@ -255,8 +261,8 @@ int ensure_trace(mp3b_batch *b) {
 }
 
 // One API call = encode(samples:) on every stream (+ optional flush()), split into passes of at most Fc frames.
-int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, bool device_ptrs, int flush,
-             const uint8_t *flush_mask, bool download, size_t row_floats = 0, int elem_bytes = 4) {
+int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, bool device_ptrs, int flush,
+                  const uint8_t *flush_mask, bool download, size_t row_floats, int elem_bytes) {
   // elem_bytes = 2: pcm[] really are const int16_t * (mp3b_batch_encode_i16); sample i means Float(pcm[i]) / 32768
   if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");
   if (b->sticky) return fail(b->sticky, "batch is in a failed state: %s", g_err.c_str());
@@ -444,6 +450,7 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
   };
   int slot = 0, par = 0;
   int open_slot = -1, open_par = 0;                              // the pass whose host-side work is still outstanding
+  b->planned = true;                                             // from here on the host bookkeeping (pending) runs ahead of the device
   bool have = plan_pass(slot);
   if (have) { rc = issue_h2d(slot); if (rc) return rc; }
   while (have) {
@@ -552,6 +559,16 @@ int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, boo
   { float ms = 0; cudaEventElapsedTime(&ms, b->ev[0], b->ev[1]); b->stage_ms[MP3B_STAGE_D2H] += ms; b->stage_ms[MP3B_STAGE_TOTAL] += ms; }
   return MP3B_OK;
 #undef LAUNCH
+}
+
+// A failure after the first plan_pass leaves the host-side bookkeeping (pending floats, cursors) ahead of the device state:
+// the batch is then unusable until mp3b_batch_reset, whatever the failing call was.
+int run_call(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, bool device_ptrs, int flush,
+             const uint8_t *flush_mask, bool download, size_t row_floats = 0, int elem_bytes = 4) {
+  if (b) b->planned = false;
+  const int rc = run_call_impl(b, pcm, n_floats, device_ptrs, flush, flush_mask, download, row_floats, elem_bytes);
+  if (rc != MP3B_OK && b && b->planned && !b->sticky) b->sticky = rc;
+  return rc;
 }
 
 int copy_out(const uint8_t *src, size_t len, uint8_t *out, size_t cap, size_t *written) {
@@ -702,6 +719,10 @@ int mp3b_session_xing_header(const mp3b_session *s, uint8_t *out, size_t cap, si
   if (!s) return fail(MP3B_ERR_BAD_ARG, "null session");
   return xing_header(s->b, 0, out, cap, written);
 }
+int mp3b_xing_frame_size(const mp3b_options *o) {                  // SRC:198-200
+  if (!o || o->sample_rate <= 0) return fail(MP3B_ERR_BAD_ARG, "null options or sample_rate <= 0");
+  return (int)(144LL * bitrate_value(bitrate_index(o->bitrate_kbps, o->sample_rate)) * 1000 / o->sample_rate);
+}
 uint32_t mp3b_session_frame_count(const mp3b_session *s) { return s ? s->b->frame_count[0] : 0; }
 uint32_t mp3b_session_byte_count(const mp3b_session *s) { return s ? s->b->byte_count[0] : 0; }
 
@@ -804,12 +825,14 @@ int mp3b_batch_clone(const mp3b_batch *src, mp3b_batch **out) {
   const size_t S = (size_t)src->S, fsc2 = 2 * (size_t)src->cfg.fsc, ch = (size_t)src->cfg.channels;
   cudaError_t e = cudaStreamSynchronize(src->st);
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-  A(cudaMemcpy(b->pb.state, src->pb.state, S * sizeof(StreamState), cudaMemcpyDeviceToDevice));
-  A(cudaMemcpy(b->d_head[0], src->d_head[0], S * fsc2 * sizeof(float), cudaMemcpyDeviceToDevice));
-  A(cudaMemcpy(b->d_head[1], src->d_head[1], S * fsc2 * sizeof(float), cudaMemcpyDeviceToDevice));
-  A(cudaMemcpy2D(b->pb.sub, (size_t)b->pb.sub_rows * 32 * sizeof(float), src->pb.sub, (size_t)src->pb.sub_rows * 32 * sizeof(float),
-                 576 * sizeof(float), S * ch, cudaMemcpyDeviceToDevice));
-  A(cudaMemcpy(b->pb.md_carry, src->pb.md_carry, S * kMdCarryCap, cudaMemcpyDeviceToDevice));
+  // on the clone's own stream (create_batch has already waited for its zero fills), finished before the handle is returned
+  A(cudaMemcpyAsync(b->pb.state, src->pb.state, S * sizeof(StreamState), cudaMemcpyDeviceToDevice, b->st));
+  A(cudaMemcpyAsync(b->d_head[0], src->d_head[0], S * fsc2 * sizeof(float), cudaMemcpyDeviceToDevice, b->st));
+  A(cudaMemcpyAsync(b->d_head[1], src->d_head[1], S * fsc2 * sizeof(float), cudaMemcpyDeviceToDevice, b->st));
+  A(cudaMemcpy2DAsync(b->pb.sub, (size_t)b->pb.sub_rows * 32 * sizeof(float), src->pb.sub, (size_t)src->pb.sub_rows * 32 * sizeof(float),
+                      576 * sizeof(float), S * ch, cudaMemcpyDeviceToDevice, b->st));
+  A(cudaMemcpyAsync(b->pb.md_carry, src->pb.md_carry, S * kMdCarryCap, cudaMemcpyDeviceToDevice, b->st));
+  A(cudaStreamSynchronize(b->st));
   if (e != cudaSuccess) { free_batch(b); return fail(MP3B_ERR_CUDA, "clone failed: %s", cudaGetErrorString(e)); }
   b->head_sel = src->head_sel;
   b->pending = src->pending; b->frame_count = src->frame_count; b->byte_count = src->byte_count; b->frame_sizes = src->frame_sizes;

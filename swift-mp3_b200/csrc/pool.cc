@@ -6,6 +6,13 @@
 // its request and either all open sessions are present or `max_wait_us` has elapsed since the first of them arrived.
 //
 // The worker thread owns the batch (and the CUDA work); client threads only copy their PCM in and their bytes out.
+//
+// Contract details: (1) a session that is open but not inside a call is indistinguishable from one that is about to call, so
+// every step then waits the full `max_wait_us` for it — close (flush) sessions that go idle, or pick max_wait_us as the
+// latency an idle peer may cost.  (2) A CUDA / engine-limit failure of a step is sticky for the batch (include/mp3b200.h):
+// every session then fails until all of them have been closed; the next mp3b_pool_open resets the batch (fresh sessions).
+// (3) mp3b_pool_destroy may be called while clients are blocked: they return MP3B_ERR_INTERNAL, and destroy waits for the
+// last of them to leave the pool before it frees anything.
 #include <chrono>
 #include <condition_variable>
 #include <cstring>
@@ -43,7 +50,10 @@ struct mp3b_pool {
   std::condition_variable cv_worker;
   std::thread worker;
   bool stop = false;
+  bool failed = false;       // a step left the batch in its sticky failed state
   int n_open = 0, n_pending = 0;
+  int in_flight = 0;         // client threads currently inside pool_call / take_output
+  std::condition_variable cv_idle;
   std::chrono::steady_clock::time_point first_pending;
   // statistics
   uint64_t steps = 0, requests = 0;
@@ -100,6 +110,7 @@ static void pool_worker(mp3b_pool *p) {
       s.cv.notify_one();
     }
     lk.lock();
+    if (rc == MP3B_ERR_CUDA || rc == MP3B_ERR_INTERNAL || rc == MP3B_ERR_OOM) p->failed = true;
     p->steps += 1; p->requests += p->members.size();
   }
 }
@@ -131,8 +142,12 @@ void mp3b_pool_destroy(mp3b_pool *p) {
   if (!p) return;
   { std::lock_guard<std::mutex> lk(p->mu); p->stop = true; }
   p->cv_worker.notify_all();
-  for (Slot *s : p->slots) { { std::lock_guard<std::mutex> g(s->m); s->done = true; s->rc = MP3B_ERR_INTERNAL; s->err = "pool destroyed"; } s->cv.notify_all(); }
-  if (p->worker.joinable()) p->worker.join();
+  if (p->worker.joinable()) p->worker.join();       // a step in progress completes and delivers; nothing new starts
+  for (Slot *s : p->slots) { { std::lock_guard<std::mutex> g(s->m); s->done = true; } s->cv.notify_all(); }
+  {                                                  // blocked clients wake, see `stop`, and leave without touching the pool again
+    std::unique_lock<std::mutex> lk(p->mu);
+    p->cv_idle.wait(lk, [&] { return p->in_flight == 0; });
+  }
   mp3b_batch_destroy(p->batch);
   mp3b_host_free(p->arena);
   delete p;
@@ -141,6 +156,11 @@ void mp3b_pool_destroy(mp3b_pool *p) {
 int mp3b_pool_open(mp3b_pool *p, int *slot) {
   if (!p || !slot) return MP3B_ERR_BAD_ARG;
   std::lock_guard<std::mutex> lk(p->mu);
+  if (p->stop) return MP3B_ERR_BAD_ARG;
+  if (p->failed && p->n_open == 0) {                // every session of the failed batch is closed: start over with fresh ones
+    if (mp3b_batch_reset(p->batch) != MP3B_OK) { t_pool_err = mp3b_last_error(); return MP3B_ERR_CUDA; }
+    p->failed = false;
+  }
   for (int i = 0; i < p->n; ++i)
     if (!p->slots[i]->open && !p->slots[i]->undelivered) { Slot &s = *p->slots[i]; s.pending = s.done = false; s.flush = s.rc = 0; s.n = 0; s.open = true; p->n_open += 1; *slot = i; return MP3B_OK; }
   return MP3B_ERR_BAD_ARG;                         // every session of the pool is in use
@@ -150,10 +170,13 @@ static int pool_call(mp3b_pool *p, int slot, const float *pcm, size_t n_floats, 
   if (written) *written = 0;
   if (!p || slot < 0 || slot >= p->n || (n_floats && !pcm)) return MP3B_ERR_BAD_ARG;
   Slot &s = *p->slots[slot];
+  // leaves the pool: the last thing a client does with `p` (mp3b_pool_destroy frees it once the count is zero)
+  auto leave = [p](int rc) { { std::lock_guard<std::mutex> lk(p->mu); p->in_flight -= 1; p->cv_idle.notify_all(); } return rc; };
   {
     std::unique_lock<std::mutex> lk(p->mu);
     if (s.undelivered) { t_pool_err = "output of the previous call is still pending: call mp3b_pool_take_output"; return MP3B_ERR_BAD_ARG; }
     if (!s.open || s.pending || p->stop) return MP3B_ERR_BAD_ARG;      // one call per session at a time (README:207)
+    p->in_flight += 1;
     s.n = n_floats;
     if (n_floats > p->row) s.big.assign(pcm, pcm + n_floats);
     else if (n_floats) memcpy(p->arena + (size_t)slot * p->row, pcm, n_floats * sizeof(float));
@@ -167,19 +190,24 @@ static int pool_call(mp3b_pool *p, int slot, const float *pcm, size_t n_floats, 
     s.cv.wait(g, [&] { return s.done; });
     s.done = false;
   }
-  if (flush) {                                                        // a flushed session no longer holds steps back
+  {
     std::lock_guard<std::mutex> lk(p->mu);
-    s.open = false; p->n_open -= 1; p->cv_worker.notify_one();
+    if (p->stop && s.pending) {                                       // woken by mp3b_pool_destroy, the request never ran
+      s.pending = false;
+      t_pool_err = "pool destroyed";
+      p->in_flight -= 1; p->cv_idle.notify_all();
+      return MP3B_ERR_INTERNAL;
+    }
+    if (flush) { s.open = false; p->n_open -= 1; p->cv_worker.notify_one(); }   // a flushed session no longer holds steps back
   }
-  if (s.rc) { t_pool_err = s.err; return s.rc; }
+  if (s.rc) { t_pool_err = s.err; return leave(s.rc); }
   if (written) *written = s.out.size();
   if (s.out.size() > cap || (!s.out.empty() && !out)) {               // nothing is lost: the bytes wait for mp3b_pool_take_output
-    std::lock_guard<std::mutex> lk(p->mu);
-    s.undelivered = true;
-    return MP3B_ERR_BUFFER_TOO_SMALL;
+    { std::lock_guard<std::mutex> lk(p->mu); s.undelivered = true; }
+    return leave(MP3B_ERR_BUFFER_TOO_SMALL);
   }
   if (!s.out.empty()) memcpy(out, s.out.data(), s.out.size());
-  return MP3B_OK;
+  return leave(MP3B_OK);
 }
 
 int mp3b_pool_encode(mp3b_pool *p, int slot, const float *pcm, size_t n_floats, uint8_t *out, size_t cap, size_t *written) {
