@@ -12,7 +12,12 @@ sharded by stream over the N GPUs (4096 / N streams each; at N = 1 the whole bat
   e2e   : the same step through the reference-facing call with HOST buffers (pinned): H2D of the PCM and D2H of the
           MP3 bytes inside the timed region, wall clock bracketed by synchronize + barrier, max over ranks.
   --impl reference : the CPU restatement of the reference (oracle/, the Swift original cannot be built here) on all
-          host cores, on a bounded sample of the same workload.
+          host cores, on a bounded sample of the same workload (the same synthetic streams, from the generator's CPU twin).
+  parity: EVERY stream of every rank's shard is compared byte for byte with the oracle (untimed; config.parity reads
+          "4096/4096"), the e2e leg's bytes with the device leg's.
+  other_configs: BASELINE configs 1, 2, 3 (single streams: session plane with host buffers, device plane, the oracle on one
+          core) and 5 (1024 sessions x 1152-sample chunks: p50 / p99 per call) ride in the default line; `--workload cN`
+          prints one of them as the line of its own.
 """
 import argparse
 import ctypes as C
@@ -89,71 +94,192 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "power_w": max(pw) if pw else None, "note": note}
 
 
-def cpu_reference(seconds_per_stream, min_wall=10.0, max_wall=40.0):
-    """The CPU restatement of the reference on every host core: bounded sample of the C4 workload."""
-    import numpy as np
+def c4_stream(i, seconds):
+    """Stream i of BASELINE config 4 from the CPU twin of the device generator (bit-identical to mp3b_synth_fill)."""
     import oracle_binding as orc
-    import signals
+    fl, fr, seed = stream_params(i)
+    return orc.synth_fill(int(round(seconds * SR)), CH, SR, fl, fr, 0.5, 0.05, seed)
+
+
+def cpu_reference(seconds_per_stream, min_wall=10.0, max_wall=40.0):
+    """The CPU restatement of the reference, built -O3 -march=native on this host (oracle/Makefile `native`), on every host
+    core and on one core: a bounded sample of the C4 workload (streams 0, 1, 2, ... of the same recipe the GPU arm encodes)."""
+    import oracle_binding as orc
     cores = os.cpu_count() or 1
     n = max(2 * cores, 8)
-    pcms = [signals.sine_noise(seconds_per_stream, sr=SR, f_left=stream_params(i)[0], f_right=stream_params(i)[1],
-                               seed=stream_params(i)[2]) for i in range(min(n, 16))]
-    pcms = [pcms[i % len(pcms)] for i in range(n)]
+    pcms = [c4_stream(i, seconds_per_stream) for i in range(n)]
     opts = dict(sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")
-    orc.encode_streams(pcms[:cores], cores, **opts)            # warm-up
+    _, d_native = orc.encode_streams(pcms[:cores], cores, native=True, **opts)            # warm-up
+    _, d_check = orc.encode_streams(pcms[:cores], cores, **opts)
+    assert d_native == d_check, "the -march=native build of the oracle disagrees with the checker build"
+    t1 = time.perf_counter(); k1 = 0
+    while time.perf_counter() - t1 < 3.0:                                                  # one session on one core
+        orc.encode_streams(pcms[k1 % n:k1 % n + 1], 1, native=True, **opts); k1 += 1
+    one_core = k1 * seconds_per_stream / (time.perf_counter() - t1)
     done, t0 = 0, time.perf_counter()
     while True:
-        orc.encode_streams(pcms, cores, **opts)
+        orc.encode_streams(pcms, cores, native=True, **opts)
         done += n
         el = time.perf_counter() - t0
         if el >= min_wall or el >= max_wall:
             break
     audio = done * seconds_per_stream
-    return {"value": audio / el, "unit": "x realtime (audio s / s)", "cores": cores, "kind": "port",
-            "sample": "%d streams x %.0f s of the C4 recipe (44.1 kHz stereo CBR128), one oracle session per stream, "
-                      "%d threads, %.1f s wall" % (done, seconds_per_stream, cores, el)}, el, audio
+    return {"value": audio / el, "unit": "x realtime (audio s / s)", "cores": cores, "kind": "port", "one_core": one_core,
+            "build": "gcc -O3 -march=native -ffp-contract=off (digest-equal to the -O2 x86-64-v3 checker build)",
+            "sample": "%d streams x %.0f s of the C4 recipe (44.1 kHz stereo CBR128; the GPU arm's streams 0..%d from the generator's "
+                      "CPU twin), one oracle session per stream, %d threads, %.1f s wall; one_core = one session at a time on one thread"
+                      % (done, seconds_per_stream, n - 1, cores, el)}, el, audio
 
 
-def bench_c5(a, mp3, L, local, rank, world):
-    """BASELINE config 5: 1024 concurrent sessions fed 1152-sample stereo chunks through encode(samples:) — one batch call
-    per chunk with pinned host buffers in, MP3 bytes out; p50 / p99 latency of a call (= of every frame in it)."""
+def check_all_streams(mp3, L, b, pcm, S, local):
+    """Untimed parity of a whole shard: every stream's bytes (the batch's downloaded output) against an oracle session fed the
+    same PCM (downloaded from the device in slices).  Returns (streams checked, list of (stream, first differing byte))."""
+    import oracle_binding as orc
+    bad = []
+    cores = os.cpu_count() or 1
+    for lo in range(0, S, 128):
+        hi = min(S, lo + 128)
+        host = pcm[lo:hi].cpu().numpy()
+        ep, en = [], []
+        for i in range(lo, hi):
+            p_, n_ = C.c_void_p(), C.c_size_t(0)
+            assert L.mp3b_batch_output(b._h, i, C.byref(p_), C.byref(n_)) == 0, L.mp3b_last_error()
+            ep.append(p_.value or host.ctypes.data); en.append(n_.value)
+        r = orc.compare_streams_raw([host[i].ctypes.data for i in range(hi - lo)], [host.shape[1]] * (hi - lo), ep, en, cores,
+                                    sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")
+        bad += [(lo + i, off) for i, off in r]
+    return S, bad
+
+
+def stream_digests(L, b, S):
+    import hashlib
+    out = []
+    for i in range(S):
+        p_, n_ = C.c_void_p(), C.c_size_t(0)
+        assert L.mp3b_batch_output(b._h, i, C.byref(p_), C.byref(n_)) == 0
+        out.append(hashlib.blake2b(C.string_at(p_.value, n_.value) if n_.value else b"", digest_size=16).digest())
+    return out
+
+
+def single_stream_config(name, mp3, L, local, repeats=5):
+    """BASELINE configs 1-3: ONE stream ("replicas only": no sharding).  Session plane with host buffers (the reference-facing
+    call: encode(samples:) of the whole stream + flush()), device plane (PCM in HBM), and the oracle on one core."""
     import numpy as np
     import torch
-    S, steps = 1024, max(a.steps, 200)
+    import oracle_binding as orc
+    import signals
+    if name == "c1":
+        pcm, o, label = orc.synth_fill(10 * 44100, 2, 44100, 440.0, 554.37, 0.5, 0.05, 1234), dict(sample_rate=44100, bitrate_kbps=128, mode="stereo"), \
+            "C1: 44.1 kHz stereo CBR 128, 10 s sine + noise, single stream"
+    elif name == "c2":
+        pcm, o, label = signals.white(60.0), dict(sample_rate=48000, bitrate_kbps=320, mode="mono"), "C2: 48 kHz mono CBR 320, 60 s white noise, single stream"
+    elif name == "c2pink":
+        pcm, o, label = signals.pink(60.0), dict(sample_rate=48000, bitrate_kbps=320, mode="mono"), "C2: 48 kHz mono CBR 320, 60 s pink noise, single stream"
+    else:
+        pcm, o, label = signals.castanets(30.0), dict(sample_rate=44100, bitrate_kbps=128, mode="jointStereo", vbr=True, quality=2), \
+            "C3: 44.1 kHz joint-stereo VBR q2, 30 s castanet-like transients, single stream"
+    ch = 1 if o["mode"] == "mono" else 2
+    seconds = pcm.size / ch / o["sample_rate"]
+    mo = mp3.MP3EncoderOptions(sampleRate=o["sample_rate"], bitrateKbps=o["bitrate_kbps"], vbr=o.get("vbr", False),
+                               mode={"mono": 0, "stereo": 1, "jointStereo": 2}[o["mode"]], quality=o.get("quality", 5))
+    ref, rs = orc.encode_all(pcm, **o)
+    # session plane, host buffers
+    ts = []
+    for _ in range(repeats + 2):
+        s = mp3.EncoderSession(mo, local)
+        t0 = time.perf_counter()
+        out = s.encode(pcm) + s.flush()
+        ts.append(time.perf_counter() - t0)
+        s.close()
+        assert out == ref, name + ": session output differs from the oracle"
+    t_sess = sorted(ts[2:])[len(ts[2:]) // 2]
+    # device plane
+    dev = torch.from_numpy(pcm).cuda()
+    b = mp3.EncoderBatch(mo, 1, local)
+    ptrs, ns = (C.c_void_p * 1)(dev.data_ptr()), (C.c_size_t * 1)(pcm.size)
+    td = []
+    for _ in range(repeats + 2):
+        b.reset()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        b.encode_device(ptrs, ns, flush=True, download=True)
+        td.append(time.perf_counter() - t0)
+    assert b.output(0) == ref, name + ": device-plane output differs from the oracle"
+    t_dev = sorted(td[2:])[len(td[2:]) // 2]
+    launches, passes = b.launch_count, b.pass_count
+    b.close()
+    # the oracle on one core (native build)
+    t0 = time.perf_counter(); k = 0
+    while time.perf_counter() - t0 < 2.0:
+        orc.encode_streams([pcm], 1, native=True, **o); k += 1
+    t_cpu = (time.perf_counter() - t0) / k
+    gc = rs.frame_count * 2 * ch
+    return {"workload": label, "audio_seconds": seconds, "frames": int(rs.frame_count), "granule_channels": int(gc),
+            "value": seconds / t_dev, "unit": "x realtime", "ms_device_plane": 1e3 * t_dev,
+            "e2e": {"value": seconds / t_sess, "unit": "x realtime", "ms": 1e3 * t_sess, "h2d_bytes": int(pcm.nbytes), "d2h_bytes": len(ref),
+                    "call": "mp3b_session_encode(whole stream) + mp3b_session_flush, host buffers"},
+            "cpu_one_core": {"value": seconds / t_cpu, "unit": "x realtime", "ms": 1e3 * t_cpu, "kind": "port", "cores": 1},
+            "gpu_launches": int(launches), "passes": int(passes), "scaling": "replicas only (one stream)",
+            "parity": "byte-identical to the oracle (session plane and device plane)"}
+
+
+def bench_c5(steps, mp3, L, local):
+    """BASELINE config 5: 1024 concurrent sessions (C4 streams 0...1023) fed 1152-sample stereo chunks through
+    encode(samples:) — one mp3b_batch_encode_strided call per chunk with a pinned host arena in, MP3 bytes out; p50 / p99
+    latency of a call (= of every frame in it).  EVERY session's bytes are compared with an oracle session fed the same chunks."""
+    import numpy as np
+    import torch
+    import oracle_binding as orc
+    S, steps = 1024, max(steps, 200)
     chunk = 1152 * CH
     opts = mp3.MP3EncoderOptions(sampleRate=SR, bitrateKbps=KBPS, mode=mp3.Mode.stereo)
     b = mp3.EncoderBatch(opts, S, local, 8)
     n_chunks = 64                                                   # distinct chunks per stream, cycled
-    hp = C.c_void_p()
-    assert L.mp3b_host_alloc(S * n_chunks * chunk * 4, C.byref(hp)) == 0, L.mp3b_last_error()
     pcm = torch.empty((S, n_chunks * chunk), dtype=torch.float32, device="cuda")
     for i in range(S):
         fl, fr, seed = stream_params(i)
         assert L.mp3b_synth_fill(local, pcm[i].data_ptr(), n_chunks * 1152, CH, SR, fl, fr, 0.5, 0.05, seed) == 0
-    assert L.mp3b_device_copy(local, hp, pcm.data_ptr(), S * n_chunks * chunk * 4, 1) == 0
+    host = pcm.cpu().numpy()
+    hp = C.c_void_p()
+    assert L.mp3b_host_alloc(S * chunk * 4, C.byref(hp)) == 0, L.mp3b_last_error()
+    arena = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_float)), shape=(S, chunk))
     ns = (C.c_size_t * S)(*([chunk] * S))
-    lat = []
-    for k in range(steps + 20):
-        ptrs = (C.c_void_p * S)(*[hp.value + (i * n_chunks + k % n_chunks) * chunk * 4 for i in range(S)])
+    lat, got = [], [bytearray() for _ in range(S)]
+    total = steps + 20
+    for k in range(total):
+        arena[:] = host[:, (k % n_chunks) * chunk:(k % n_chunks + 1) * chunk]     # the caller's side: chunks arrive in its own buffers
         t0 = time.perf_counter()
-        b.encode_ptrs(ptrs, ns, flush=False)
+        b.encode_strided(hp.value, chunk, ns, flush=False)
         lat.append(time.perf_counter() - t0)
+        for i in range(S):
+            got[i] += b.output(i)
+    stage, launches = b.stage_ms(), b.launch_count
     lat = np.array(lat[20:]) * 1e3
-    if rank == 0:
-        import oracle_binding as orc
-        host = pcm[3].cpu().numpy()
-        rs = orc.Session(sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")
-        ref = b"".join(rs.encode(host[(k % n_chunks) * chunk:(k % n_chunks + 1) * chunk]) for k in range(steps + 20))
-        assert b.byte_count(3) == len(ref) and b.output(3) == ref[-len(b.output(3)):], "streaming output differs from the oracle"
-        p50, p99 = float(np.percentile(lat, 50)), float(np.percentile(lat, 99))
-        emit({"metric": "per-frame latency, 1024 concurrent sessions (config 5)", "value": p50, "unit": "ms (p50)",
-                          "p99_ms": p99, "mean_ms": float(lat.mean()), "n_gpus": 1, "steps": steps, "higher_is_better": False,
-                          "frame_period_ms": 1152 / SR * 1e3, "realtime_factor_p50": S * 1152 / SR * 1e3 / p50,
-                          "data": "synthetic", "config": {"workload": "C5: 1024 sessions x 1152-sample stereo chunks, host buffers in, bytes out"},
-                          "stage_ms_last_call": b.stage_ms(), "gpu_launches_per_call": b.launch_count,
-                          "parity": "session 3 byte-identical to the oracle over %d chunks" % (steps + 20)})
+    # parity: all sessions; the oracle is fed the same chunk sequence (the 64 chunks cycled)
+    reps = -(-total // n_chunks)
+    seq = [np.ascontiguousarray(np.tile(host[i], reps)[: total * chunk]) for i in range(S)]
+    refs = [bytes(g) for g in got]
+    cores = os.cpu_count() or 1
+    # no flush was issued: compare against encode() only by appending the oracle's flush-free prefix -> use sessions directly
+    bad = 0
+    ep = [np.frombuffer(r, np.uint8) if r else np.zeros(1, np.uint8) for r in refs]
+    diff = orc.compare_streams_raw([x.ctypes.data for x in seq], [x.size for x in seq], [e.ctypes.data for e in ep], [len(r) for r in refs],
+                                   cores, chunk_floats=chunk, sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")
+    # the oracle driver flushes at the end (one more frame than the un-flushed batch emitted): a session is identical when the
+    # first difference is exactly at the end of the batch's bytes
+    bad = [(i, off) for i, off in diff if off != len(refs[i])]
+    assert not bad, "streaming output differs from the oracle: %r" % bad[:4]
+    assert len(diff) == S, "the oracle's flush frame is missing for some sessions"
+    p50, p99 = float(np.percentile(lat, 50)), float(np.percentile(lat, 99))
+    res = {"workload": "C5: 1024 sessions x 1152-sample stereo chunks, host arena in (mp3b_batch_encode_strided), bytes out",
+           "metric": "per-frame latency, 1024 concurrent sessions (config 5)", "value": p50, "unit": "ms (p50)",
+           "p99_ms": p99, "mean_ms": float(lat.mean()), "steps": steps, "higher_is_better": False,
+           "frame_period_ms": 1152 / SR * 1e3, "realtime_factor_p50": S * 1152 / SR * 1e3 / p50,
+           "stage_ms_last_call": stage, "gpu_launches_per_call": launches,
+           "parity": "%d/%d sessions byte-identical to the oracle over %d chunks" % (S, S, total)}
     L.mp3b_host_free(hp)
-    return 0
+    b.close()
+    return res
 
 
 _REAL_STDOUT = None
@@ -191,8 +317,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--i16", action="store_true", help="also time the 16-bit-input extension end to end (reported as e2e_i16, not the headline)")
-    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
-                    help="c4 (default, the headline): batch of 30 s streams; c5: streaming latency, 1024 sessions x 1152-sample chunks")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c1", "c2", "c3", "c5"],
+                    help="c4 (default, the headline): batch of 30 s streams; c1 / c2 / c3: the single-stream configs; "
+                         "c5: streaming latency, 1024 sessions x 1152-sample chunks")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_configs legs (C1, C2, C3, C5) of the default line")
+    ap.add_argument("--parity", default="all", choices=["all", "spot"], help="all (default): every stream of the shard against "
+                    "the oracle; spot: two streams (profiling runs)")
     a = ap.parse_args()
     quiet_stdout()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,8 +341,8 @@ def main():
         line = {"impl": "reference", "metric": metric, "value": res["value"], "unit": "x realtime", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * el / max(a.steps, 1), "higher_is_better": True,
                 "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "reference": "C restatement of SwiftMP3 (oracle/); the Swift + Accelerate "
-                           "original cannot be built on Linux"},
+                "config": {"workload": workload, "reference": "C restatement of SwiftMP3 (oracle/, built -O3 -march=native on this host); "
+                           "the Swift + Accelerate original cannot be built on Linux", "one_core_x_realtime": res["one_core"]},
                 "cpu_baseline": res,
                 "e2e": {"value": res["value"], "unit": "x realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
@@ -227,7 +357,9 @@ def main():
     sampler = ClockSampler(local); sampler.start()
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("MP3B_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL's log (rank / topology lines the driver checks) goes to stderr: file descriptor 1 points there while the bench
+        # runs (quiet_stdout), so stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("MP3B_NCCL_DEBUG", "INFO"))
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -243,10 +375,24 @@ def main():
     def sum_over_ranks(v):
         return sharding.sum_over_ranks(v, dist, "cuda")
 
-    if a.workload == "c5":
-        rc = bench_c5(a, mp3, L, local, rank, world)
+    if a.workload != "c4":                                          # single-GPU configs: rank 0 runs them, "replicas only"
+        if rank == 0:
+            if a.workload == "c5":
+                res = bench_c5(a.steps, mp3, L, local)
+            else:
+                res = single_stream_config(a.workload, mp3, L, local)
+                if a.workload == "c2":
+                    res["pink"] = single_stream_config("c2pink", mp3, L, local)
+            line = dict(res)
+            line.setdefault("metric", metric)
+            line.update({"n_gpus": 1, "warmup": a.warmup, "dtype": "f32", "data": "synthetic", "vs_baseline": None,
+                         "config": {"workload": res["workload"]}})
+            line.setdefault("steps", a.steps); line.setdefault("higher_is_better", True)
+            emit(line)
         sampler.stop()
-        return rc
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return 0
     S = a.streams                                                  # streams of this rank
     shard_lo, shard_hi = sharding.shard_range(S * world, rank, world)
     assert shard_hi - shard_lo == S
@@ -262,21 +408,34 @@ def main():
     ns = (C.c_size_t * S)(*([n_floats] * S))
     opts = mp3.MP3EncoderOptions(sampleRate=SR, bitrateKbps=KBPS, mode=mp3.Mode.stereo)
     b = mp3.EncoderBatch(opts, S, local)
+    frames_per_pass = b.frames_per_pass
     ext = torch.cuda.ExternalStream(b.cuda_stream, device=torch.device("cuda", local))
     audio_per_step = S * a.seconds
 
-    # ---- parity spot check (untimed): two streams of this shard against the CPU oracle
-    parity = None
-    if rank == 0:
-        import oracle_binding as orc
-        b.reset()
-        b.encode_device(dptrs, ns, flush=True, download=True)
-        checked = 0
+    # ---- parity (untimed): EVERY stream of this rank's shard against the CPU oracle, on every rank; the inputs are the CPU
+    # twin's bit for bit, so the reference arm encodes the same streams
+    import oracle_binding as orc
+    b.reset()
+    b.encode_device(dptrs, ns, flush=True, download=True)
+    t_par = time.perf_counter()
+    if a.parity == "all":
+        checked, bad = check_all_streams(mp3, L, b, pcm, S, local)
+    else:
+        checked, bad = 0, []
         for i in (0, S - 1):
             ref, _ = orc.encode_all(pcm[i].cpu().numpy(), sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")
-            assert b.output(i) == ref, "stream %d differs from the oracle" % i
             checked += 1
-        parity = "%d streams bit-identical to the oracle" % checked
+            if b.output(i) != ref:
+                bad.append((i, -1))
+    t_par = time.perf_counter() - t_par
+    for i in (0, S // 2, S - 1):
+        twin = c4_stream(shard_lo + i, a.seconds)
+        assert np.array_equal(pcm[i].cpu().numpy().view("<u4"), twin.view("<u4")), "device PCM differs from the CPU twin (stream %d)" % (shard_lo + i)
+    assert not bad, "rank %d: %d stream(s) differ from the oracle, first %r" % (rank, len(bad), bad[:4])
+    device_digests = stream_digests(L, b, S)
+    checked_total = int(sum_over_ranks(checked))
+    parity = "%d/%d streams byte-identical to the oracle (every rank checks its own shard; %.0f s on rank 0); inputs bit-identical " \
+             "to the generator's CPU twin" % (checked_total, S * world, t_par)
 
     # ---- value: device plane, K steps
     def step_device():
@@ -319,15 +478,20 @@ def main():
     algo = dict(ALGO_BYTES, pack=2304 + out_per_gc, frames=2 * out_per_gc + 30)
     fp32_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) / 1000.0) / 1000.0   # nominal TFLOP/s, non-tensor FP32
     flops = {"filterbank": FLOP_FILTERBANK, "granule": FLOP_GRANULE}
-    ncu = {}
-    try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")))
-    except Exception:
-        pass
+    ncu, ncu_file = {}, None
+    for name in ("r02_kernel_traffic.json", "r01_kernel_traffic.json"):       # the newest committed ncu --set full summary
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", name)))
+            ncu_file = name
+            break
+        except Exception:
+            pass
     stage_table = {}
     fused_prepass = stages["prepass"] / max(passes, 1) < 0.02     # CBR without joint stereo: k_prepass is not launched at all
     if fused_prepass:
         algo["granule"] += 2304                                   # k_granule then reads the granule's PCM itself (block-type decision)
+    sm_clock_hz = peaks.get("sm_max_mhz", 1965.0) * 1e6
+    issue_peak = 148 * 4 * sm_clock_hz / 1e9                      # G warp-instructions / s: one per scheduler per cycle
     for k in algo:
         if k == "prepass" and fused_prepass:
             stage_table[k] = {"ms_per_step": 0.0, "share": 0.0, "skipped": "CBR without joint stereo: the block types are decided inside k_granule, "
@@ -341,25 +505,41 @@ def main():
             row["fp32_frac_of_nominal"] = row["fp32_TFLOPs"] / fp32_peak
         if k in ncu:
             row["ncu"] = ncu[k]
+            if ncu[k].get("inst_executed_per_gc"):
+                row["issue_Ginst_per_s"] = gc_per_step * ncu[k]["inst_executed_per_gc"] / sec / 1e9
+                row["issue_frac"] = row["issue_Ginst_per_s"] / issue_peak
         stage_table[k] = row
     dom = max(algo, key=lambda k: stages[k])
     dom_ms_per_launch = stages[dom] / max(passes, 1)
-    achieved = gc_per_launch * algo[dom] / (dom_ms_per_launch / 1000.0) / 1e9
+    dom_s = dom_ms_per_launch / 1000.0
+    hbm_achieved = gc_per_launch * algo[dom] / dom_s / 1e9
     traffic = ncu[dom]["dram_bytes_per_gc"] * gc_per_launch if dom in ncu and "dram_bytes_per_gc" in ncu[dom] else None
-    roofline = {"kernel": KERNEL_OF[dom], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": which, "ms_per_launch": dom_ms_per_launch,
-                "gc_per_launch": gc_per_launch, "share_of_step": stages[dom] / max(stages["total"], 1e-9),
-                "limiter": ("FP32 FMA pipe and shared-memory wavefronts, not HBM: the reference's direct-form 32x64 matrixing is kept "
-                            "operation for operation (bit-exact parity); see fp32 and DESIGN.md section 4") if dom == "filterbank" else
-                           "instruction issue (MDCT with immediate coefficients, FP64 |x|^0.75, integer bit counting); see DESIGN.md section 4",
-                "stages": stage_table, "stage_ms_per_step": {k: v / a.steps for k, v in stages.items()}}
-    if dom in flops:
-        ach = gc_per_launch * flops[dom] / (dom_ms_per_launch / 1000.0) / 1e12
-        roofline["fp32"] = {"achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
-                            "peak_source": "nominal 148 SM x 128 lanes x 2 x sm_max_mhz (no measured FP32 peak in MEASURED_PEAKS.json)",
-                            "peak_measured": FP32_MEASURED_FRACTION * fp32_peak, "frac_of_measured": ach / (FP32_MEASURED_FRACTION * fp32_peak),
-                            "peak_measured_source": "tools/microbench/mb.cu kernel C on a B200 of this pool: register-only FFMA2 stream "
-                                                    "reaches 90.5-91.0 % of the nominal issue rate"}
+    # The bound is the limiter ncu shows for the kernel, not an assumption: k_filterbank is bound by the FP32 FMA pipe (direct-form
+    # matrixing kept operation for operation), k_granule by instruction issue (MDCT immediates + FP64 |x|^0.75 + integer bit
+    # counting), the small kernels by latency.  The HBM view (algorithmic bytes / time vs the measured copy bandwidth) rides along.
+    hbm_view = {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak, "traffic": traffic,
+                "peak_source": which, "algo_bytes_per_gc": algo[dom]}
+    if dom in flops and (dom == "filterbank" or not (dom in ncu and ncu[dom].get("inst_executed_per_gc"))):
+        ach = gc_per_launch * flops[dom] / dom_s / 1e12
+        roofline = {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+                    "peak_source": "nominal non-tensor FP32: 148 SM x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json holds no FP32 figure)",
+                    "peak_measured": FP32_MEASURED_FRACTION * fp32_peak, "frac_of_measured": ach / (FP32_MEASURED_FRACTION * fp32_peak),
+                    "peak_measured_source": "tools/microbench/mb.cu kernel C on a B200 of this pool (profiles/r02_microbench.txt): a register-only "
+                                            "FFMA2 stream reaches 90.5-91.0 % of the nominal issue rate",
+                    "flop_per_gc": flops[dom]}
+    elif dom in ncu and ncu[dom].get("inst_executed_per_gc"):
+        ach = gc_per_launch * ncu[dom]["inst_executed_per_gc"] / dom_s / 1e9
+        roofline = {"bound": "issue", "achieved": ach, "peak": issue_peak, "unit": "Ginst/s (warp instructions)", "frac": ach / issue_peak,
+                    "peak_source": "148 SM x 4 schedulers x 1 warp instruction per cycle x sm_max_mhz",
+                    "inst_per_gc": ncu[dom]["inst_executed_per_gc"], "inst_source": "smsp__inst_executed.sum, profiles/" + ncu_file}
+    else:
+        roofline = dict(hbm_view, bound="hbm")
+    roofline.update({"kernel": KERNEL_OF[dom], "traffic": traffic, "hbm": hbm_view, "ms_per_launch": dom_ms_per_launch,
+                     "gc_per_launch": gc_per_launch, "share_of_step": stages[dom] / max(stages["total"], 1e-9),
+                     "limiter": ("FP32 FMA pipe and shared-memory wavefronts, not HBM: the reference's direct-form 32x64 matrixing is kept "
+                                 "operation for operation (bit-exact parity); see DESIGN.md section 4") if dom == "filterbank" else
+                                "instruction issue (MDCT with immediate coefficients, FP64 |x|^0.75, integer bit counting); see DESIGN.md section 4",
+                     "stages": stage_table, "stage_ms_per_step": {k: v / a.steps for k, v in stages.items()}})
 
     # ---- e2e: host plane (pinned PCM in, MP3 bytes out), wall clock
     e2e_steps = a.e2e_steps or min(a.steps, 5)
@@ -388,10 +568,8 @@ def main():
     e2e = {"value": world * audio_per_step / e2e_s, "unit": "x realtime", "h2d_bytes_per_step": S * n_floats * 4,
            "d2h_bytes_per_step": int(b.output_total), "ms_per_step": 1000.0 * e2e_s, "steps": e2e_steps,
            "stage_ms_last_step": e2e_stage}
-    if rank == 0:
-        import oracle_binding as orc
-        ref, _ = orc.encode_all(pcm[1].cpu().numpy(), sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")
-        assert b.output(1) == ref, "e2e output differs from the oracle"
+    assert stream_digests(L, b, S) == device_digests, "e2e output differs from the (oracle-checked) device-plane output"
+    e2e["parity"] = "all %d streams of every rank equal to the device-plane bytes checked against the oracle" % S
     L.mp3b_host_free(hp)
 
     # ---- optional: the same end-to-end step from 16-bit PCM (mp3b_batch_encode_i16: half the PCIe bytes); an extension of
@@ -419,7 +597,6 @@ def main():
                    "d2h_bytes_per_step": int(b.output_total), "ms_per_step": 1000.0 * s16, "steps": e2e_steps,
                    "note": "extension: int16 PCM in, widened on the device to Float(s) / 32768"}
         if rank == 0:
-            import oracle_binding as orc
             f = (pcm16[1].cpu().numpy().astype(np.float32) / np.float32(32768.0))
             ref, _ = orc.encode_all(f, sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")
             assert b.output(1) == ref, "int16 e2e output differs from the oracle"
@@ -429,16 +606,25 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
         cpu, _, _ = cpu_reference(a.seconds, min_wall=10.0, max_wall=30.0)
+    others = None
+    if rank == 0 and world == 1 and not a.no_others:
+        b.close(); del pcm                                          # the big batch's memory is not needed any more
+        torch.cuda.empty_cache()
+        others = {"c1": single_stream_config("c1", mp3, L, local), "c2": single_stream_config("c2", mp3, L, local),
+                  "c3": single_stream_config("c3", mp3, L, local), "c5": bench_c5(200, mp3, L, local)}
+        others["c2"]["pink"] = single_stream_config("c2pink", mp3, L, local, repeats=3)
     total_launches = int(sum_over_ranks(launches))
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": "x realtime", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {"workload": workload, "streams_per_gpu": S, "seconds_per_stream": a.seconds,
-                                                "frames_per_pass": b.frames_per_pass, "l2": "inputs larger than L2",
+                                                "frames_per_pass": frames_per_pass, "l2": "inputs larger than L2",
                                                 "parity": parity, "output_bytes_per_step_per_gpu": int(out_bytes), "host_numa": numa},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": total_launches, "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if others is not None:
+            line["other_configs"] = others
         if e2e_i16 is not None:
             line["e2e_i16"] = e2e_i16
         emit(line)

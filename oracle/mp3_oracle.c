@@ -757,10 +757,69 @@ uint8_t *orc_id3_build(const orc_id3 *tag, size_t *out_len) {      /* SRC:1040-1
 void orc_free(void *p) { free(p); }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Synthetic PCM, CPU twin of the product's mp3b_synth_fill (swift-mp3_b200/csrc/kernels.cu, k_synth): the BASELINE C1/C4
+ * recipe a*sin(2 pi f t) + noise*N(0,1) from a counter-based generator, every step an IEEE-754 double operation with
+ * one rounding (built with -ffp-contract=off; fma() is the fused operation), so both sides produce the same floats.    */
+static uint64_t sm64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+static double synth_ln(uint64_t k) {                                 /* ln(k / 2^53), 1 <= k <= 2^53 */
+  int e = 63 - __builtin_clzll(k);
+  double m = ldexp((double)k, -e);                                   /* exact, [1, 2) */
+  if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+  const double s = (m - 1.0) / (m + 1.0), z = s * s;
+  static const double odd[11] = {1.0, 1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0, 1.0 / 17.0, 1.0 / 19.0, 1.0 / 21.0};
+  double p = odd[10];
+  for (int i = 9; i >= 0; --i) p = fma(p, z, odd[i]);
+  return fma((double)(e - 53), 0.6931471805599453, (2.0 * s) * p);
+}
+static void synth_sincos(double t, double *sn, double *cs) {         /* (sin, cos)(2 pi t), 0 <= t < 1 */
+  static const double fs[12] = {1.0, -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -1.0 / 39916800.0, 1.0 / 6227020800.0,
+                                -1.0 / 1307674368000.0, 1.0 / 355687428096000.0, -1.0 / 121645100408832000.0,
+                                1.0 / 51090942171709440000.0, -1.0 / 25852016738884976640000.0};
+  static const double fc[13] = {1.0, -0.5, 1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0,
+                                -1.0 / 87178291200.0, 1.0 / 20922789888000.0, -1.0 / 6402373705728000.0,
+                                1.0 / 2432902008176640000.0, -1.0 / 1124000727777607680000.0, 1.0 / 620448401733239439360000.0};
+  const double q4 = floor(t * 4.0);
+  const double x = 6.283185307179586 * (t - q4 * 0.25), z = x * x;
+  double ps = fs[11], pc = fc[12];
+  for (int i = 10; i >= 0; --i) ps = fma(ps, z, fs[i]);
+  for (int i = 11; i >= 0; --i) pc = fma(pc, z, fc[i]);
+  const double s0 = x * ps;
+  switch ((int)q4) {
+    case 0: *sn = s0; *cs = pc; break;
+    case 1: *sn = pc; *cs = -s0; break;
+    case 2: *sn = -s0; *cs = -pc; break;
+    default: *sn = -pc; *cs = s0; break;
+  }
+}
+void orc_synth_fill(float *pcm, size_t n_per_channel, int channels, int sample_rate, float f_left, float f_right,
+                    float amp, float noise, uint64_t seed) {
+  for (size_t i = 0; i < n_per_channel; ++i) {
+    const uint64_t h1 = sm64(seed * 0x100000001B3ull + i), h2 = sm64(h1);
+    const double rad = sqrt(-2.0 * synth_ln((h1 >> 11) + 1));
+    double g[2];                                                     /* g[0] = cos part (left), g[1] = sin part (right) */
+    synth_sincos((double)(h2 >> 11) * 1.1102230246251565e-16, &g[1], &g[0]);
+    for (int c = 0; c < channels; ++c) {
+      const double cyc = ((double)(c == 0 ? f_left : f_right) * (double)i) / (double)sample_rate;
+      double t = cyc - floor(cyc);
+      if (c == 1) { t = t + 0.0477464829275686; if (t >= 1.0) t = t - 1.0; }
+      double sn, cs;
+      synth_sincos(t, &sn, &cs);
+      const double v = (double)amp * sn + (double)noise * (rad * g[c]);
+      float f = (float)v;
+      pcm[i * (size_t)channels + c] = f < -1.0f ? -1.0f : f > 1.0f ? 1.0f : f;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* multi-threaded CPU-baseline driver                                                               */
 typedef struct {
   const orc_options *opts; const float *const *pcm; const size_t *n_floats; size_t n_streams;
   size_t next; pthread_mutex_t mu; size_t bytes; uint64_t digest;
+  const uint8_t *const *expect; const size_t *expect_len; int64_t *first_diff; size_t chunk_floats;   /* compare mode */
 } job_t;
 static uint64_t fnv1a(const uint8_t *p, size_t n, uint64_t h) { for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; } return h; }
 static void *worker(void *arg) {
@@ -769,22 +828,53 @@ static void *worker(void *arg) {
     pthread_mutex_lock(&j->mu); size_t i = j->next++; pthread_mutex_unlock(&j->mu);
     if (i >= j->n_streams) break;
     orc_session *s = orc_create(j->opts);
-    size_t n1, n2; uint64_t h = 1469598103934665603ull;
-    const uint8_t *p = orc_encode(s, j->pcm[i], j->n_floats[i], &n1); h = fnv1a(p, n1, h);
-    p = orc_flush(s, &n2); h = fnv1a(p, n2, h);
+    size_t n1 = 0, n2; uint64_t h = 1469598103934665603ull;
+    int64_t diff = -1;                       /* compare mode: offset of the first byte that differs from expect[i], -1 = identical */
+    const uint8_t *ex = j->expect ? j->expect[i] : NULL; const size_t exn = j->expect ? j->expect_len[i] : 0;
+    /* one encode(samples:) call, or — chunk_floats > 0 — the stream fed chunk by chunk like a streaming client (SRC:297-310) */
+    const size_t total = j->n_floats[i], step = j->chunk_floats ? j->chunk_floats : (total ? total : 1);
+    for (size_t off = 0; off < total || off == 0; off += step) {
+      size_t nn; const size_t take = total - off < step ? total - off : step;
+      const uint8_t *p = orc_encode(s, j->pcm[i] + off, take, &nn); h = fnv1a(p, nn, h);
+      if (j->expect && diff < 0) for (size_t k = 0; k < nn; ++k) if (n1 + k >= exn || ex[n1 + k] != p[k]) { diff = (int64_t)(n1 + k); break; }
+      n1 += nn;
+      if (total == 0) break;
+    }
+    const uint8_t *p = orc_flush(s, &n2); h = fnv1a(p, n2, h);
+    if (j->expect && diff < 0) for (size_t k = 0; k < n2; ++k) if (n1 + k >= exn || ex[n1 + k] != p[k]) { diff = (int64_t)(n1 + k); break; }
+    if (j->expect && diff < 0 && n1 + n2 != exn) diff = (int64_t)(n1 + n2);
+    if (j->first_diff) j->first_diff[i] = diff;
     orc_destroy(s);
     pthread_mutex_lock(&j->mu); j->bytes += n1 + n2; j->digest += h * (2 * (uint64_t)i + 1); pthread_mutex_unlock(&j->mu);
   }
   return NULL;
 }
-size_t orc_encode_streams(const orc_options *opts, const float *const *pcm, const size_t *n_floats, size_t n_streams,
-                          int n_threads, uint64_t *out_digest) {
-  job_t j = {opts, pcm, n_floats, n_streams, 0, PTHREAD_MUTEX_INITIALIZER, 0, 0};
+static void run_job(job_t *j, int n_threads) {
   if (n_threads < 1) n_threads = 1;
   pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * n_threads);
-  for (int t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, worker, &j);
+  for (int t = 0; t < n_threads; ++t) pthread_create(&th[t], NULL, worker, j);
   for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
   free(th);
+}
+size_t orc_encode_streams(const orc_options *opts, const float *const *pcm, const size_t *n_floats, size_t n_streams,
+                          int n_threads, uint64_t *out_digest) {
+  job_t j = {opts, pcm, n_floats, n_streams, 0, PTHREAD_MUTEX_INITIALIZER, 0, 0, NULL, NULL, NULL, 0};
+  run_job(&j, n_threads);
   if (out_digest) *out_digest = j.digest;
   return j.bytes;
+}
+
+/* Parity driver: encodes every stream (encode + flush, or chunk_floats at a time) and compares the bytes with
+ * expect[i][0 .. expect_len[i]) — the output of the implementation under test.  first_diff[i] = -1 when identical, else the
+ * offset of the first differing byte (or the shorter length).  Returns the number of streams that differ. */
+size_t orc_compare_streams(const orc_options *opts, const float *const *pcm, const size_t *n_floats, size_t n_streams,
+                           size_t chunk_floats, int n_threads, const uint8_t *const *expect, const size_t *expect_len,
+                           int64_t *first_diff) {
+  int64_t *fd = first_diff ? first_diff : (int64_t *)malloc(sizeof(int64_t) * (n_streams ? n_streams : 1));
+  job_t j = {opts, pcm, n_floats, n_streams, 0, PTHREAD_MUTEX_INITIALIZER, 0, 0, expect, expect_len, fd, chunk_floats};
+  run_job(&j, n_threads);
+  size_t bad = 0;
+  for (size_t i = 0; i < n_streams; ++i) bad += fd[i] >= 0;
+  if (!first_diff) free(fd);
+  return bad;
 }

@@ -105,6 +105,18 @@ int   orc_bitrate_value(int index);                    /* SRC:2526-2530 */
 size_t orc_encode_streams(const orc_options *opts, const float *const *pcm, const size_t *n_floats,
                           size_t n_streams, int n_threads, uint64_t *out_digest);
 
+/* Parity driver: like orc_encode_streams, but every stream's bytes are compared with expect[i][0 .. expect_len[i]) (the
+ * output of the implementation under test); chunk_floats > 0 feeds the stream in chunks of that many floats.
+ * first_diff[i] (optional) = -1 when identical, else the offset of the first differing byte.  Returns the number of
+ * streams that differ. */
+size_t orc_compare_streams(const orc_options *opts, const float *const *pcm, const size_t *n_floats, size_t n_streams,
+                           size_t chunk_floats, int n_threads, const uint8_t *const *expect, const size_t *expect_len,
+                           int64_t *first_diff);
+
+/* CPU twin of the product's synthetic-PCM generator (mp3b_synth_fill): bit-identical floats from the same arguments. */
+void orc_synth_fill(float *pcm, size_t n_per_channel, int channels, int sample_rate, float f_left, float f_right,
+                    float amp, float noise, uint64_t seed);
+
 #ifdef __cplusplus
 }
 #endif

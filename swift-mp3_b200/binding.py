@@ -292,6 +292,12 @@ class EncoderBatch:
         """Raw variant: host_ptrs / n_floats are ctypes arrays (c_void_p / c_size_t) prepared by the caller."""
         _check(lib().mp3b_batch_encode(self._h, host_ptrs, n_floats, int(flush), None))
 
+    def encode_strided(self, base_ptr, pitch_floats, n_floats, flush=False, flush_mask=None):
+        """mp3b_batch_encode_strided: stream i = base_ptr + i * pitch_floats * 4 (one host arena, one strided upload);
+        n_floats is a ctypes c_size_t array."""
+        mask = None if flush_mask is None else np.ascontiguousarray(flush_mask, dtype=np.uint8).ctypes.data
+        _check(lib().mp3b_batch_encode_strided(self._h, base_ptr, pitch_floats, n_floats, int(flush), mask))
+
     def encode_i16(self, chunks, flush=False):
         """Extension: one interleaved int16 array per stream; equals encode([c.astype(float32) / 32768 for c in chunks])."""
         arrs = [np.ascontiguousarray(c, dtype=np.int16).reshape(-1) for c in chunks]
@@ -355,6 +361,14 @@ class EncoderBatch:
 
     def reset(self):
         _check(lib().mp3b_batch_reset(self._h))
+
+    def clone(self):
+        """Snapshot of all sessions of the batch (mp3b_batch_clone)."""
+        c = object.__new__(EncoderBatch)
+        c.options, c.n_streams, c.device = self.options, self.n_streams, self.device
+        c._h = C.c_void_p()
+        _check(lib().mp3b_batch_clone(self._h, C.byref(c._h)))
+        return c
 
     # ---- traces (tests) ----
     def set_trace(self, spectrum=False, ix=False, thresholds=False, records=True):

@@ -1202,23 +1202,66 @@ __global__ void __launch_bounds__(256) k_gather(Config cfg, PassBuffers pb, cons
 
 // ------------------------------------------------------------------------------------------------------------
 // Synthetic PCM (bench / tests), BASELINE C1/C4 recipe: a*sin(2 pi f t) + noise*N(0,1), clipped to [-1, 1].
+// Counter-based and bit-reproducible on any IEEE-754 machine: every operation is an explicitly rounded double operation
+// (no libm, no fast-math intrinsics), so the CPU twin in oracle/mp3_oracle.c (orc_synth_fill) produces the same floats and
+// the CPU arm of the bench encodes exactly the inputs the GPU arm does (tests/test_gpu_parity.py::test_synth_twin).
+//   h1 = splitmix64(seed * 0x100000001B3 + i), h2 = splitmix64(h1)
+//   u1 = ((h1 >> 11) + 1) / 2^53 in (0, 1], u2 = (h2 >> 11) / 2^53 in [0, 1)
+//   Box-Muller: rad = sqrt(-2 ln u1), (gL, gR) = rad * (cos, sin)(2 pi u2)
+//   tone_c = sin(2 pi * frac(frac(f_c * i / sr) + phase_c)), phase_L = 0, phase_R = 0.3 / (2 pi)
+//   sample = clip((float)(amp * tone_c + noise * g_c))
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
+}
+// ln(k * 2^-53), k in [1, 2^53]: k = m * 2^e with m in [sqrt(1/2), sqrt(2)), ln m = 2 atanh((m - 1) / (m + 1)) as an 11-term
+// odd series (|s| <= 0.172: the first dropped term is below 1e-18)
+__device__ __forceinline__ double synth_ln_u(uint64_t k) {
+  int e = 63 - __clzll((long long)k);                              // k = 2^e * [1, 2)
+  double m = e == 53 ? 1.0 : __longlong_as_double((long long)((k << ((52 - e) & 63)) & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ll);   // exact: k has at most 53 bits
+  if (m > 1.4142135623730951) { m = __dmul_rn(m, 0.5); e += 1; }
+  const double sq = __ddiv_rn(__dadd_rn(m, -1.0), __dadd_rn(m, 1.0)), z = __dmul_rn(sq, sq);
+  double p = 1.0 / 21.0;
+  p = __fma_rn(p, z, 1.0 / 19.0); p = __fma_rn(p, z, 1.0 / 17.0); p = __fma_rn(p, z, 1.0 / 15.0); p = __fma_rn(p, z, 1.0 / 13.0);
+  p = __fma_rn(p, z, 1.0 / 11.0); p = __fma_rn(p, z, 1.0 / 9.0); p = __fma_rn(p, z, 1.0 / 7.0); p = __fma_rn(p, z, 1.0 / 5.0);
+  p = __fma_rn(p, z, 1.0 / 3.0); p = __fma_rn(p, z, 1.0);
+  return __fma_rn((double)(e - 53), 0.6931471805599453, __dmul_rn(__dmul_rn(2.0, sq), p));
+}
+// (sin, cos)(2 pi t), t in [0, 1): quadrant from t * 4 (exact), Taylor polynomials on [0, pi / 2)
+__device__ __forceinline__ void synth_sincos_turn(double t, double &sn, double &cs) {
+  const double q4 = floor(__dmul_rn(t, 4.0));
+  const double x = __dmul_rn(6.283185307179586, __dadd_rn(t, -__dmul_rn(q4, 0.25))), z = __dmul_rn(x, x);
+  double ps = -1.0 / 25852016738884976640000.0;                    // -1/23!
+  ps = __fma_rn(ps, z, 1.0 / 51090942171709440000.0); ps = __fma_rn(ps, z, -1.0 / 121645100408832000.0); ps = __fma_rn(ps, z, 1.0 / 355687428096000.0);
+  ps = __fma_rn(ps, z, -1.0 / 1307674368000.0); ps = __fma_rn(ps, z, 1.0 / 6227020800.0); ps = __fma_rn(ps, z, -1.0 / 39916800.0);
+  ps = __fma_rn(ps, z, 1.0 / 362880.0); ps = __fma_rn(ps, z, -1.0 / 5040.0); ps = __fma_rn(ps, z, 1.0 / 120.0);
+  ps = __fma_rn(ps, z, -1.0 / 6.0); ps = __fma_rn(ps, z, 1.0);
+  const double s0 = __dmul_rn(x, ps);
+  double pc = 1.0 / 620448401733239439360000.0;                    // 1/24!
+  pc = __fma_rn(pc, z, -1.0 / 1124000727777607680000.0); pc = __fma_rn(pc, z, 1.0 / 2432902008176640000.0); pc = __fma_rn(pc, z, -1.0 / 6402373705728000.0);
+  pc = __fma_rn(pc, z, 1.0 / 20922789888000.0); pc = __fma_rn(pc, z, -1.0 / 87178291200.0); pc = __fma_rn(pc, z, 1.0 / 479001600.0);
+  pc = __fma_rn(pc, z, -1.0 / 3628800.0); pc = __fma_rn(pc, z, 1.0 / 40320.0); pc = __fma_rn(pc, z, -1.0 / 720.0);
+  pc = __fma_rn(pc, z, 1.0 / 24.0); pc = __fma_rn(pc, z, -0.5); pc = __fma_rn(pc, z, 1.0);
+  const int q = (int)q4;
+  sn = q == 0 ? s0 : q == 1 ? pc : q == 2 ? -s0 : -pc;
+  cs = q == 0 ? pc : q == 1 ? -s0 : q == 2 ? -pc : s0;
 }
 __global__ void k_synth(float *pcm, size_t n, int channels, int sample_rate, float f_left, float f_right, float amp,
                         float noise, uint64_t seed) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint64_t h = splitmix64(seed * 0x100000001B3ull + i);
-  float u1 = ((uint32_t)(h >> 40) + 1u) * (1.0f / 16777217.0f), u2 = ((uint32_t)h >> 8) * (1.0f / 16777216.0f);
-  float rad = sqrtf(-2.0f * __logf(u1)), sn, cs;
-  __sincosf(6.28318530718f * u2, &sn, &cs);
+  const uint64_t h1 = splitmix64(seed * 0x100000001B3ull + i), h2 = splitmix64(h1);
+  const double rad = __dsqrt_rn(__dmul_rn(-2.0, synth_ln_u((h1 >> 11) + 1)));
+  double gs, gc;
+  synth_sincos_turn(__dmul_rn((double)(h2 >> 11), 1.1102230246251565e-16), gs, gc);   // * 2^-53, exact
   for (int c = 0; c < channels; ++c) {
-    double cyc = (double)(c == 0 ? f_left : f_right) * (double)i / (double)sample_rate;
-    float ph = (float)(cyc - floor(cyc));
-    float v = amp * sinpif(2.0f * ph + (c == 1 ? 0.3f / 3.14159265f : 0.0f)) + noise * rad * (c == 0 ? cs : sn);
-    pcm[i * channels + c] = fminf(fmaxf(v, -1.0f), 1.0f);
+    const double cyc = __ddiv_rn(__dmul_rn((double)(c == 0 ? f_left : f_right), (double)i), (double)sample_rate);
+    double t = __dadd_rn(cyc, -floor(cyc));
+    if (c == 1) { t = __dadd_rn(t, 0.0477464829275686); if (t >= 1.0) t = __dadd_rn(t, -1.0); }   // + 0.3 rad
+    double sn, cs;
+    synth_sincos_turn(t, sn, cs);
+    const double v = __dadd_rn(__dmul_rn((double)amp, sn), __dmul_rn((double)noise, __dmul_rn(rad, c == 0 ? gc : gs)));
+    pcm[i * channels + c] = fminf(fmaxf(__double2float_rn(v), -1.0f), 1.0f);
   }
 }
 

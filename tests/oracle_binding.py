@@ -31,19 +31,14 @@ FRAME_TRACE = np.dtype([("frame_energy", "<f4"), ("ms", "<i4"), ("bitrate_kbps",
                         ("reservoir_bits", "<i4"), ("huff_bytes", "<i4"), ("is_final", "<i4")])
 
 _lib = None
+_native = None
 
 
 def build():
     subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "oracle")])
 
 
-def lib():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(_SO):
-        build()
-    L = C.CDLL(_SO)
+def _declare(L):
     L.orc_create.restype = C.c_void_p; L.orc_create.argtypes = [C.POINTER(Options)]
     L.orc_destroy.argtypes = [C.c_void_p]
     L.orc_clone.restype = C.c_void_p; L.orc_clone.argtypes = [C.c_void_p]
@@ -72,8 +67,32 @@ def lib():
     L.orc_encode_streams.restype = C.c_size_t
     L.orc_encode_streams.argtypes = [C.POINTER(Options), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t,
                                      C.c_int, C.POINTER(C.c_uint64)]
-    _lib = L
+    L.orc_compare_streams.restype = C.c_size_t
+    L.orc_compare_streams.argtypes = [C.POINTER(Options), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_size_t,
+                                      C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int64)]
+    L.orc_synth_fill.restype = None
+    L.orc_synth_fill.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint64]
     return L
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        build()
+    _lib = _declare(C.CDLL(_SO))
+    return _lib
+
+
+def native_lib():
+    """The oracle rebuilt -O3 -march=native ON THIS HOST (oracle/Makefile `native`): the timed CPU baseline of bench.py.
+    Same source, same results (no fast-math, no contraction); the default build stays the checker."""
+    global _native
+    if _native is None:
+        subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(_ROOT, "oracle"), "native"])
+        _native = _declare(C.CDLL(os.path.join(_ROOT, "oracle", "libmp3oracle_native.so")))
+    return _native
 
 
 MODES = {"mono": 0, "stereo": 1, "jointStereo": 2}
@@ -165,12 +184,42 @@ def id3_build(title=None, artist=None, album=None, genre=None, comment=None, tra
     return out
 
 
-def encode_streams(pcms, n_threads, **opts):
-    """Multi-threaded CPU baseline: returns (total_bytes, digest)."""
+def encode_streams(pcms, n_threads, native=False, **opts):
+    """Multi-threaded CPU baseline: returns (total_bytes, digest).  native=True: the -O3 -march=native build."""
     o = make_options(**opts)
     arrs = [np.ascontiguousarray(p, dtype=np.float32) for p in pcms]
     ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
     lens = (C.c_size_t * len(arrs))(*[a.size for a in arrs])
     dig = C.c_uint64()
-    n = lib().orc_encode_streams(C.byref(o), ptrs, lens, len(arrs), n_threads, C.byref(dig))
+    L = native_lib() if native else lib()
+    n = L.orc_encode_streams(C.byref(o), ptrs, lens, len(arrs), n_threads, C.byref(dig))
     return n, dig.value
+
+
+def compare_streams_raw(pcm_ptrs, n_floats, expect_ptrs, expect_lens, n_threads, chunk_floats=0, **opts):
+    """orc_compare_streams on raw addresses (ints): every stream is encoded by the oracle and compared with the bytes at
+    expect_ptrs[i].  Returns the list of (stream, first differing byte offset) — empty when everything is identical."""
+    o = make_options(**opts)
+    n = len(pcm_ptrs)
+    pp = (C.c_void_p * n)(*pcm_ptrs); nn = (C.c_size_t * n)(*n_floats)
+    ep = (C.c_void_p * n)(*expect_ptrs); en = (C.c_size_t * n)(*expect_lens)
+    fd = (C.c_int64 * n)()
+    bad = lib().orc_compare_streams(C.byref(o), pp, nn, n, chunk_floats, n_threads, ep, en, fd)
+    out = [(i, int(fd[i])) for i in range(n) if fd[i] >= 0]
+    assert len(out) == bad
+    return out
+
+
+def compare_streams(pcms, outputs, n_threads=0, chunk_floats=0, **opts):
+    """The same for numpy PCM arrays and bytes objects."""
+    arrs = [np.ascontiguousarray(p, dtype=np.float32).reshape(-1) for p in pcms]
+    bufs = [np.frombuffer(o, dtype=np.uint8) if len(o) else np.zeros(1, np.uint8) for o in outputs]
+    return compare_streams_raw([a.ctypes.data for a in arrs], [a.size for a in arrs], [b.ctypes.data for b in bufs],
+                               [len(o) for o in outputs], n_threads or (os.cpu_count() or 1), chunk_floats, **opts)
+
+
+def synth_fill(n_per_channel, channels=2, sample_rate=44100, f_left=440.0, f_right=554.37, amp=0.5, noise=0.05, seed=1234):
+    """CPU twin of mp3b_synth_fill: interleaved float32, bit-identical to the device generator."""
+    out = np.empty(n_per_channel * channels, dtype=np.float32)
+    lib().orc_synth_fill(out.ctypes.data, n_per_channel, channels, sample_rate, f_left, f_right, amp, noise, seed)
+    return out

@@ -122,3 +122,36 @@ def test_generated_tables_are_current(tmp_path):
     out = tmp_path / "tables_gen.h"
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_device_tables.py"), str(out)], check=True, capture_output=True, timeout=120)
     assert out.read_text() == open(os.path.join(ROOT, "swift-mp3_b200", "csrc", "tables_gen.h")).read()
+
+
+def test_xing_frame_size_uses_the_snapped_bitrate(mp3):
+    """SRC:198-200: bitrateValue(bitrateIndex(125, 44100)) = 128 -> 144 * 128000 / 44100 = 417; 64 kbps at 22.05 kHz goes through the
+    MPEG-2 index table but the MPEG-1 value table: index 8 -> 112 kbps -> 731.  Host-only entry point."""
+    from importlib import import_module
+    b = import_module("swift-mp3_b200.binding")
+    L = mp3.lib()
+    for kbps, sr, want in ((125, 44100, 417), (128, 44100, 417), (130, 44100, 417), (320, 48000, 960), (32, 48000, 96), (64, 22050, 731)):
+        o = b._Options(sr, kbps, 0, 1, 5, 0, 1, 0)
+        assert L.mp3b_xing_frame_size(C.byref(o)) == want, (kbps, sr)
+    assert L.mp3b_xing_frame_size(None) < 0
+
+
+def test_stream_limit_is_rejected_at_creation(mp3):
+    """More streams than a grid dimension holds fail cleanly at creation (bad argument), not at the first launch."""
+    from importlib import import_module
+    b = import_module("swift-mp3_b200.binding")
+    L = mp3.lib()
+    o = b._Options(44100, 128, 0, 1, 5, 0, 1, 0)
+    h = C.c_void_p()
+    assert L.mp3b_batch_create(C.byref(o), 65536, 0, C.byref(h)) == -1 and b"65535" in L.mp3b_last_error()
+
+
+def test_synth_twin_is_pinned(orc):
+    """The CPU generator of the bench inputs (twin of the device kernel): statistics of the C1 recipe and a pinned digest."""
+    import hashlib
+    x = orc.synth_fill(44100, 2, 44100, 440.0, 554.37, 0.5, 0.05, 1234)
+    t = np.arange(44100) / 44100.0
+    nl, nr = x[0::2] - 0.5 * np.sin(2 * np.pi * 440.0 * t), x[1::2] - 0.5 * np.sin(2 * np.pi * 554.37 * t + 0.3)
+    assert abs(nl.std() - 0.05) < 1e-3 and abs(nr.std() - 0.05) < 1e-3 and abs(np.corrcoef(nl, nr)[0, 1]) < 0.02
+    assert abs(nl.mean()) < 1e-3 and np.abs(x).max() <= 1.0
+    assert hashlib.sha256(x.tobytes()).hexdigest() == open(os.path.join(ROOT, "tests", "golden", "synth_c1_sha256.txt")).read().strip()

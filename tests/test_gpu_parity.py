@@ -175,7 +175,7 @@ def test_baseline_configs_at_full_size(mp3, orc):
 def test_batch_shard_properties(mp3, orc):
     """A slice of BASELINE config 4 (64 streams x 30 s, synthesised on the device like bench.py does) through the device
     plane: every stream has the frame count and byte count the format dictates, the batch is deterministic, duplicate
-    streams give duplicate bytes, and two of the streams equal the oracle."""
+    streams give duplicate bytes, the device-generated PCM equals the CPU twin, and EVERY stream equals the oracle."""
     import ctypes as C
     import importlib
     import torch
@@ -202,9 +202,11 @@ def test_batch_shard_properties(mp3, orc):
     b.reset()
     b.encode_device(ptrs, ns, flush=True, download=True)
     assert [b.output(i) for i in range(S)] == first
-    for i in (0, 47):
-        ref, _ = orc.encode_all(pcm[i].cpu().numpy())
-        assert first[i] == ref
+    host = pcm.cpu().numpy()
+    for i in (0, 17, 47):                                                   # the CPU generator is a bit-exact twin of the device one
+        fl, fr, seed = sharding.stream_params(i % 48)
+        assert np.array_equal(host[i].view("<u4"), orc.synth_fill(n_per, 2, 44100, fl, fr, 0.5, 0.05, seed).view("<u4"))
+    assert orc.compare_streams(list(host), first) == []                     # all 64 streams, byte for byte
     b.close()
 
 
@@ -433,3 +435,138 @@ def test_session_clone_is_a_snapshot(mp3, orc):
     assert s2.encode(y) + s2.flush() == r2.encode(y) + r2.flush()
     assert s2.encodedFrameCount == r2.frame_count and s.encodedFrameCount == r.frame_count
     s.close(); s2.close()
+
+
+def test_synth_twin(mp3, orc):
+    """mp3b_synth_fill (device) and orc_synth_fill (CPU) are bit-identical for every argument combination: the CPU arm of
+    the bench encodes exactly the inputs the GPU arm does."""
+    import torch
+    L = mp3.lib()
+    for n, ch, sr, fl, fr, amp, noise, seed in ((50001, 2, 44100, 440.0, 554.37, 0.5, 0.05, 1234), (70000, 1, 48000, 1000.0, 0.0, 0.9, 0.5, 7),
+                                               (33333, 2, 32000, 110.0, 138.6, 0.0, 1.0, 2 ** 40 + 3), (4097, 2, 44100, 20000.0, 19999.5, 1.0, 0.0, 0)):
+        t = torch.empty(n * ch, dtype=torch.float32, device="cuda")
+        assert L.mp3b_synth_fill(0, t.data_ptr(), n, ch, sr, fl, fr, amp, noise, seed) == 0, L.mp3b_last_error()
+        got, want = t.cpu().numpy(), orc.synth_fill(n, ch, sr, fl, fr, amp, noise, seed)
+        bad = np.nonzero(got.view("<u4") != want.view("<u4"))[0]
+        assert bad.size == 0, "first difference at float %d: device %r cpu %r" % (bad[0], got[bad[0]], want[bad[0]])
+        assert np.abs(got).max() <= 1.0 and (noise == 0 or got.std() > 0.01)
+
+
+def test_clone_then_immediate_device_encode(mp3, orc):
+    """A batch clone is complete when mp3b_batch_clone returns: the first thing done with it is a device-plane encode (only the
+    plan upload precedes the kernels), on a wide batch so that the copied state is large; both halves equal the oracle."""
+    import ctypes as C
+    import torch
+    S = 256
+    base = [signals.sine_noise(0.9, seed=800 + i, f_left=300.0 + 40 * i) for i in range(4)]
+    cut = 2304 * 9 + 500
+    b = mp3.EncoderBatch(_opts(mp3), S, 0, 8)
+    head = b.encode([base[i % 4][:cut] for i in range(S)], flush=False)
+    dev = [torch.from_numpy(base[i][cut:].copy()).cuda() for i in range(4)]
+    torch.cuda.synchronize()
+    ptrs = (C.c_void_p * S)(*[dev[i % 4].data_ptr() for i in range(S)])
+    ns = (C.c_size_t * S)(*[dev[i % 4].numel() for i in range(S)])
+    c = b.clone()
+    c.encode_device(ptrs, ns, flush=True, download=True)
+    tail = c.outputs()
+    for i in range(S):
+        ref = orc.Session()
+        want = ref.encode(base[i % 4][:cut]), ref.encode(base[i % 4][cut:]) + ref.flush()
+        assert head[i] == want[0] and tail[i] == want[1], "stream %d" % i
+    b.close(); c.close()
+
+
+def _c5_inputs(orc, S, chunks):
+    sharding = __import__("importlib").import_module("swift-mp3_b200.sharding")
+    n_per = chunks * 1152
+    pcm = np.empty((S, n_per * 2), np.float32)
+    for i in range(S):
+        fl, fr, seed = sharding.stream_params(i)
+        pcm[i] = orc.synth_fill(n_per, 2, 44100, fl, fr, 0.5, 0.05, seed)
+    return pcm
+
+
+def test_c5_1024_sessions_batch_strided(mp3, orc):
+    """BASELINE config 5 at full width: 1024 concurrent sessions (C4 streams 0...1023) fed 56 chunks of 1152 stereo samples,
+    one mp3b_batch_encode_strided call per chunk.  EVERY session's bytes equal an oracle session fed the same chunks
+    (SRC:297-310), eight sessions are also compared call by call, and the first call returns nothing (one-frame delay)."""
+    import ctypes as C
+    S, chunks, cf = 1024, 56, 2304
+    pcm = _c5_inputs(orc, S, chunks)
+    L = mp3.lib()
+    hp = C.c_void_p()
+    assert L.mp3b_host_alloc(S * cf * 4, C.byref(hp)) == 0
+    arena = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_float)), shape=(S, cf))
+    ns = (C.c_size_t * S)(*([cf] * S))
+    b = mp3.EncoderBatch(_opts(mp3), S, 0, 8)
+    watch = [0, 1, 2, 3, 511, 777, 1022, 1023]
+    per_call = {i: [] for i in watch}
+    got = [bytearray() for _ in range(S)]
+    for k in range(chunks):
+        arena[:] = pcm[:, k * cf:(k + 1) * cf]
+        b.encode_strided(hp.value, cf, ns, flush=(k == chunks - 1))
+        for i in range(S):
+            got[i] += b.output(i)
+        for i in watch:
+            per_call[i].append(b.output(i))
+        if k == 0:
+            assert b.output_total == 0                                           # SRC:546-562: the first frame is held back
+    assert orc.compare_streams(list(pcm), [bytes(g) for g in got], chunk_floats=cf) == []
+    for i in watch:
+        rs = orc.Session()
+        want = [rs.encode(pcm[i, k * cf:(k + 1) * cf]) for k in range(chunks)]
+        want[-1] += rs.flush()
+        assert per_call[i] == want, "session %d" % i
+        assert b.frame_count(i) == rs.frame_count == chunks
+    b.close()
+    L.mp3b_host_free(hp)
+
+
+def test_c5_1024_sessions_through_pool(mp3, orc):
+    """The same workload through the session pool: 1024 OS threads, each blocking in its own encode(samples:) per chunk
+    (SRC:297-310) and flushing at the end; the pool turns the calls into shared GPU steps.  Every session against the oracle."""
+    import threading
+    S, chunks, cf = 1024, 50, 2304
+    pcm = _c5_inputs(orc, S, chunks)
+    pool = mp3.SessionPool(_opts(mp3), S, 0, max_wait_us=3000)
+    got, errs = [None] * S, []
+    sessions = [pool.newSession() for _ in range(S)]                              # all open before the first call: full steps
+
+    def client(i):
+        try:
+            s, out = sessions[i], bytearray()
+            for k in range(chunks):
+                out += s.encode(pcm[i, k * cf:(k + 1) * cf])
+            out += s.flush()
+            got[i] = bytes(out)
+        except Exception as e:  # pragma: no cover
+            errs.append((i, repr(e)))
+
+    old = threading.stack_size(512 * 1024)
+    threads = [threading.Thread(target=client, args=(i,)) for i in range(S)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    threading.stack_size(old)
+    assert not errs, errs[:3]
+    assert all(g is not None for g in got)
+    assert orc.compare_streams(list(pcm), got, chunk_floats=cf) == []
+    st = pool.stats()
+    assert st["requests"] == S * (chunks + 1) and st["steps"] <= st["requests"] / 64, st       # >= 64 calls per GPU step on average
+    pool.close()
+
+
+def test_encode_to_file_layout(mp3, orc, tmp_path):
+    """MP3Encoder.encode(_:to:) (SRC:189-230) with an off-table bitrate: the placeholder is sized from the SNAPPED bitrate
+    (125 -> 128 kbps: 417 bytes), so the final Xing frame replaces exactly the placeholder and the audio frames follow intact."""
+    pcm = signals.sine_noise(0.6, seed=3)
+    o = mp3.MP3EncoderOptions(bitrateKbps=125, id3Tag=mp3.ID3Tag(title="t", artist="a"))
+    path = tmp_path / "out.mp3"
+    mp3.MP3Encoder(o).encode_to([pcm[:30000], pcm[30000:]], str(path))
+    data = path.read_bytes()
+    rs = orc.Session(bitrate_kbps=125)
+    frames = rs.encode(pcm) + rs.flush()
+    id3 = orc.id3_build(title="t", artist="a")
+    assert data == id3 + rs.xing_header() + frames
+    assert len(rs.xing_header()) == 417 == mp3.lib().mp3b_xing_frame_size(__import__("ctypes").byref(o._c()))
