@@ -282,6 +282,74 @@ def bench_c5(steps, mp3, L, local):
     return res
 
 
+def bench_multi(a, mp3, L, metric):
+    """BASELINE config 4 through the multi-device batch plane of the C ABI (mp3b_batch_create_multi) from ONE process — what a
+    Swift host would call: 4096 streams partitioned by stream over `--gpus` devices, one host thread per device inside the
+    library.  value = device plane (each stream's PCM on its own device), e2e = pinned host buffers in, bytes out; wall clock
+    around the call with every device synchronised.  All streams are checked against the oracle."""
+    import numpy as np
+    import torch
+    import oracle_binding as orc
+    G = a.gpus
+    S = a.streams if a.streams > 0 else TOTAL_STREAMS
+    n_per = int(round(a.seconds * SR)); n_floats = n_per * CH
+    opts = mp3.MP3EncoderOptions(sampleRate=SR, bitrateKbps=KBPS, mode=mp3.Mode.stereo)
+    b = mp3.EncoderBatch(opts, S, devices=list(range(G)))
+    dev_of = [b.stream_device(i) for i in range(S)]
+    pcm = [torch.empty((dev_of.count(d), n_floats), dtype=torch.float32, device="cuda:%d" % d) for d in range(G)]
+    row, seen = [], [0] * G
+    for i in range(S):
+        d = dev_of[i]; t = pcm[d][seen[d]]; seen[d] += 1
+        fl, fr, seed = stream_params(i)
+        assert L.mp3b_synth_fill(d, t.data_ptr(), n_per, CH, SR, fl, fr, 0.5, 0.05, seed) == 0, L.mp3b_last_error()
+        row.append(t)
+    sync = lambda: [L.mp3b_device_sync(d) for d in range(G)]
+    sync()
+    dptrs = (C.c_void_p * S)(*[t.data_ptr() for t in row]); ns = (C.c_size_t * S)(*([n_floats] * S))
+    # parity of every stream (device plane, downloaded)
+    b.encode_device(dptrs, ns, flush=True, download=True)
+    bad, cores = [], os.cpu_count() or 1
+    for lo in range(0, S, 128):
+        hi = min(S, lo + 128)
+        host = [row[i].cpu().numpy() for i in range(lo, hi)]
+        outs = [b.output(i) for i in range(lo, hi)]
+        bad += [(lo + i, off) for i, off in orc.compare_streams(host, outs, cores, sample_rate=SR, bitrate_kbps=KBPS, mode="stereo")]
+    assert not bad, "multi-device batch differs from the oracle: %r" % bad[:4]
+    digests = stream_digests(L, b, S)
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            b.reset(); fn()
+        sync(); t0 = time.perf_counter()
+        for _ in range(steps):
+            b.reset(); fn()
+        sync()
+        return (time.perf_counter() - t0) / steps
+    t_dev = timed(lambda: b.encode_device(dptrs, ns, flush=True, download=False), a.steps, a.warmup)
+    stage_dev, launches = b.stage_ms(), b.launch_count
+    hp = C.c_void_p()
+    assert L.mp3b_host_alloc(S * n_floats * 4, C.byref(hp)) == 0, L.mp3b_last_error()
+    for i in range(S):
+        assert L.mp3b_device_copy(dev_of[i], hp.value + i * n_floats * 4, row[i].data_ptr(), n_floats * 4, 1) == 0
+    hptrs = (C.c_void_p * S)(*[hp.value + i * n_floats * 4 for i in range(S)])
+    e2e_steps = a.e2e_steps or min(a.steps, 5)
+    t_e2e = timed(lambda: b.encode_ptrs(hptrs, ns, flush=True), e2e_steps, 1)
+    assert stream_digests(L, b, S) == digests, "e2e output differs from the oracle-checked device-plane output"
+    audio = S * a.seconds
+    emit({"metric": metric, "value": audio / t_dev, "unit": "x realtime", "n_gpus": G, "steps": a.steps, "warmup": a.warmup,
+          "ms_per_step": 1e3 * t_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": "C4: %d streams x %.0f s partitioned by stream over %d GPU(s) by mp3b_batch_create_multi, ONE process "
+                                 "(one host thread per device inside the library)" % (S, a.seconds, G),
+                     "parity": "%d/%d streams byte-identical to the oracle" % (S, S), "timing": "wall clock around the C-ABI call, all devices synchronised"},
+          "e2e": {"value": audio / t_e2e, "unit": "x realtime", "ms_per_step": 1e3 * t_e2e, "steps": e2e_steps,
+                  "h2d_bytes_per_step": S * n_floats * 4, "d2h_bytes_per_step": int(b.output_total),
+                  "h2d_GBps_aggregate": S * n_floats * 4 / t_e2e / 1e9},
+          "gpu_launches": int(launches) * a.steps, "stage_ms_device_plane_slowest_device": stage_dev})
+    L.mp3b_host_free(hp)
+    b.close()
+    return 0
+
+
 _REAL_STDOUT = None
 
 
@@ -320,6 +388,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["c4", "c1", "c2", "c3", "c5"],
                     help="c4 (default, the headline): batch of 30 s streams; c1 / c2 / c3: the single-stream configs; "
                          "c5: streaming latency, 1024 sessions x 1152-sample chunks")
+    ap.add_argument("--single-process", action="store_true", help="drive all --gpus devices from this one process through "
+                    "mp3b_batch_create_multi (no torchrun): the multi-device plane of the C ABI")
     ap.add_argument("--no-others", action="store_true", help="skip the other_configs legs (C1, C2, C3, C5) of the default line")
     ap.add_argument("--parity", default="all", choices=["all", "spot"], help="all (default): every stream of the shard against "
                     "the oracle; spot: two streams (profiling runs)")
@@ -352,6 +422,9 @@ def main():
     import torch
     mp3 = importlib.import_module("swift-mp3_b200")
     L = mp3.lib()
+    if a.single_process:
+        assert world == 1, "--single-process is not run under torchrun"
+        return bench_multi(a, mp3, L, metric)
     torch.cuda.set_device(local)
     numa = sharding.bind_near_gpu(local)           # before any pinned allocation
     sampler = ClockSampler(local); sampler.start()

@@ -99,6 +99,14 @@ int mp3b_id3_build(const mp3b_id3 *tag, uint8_t *out, size_t cap, size_t *writte
 int mp3b_batch_create(const mp3b_options *opts, int n_streams, int device, mp3b_batch **out);
 /* Same with an explicit pass size (frames of every stream processed per device pass; 0 = automatic). */
 int mp3b_batch_create_ex(const mp3b_options *opts, int n_streams, int device, int frames_per_pass, mp3b_batch **out);
+/* The same batch spread over several devices (sessions share nothing, SRC:237-258, so the batch is
+ * partitioned BY STREAM with no collective): streams are cut into n_dev contiguous blocks, block k lives on devices[k] and is
+ * driven by a host thread of its own, so uploads, kernels and downloads of all devices overlap.  Every mp3b_batch_* call
+ * works on the handle as on a single-device batch, indexed by the global stream number.  A device may be listed more than
+ * once.  frames_per_pass: 0 = automatic.  For mp3b_batch_encode_device, d_pcm[i] must live on mp3b_batch_stream_device(b, i). */
+int mp3b_batch_create_multi(const mp3b_options *opts, int n_streams, const int *devices, int n_dev, int frames_per_pass, mp3b_batch **out);
+int mp3b_batch_device_count(const mp3b_batch *b);
+int mp3b_batch_stream_device(const mp3b_batch *b, int stream);
 int mp3b_batch_frames_per_pass(const mp3b_batch *b);
 void mp3b_batch_destroy(mp3b_batch *b);
 int mp3b_batch_stream_count(const mp3b_batch *b);
@@ -173,7 +181,8 @@ enum {
 int mp3b_batch_stage_ms(const mp3b_batch *b, float *ms, int n);
 /* Number of device passes of the last batch call (each stage kernel is launched once per pass). */
 int mp3b_batch_pass_count(const mp3b_batch *b);
-/* The CUDA stream (cudaStream_t) all work of this batch is issued on, so that callers can record their own events. */
+/* The CUDA stream (cudaStream_t) all work of this batch is issued on, so that callers can record their own events
+ * (multi-device batch: the stream of its first device; stage times are then the maximum over the devices). */
 void *mp3b_batch_stream(const mp3b_batch *b);
 /* Number of kernel launches issued by the last batch call. */
 int mp3b_batch_launch_count(const mp3b_batch *b);

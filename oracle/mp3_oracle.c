@@ -82,6 +82,9 @@ static int bw_bitcount(const bitw_t *w) { return (int)w->data.n * 8 + w->bits_in
 static float T_window[512], T_analysis[32 * 64], T_analysis_t[64 * 32];
 static float T_mdct_long[18 * 36], T_mdct_long_t[36 * 18], T_mdct_short[6 * 12], T_win_long[36], T_win_short[12];
 static float T_inv_step[256];
+#ifdef ORC_VARIANTS
+#include "variants.inc"   /* alternative summation orders / pow / split-TF32 matrixing for tools/order_sensitivity.py; never in the default build */
+#endif
 static uint16_t T_crc[256];
 static pthread_once_t tables_once = PTHREAD_ONCE_INIT;
 
@@ -132,7 +135,12 @@ const uint8_t *orc_table_code15(void) { return ISO_HUFF15_CODE; }
 float orc_inv_step(int gain) { tables(); return T_inv_step[gain < 0 ? 0 : gain > 255 ? 255 : gain]; }
 
 /* [OD3] */
-float orc_pow34(float a) { double d = (double)a; double r = sqrt(d); return (float)(r * sqrt(r)); }
+float orc_pow34(float a) {
+#ifdef ORC_VARIANTS
+  if (g_variant == 4 || g_variant == 5) return pow34_var(a);
+#endif
+  double d = (double)a; double r = sqrt(d); return (float)(r * sqrt(r));
+}
 
 /* MP3Tables.bitrateIndex SRC:2509-2523 */
 int orc_bitrate_index(int bitrate, int sample_rate) {
@@ -156,6 +164,9 @@ static const uint8_t *band_table(int sr) {                        /* SRC:1879-18
 
 /* FrameAnalysis.energy SRC:1902-1907  [OD1b] */
 static float sumsq(const float *x, int n) {                       /* vDSP_svesq [OD1b] */
+#ifdef ORC_VARIANTS
+  if (g_variant == 9 || g_variant == 10) return sumsq_var(x, n);
+#endif
   float p[32], q[32];
   for (int j = 0; j < 32; ++j) p[j] = 0.0f;
   for (int i = 0; i < n; ++i) p[i & 31] = fmaf(x[i], x[i], p[i & 31]);
@@ -239,6 +250,9 @@ static orc_frame_trace *trace_frame_new(orc_session *s) {
 
 /* PolyphaseFilterbank.analyze SRC:1367-1411 */
 static void filterbank_step(const float *new32, float *buffer, float *out32) {
+#ifdef ORC_VARIANTS
+  if (g_variant) { filterbank_step_var(new32, buffer, out32); return; }
+#endif
   memmove(buffer, buffer + 32, 480 * sizeof(float));               /* SRC:1373 */
   memcpy(buffer + 480, new32, 32 * sizeof(float));                 /* SRC:1375-1381 */
   float z[512];
@@ -260,6 +274,9 @@ static void filterbank_step(const float *new32, float *buffer, float *out32) {
 
 /* MDCT.mdctLong SRC:1619-1636 */
 static void mdct_long(const float *comb, float *out18) {
+#ifdef ORC_VARIANTS
+  if (g_variant) { mdct_long_var(comb, out18); return; }
+#endif
   float w[36];
   for (int k = 0; k < 36; ++k) w[k] = comb[k] * T_win_long[k];     /* SRC:1625 [OD2] */
   float acc[18];
@@ -272,6 +289,9 @@ static void mdct_long(const float *comb, float *out18) {
 }
 /* MDCT.mdctShort SRC:1639-1662 */
 static void mdct_short(const float *comb, float *out18) {
+#ifdef ORC_VARIANTS
+  if (g_variant) { mdct_short_var(comb, out18); return; }
+#endif
   for (int w = 0; w < 3; ++w) {
     int offset = w * 6 + 6;
     float seg[12];
@@ -878,3 +898,13 @@ size_t orc_compare_streams(const orc_options *opts, const float *const *pcm, con
   if (!first_diff) free(fd);
   return bad;
 }
+
+#ifdef ORC_VARIANTS
+/* quantizeWithGain of one spectrum at a given gain, with the variant's arithmetic (tools/order_sensitivity.py). */
+void orc_requantize(const float *spec, int gain, int32_t *ix) {
+  tables();
+  float mag[576];
+  for (int i = 0; i < 576; ++i) mag[i] = orc_pow34(fmaxf(fabsf(spec[i]), 1e-10f));
+  quantize_with_gain(spec, mag, gain < 0 ? 0 : gain > 255 ? 255 : gain, ix);
+}
+#endif

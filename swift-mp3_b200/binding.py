@@ -77,6 +77,8 @@ def lib():
         "mp3b_batch_create": (i32, [C.POINTER(_Options), i32, i32, C.POINTER(vp)]),
         "mp3b_batch_create_ex": (i32, [C.POINTER(_Options), i32, i32, i32, C.POINTER(vp)]),
         "mp3b_batch_frames_per_pass": (i32, [vp]),
+        "mp3b_batch_create_multi": (i32, [C.POINTER(_Options), i32, C.POINTER(i32), i32, i32, C.POINTER(vp)]),
+        "mp3b_batch_device_count": (i32, [vp]), "mp3b_batch_stream_device": (i32, [vp, i32]),
         "mp3b_batch_destroy": (None, [vp]), "mp3b_batch_stream_count": (i32, [vp]),
         "mp3b_batch_encode": (i32, [vp, C.POINTER(vp), szp, i32, vp]),
         "mp3b_batch_encode_device": (i32, [vp, C.POINTER(vp), szp, i32, i32]),
@@ -258,13 +260,26 @@ class EncoderSession:
 
 
 class EncoderBatch:
-    """N independent EncoderSessions with the same options advancing together on one device (the batch plane)."""
+    """N independent EncoderSessions with the same options advancing together (the batch plane): on one device, or — devices =
+    a list of CUDA ordinals — partitioned by stream over several (mp3b_batch_create_multi; one host thread per device)."""
 
-    def __init__(self, options, n_streams, device=0, frames_per_pass=0):
+    def __init__(self, options, n_streams, device=0, frames_per_pass=0, devices=None):
         self.options, self.n_streams, self.device = options, n_streams, device
         self._h = C.c_void_p()
         o = options._c()
-        _check(lib().mp3b_batch_create_ex(C.byref(o), n_streams, device, frames_per_pass, C.byref(self._h)))
+        if devices is not None:
+            self.device = devices[0]
+            arr = (C.c_int * len(devices))(*devices)
+            _check(lib().mp3b_batch_create_multi(C.byref(o), n_streams, arr, len(devices), frames_per_pass, C.byref(self._h)))
+        else:
+            _check(lib().mp3b_batch_create_ex(C.byref(o), n_streams, device, frames_per_pass, C.byref(self._h)))
+
+    @property
+    def device_count(self):
+        return lib().mp3b_batch_device_count(self._h)
+
+    def stream_device(self, stream):
+        return _check(lib().mp3b_batch_stream_device(self._h, stream))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -459,8 +474,8 @@ class MP3Encoder:
         """newSession(), SRC:143-145."""
         return EncoderSession(self.options, device)
 
-    def newBatch(self, n_streams, device=0, frames_per_pass=0):
-        return EncoderBatch(self.options, n_streams, device, frames_per_pass)
+    def newBatch(self, n_streams, device=0, frames_per_pass=0, devices=None):
+        return EncoderBatch(self.options, n_streams, device, frames_per_pass, devices)
 
     def encode(self, chunks, device=0):
         """Counterpart of encode(_:) -> AsyncThrowingStream (SRC:151-179): yields every non-empty chunk of frames."""

@@ -2,12 +2,16 @@
 // SRC = Sources/SwiftMP3/MP3Encoder.swift of the reference.  There is no CPU fallback anywhere in this file: every
 // encode call runs the CUDA pipeline of kernels.cu, and creation fails when no sm_100 device is usable.
 #include <algorithm>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -49,7 +53,25 @@ int usable_device(int device) {
 
 }  // namespace
 
+// One host thread per device of a multi-device batch (streams are independent, so a device batch
+// never waits for another one).  The thread lives as long as the batch: it issues all CUDA work of its device and keeps the
+// device current, and the calling thread only posts a job to every worker and waits for all of them.
+struct PartWorker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<int()> job;
+  bool has_job = false, done = false, stop = false;
+  int rc = 0;
+  std::string err;
+};
+
 struct mp3b_batch {
+  // ---- multi-device plane: a parent owns one device batch ("part") per entry of its device list and routes by stream index;
+  // every field below this block is unused in a parent except S, opt and cfg
+  std::vector<mp3b_batch *> parts;
+  std::vector<int> part_lo;                              // first stream of part k; part_lo[parts.size()] = S
+  std::vector<std::unique_ptr<PartWorker>> workers;
   Config cfg{};
   mp3b_options opt{};
   int device = 0, S = 0, ch = 0, Fc = 0, GC = 0;
@@ -100,6 +122,56 @@ struct mp3b_session {
 
 namespace {
 
+inline bool is_multi(const mp3b_batch *b) { return b && !b->parts.empty(); }
+// part that owns `stream` of a parent, *local = its index inside the part
+inline mp3b_batch *part_of(const mp3b_batch *b, int stream, int *local) {
+  int k = (int)(std::upper_bound(b->part_lo.begin(), b->part_lo.end(), stream) - b->part_lo.begin()) - 1;
+  k = std::min(std::max(k, 0), (int)b->parts.size() - 1);
+  *local = stream - b->part_lo[k];
+  return b->parts[k];
+}
+void part_worker_main(PartWorker *w) {
+  std::unique_lock<std::mutex> lk(w->m);
+  for (;;) {
+    w->cv.wait(lk, [&] { return w->stop || w->has_job; });
+    if (w->stop) return;
+    std::function<int()> job = std::move(w->job);
+    w->has_job = false;
+    lk.unlock();
+    const int rc = job();
+    std::string err = rc ? g_err : std::string();
+    lk.lock();
+    w->rc = rc; w->err = std::move(err); w->done = true;
+    w->cv.notify_all();
+  }
+}
+// fn(k) runs on worker k for every part at once; returns the first failure (its text becomes the caller's last error)
+int on_all_parts(const std::vector<std::unique_ptr<PartWorker>> &workers, const std::function<int(int)> &fn) {
+  for (size_t k = 0; k < workers.size(); ++k) {
+    PartWorker &w = *workers[k];
+    std::lock_guard<std::mutex> lk(w.m);
+    w.job = [&fn, k] { return fn((int)k); };
+    w.has_job = true; w.done = false;
+    w.cv.notify_all();
+  }
+  int rc = MP3B_OK;
+  for (auto &wp : workers) {
+    PartWorker &w = *wp;
+    std::unique_lock<std::mutex> lk(w.m);
+    w.cv.wait(lk, [&] { return w.done; });
+    if (w.rc && !rc) { rc = w.rc; g_err = w.err; }
+  }
+  return rc;
+}
+void stop_workers(std::vector<std::unique_ptr<PartWorker>> &workers) {
+  for (auto &wp : workers) {
+    { std::lock_guard<std::mutex> lk(wp->m); wp->stop = true; }
+    wp->cv.notify_all();
+    if (wp->th.joinable()) wp->th.join();
+  }
+  workers.clear();
+}
+
 int fill_config(const mp3b_options &o, int n_streams, Config &c) {
   if (o.sample_rate <= 0) return fail(MP3B_ERR_BAD_ARG, "sample_rate must be > 0");
   if (o.mode < 0 || o.mode > 2) return fail(MP3B_ERR_BAD_ARG, "mode must be 0 (mono), 1 (stereo) or 2 (jointStereo)");
@@ -146,6 +218,12 @@ int max_frame_bytes_of(const Config &c) {
 
 void free_batch(mp3b_batch *b) {
   if (!b) return;
+  if (is_multi(b) || !b->workers.empty()) {
+    stop_workers(b->workers);
+    for (mp3b_batch *p : b->parts) free_batch(p);
+    delete b;
+    return;
+  }
   cudaSetDevice(b->device);
   if (b->st) cudaStreamSynchronize(b->st);
   PassBuffers &p = b->pb;
@@ -635,15 +713,63 @@ int mp3b_batch_create_ex(const mp3b_options *opts, int n_streams, int device, in
   if (frames_per_pass < 0 || frames_per_pass > 16384) return fail(MP3B_ERR_BAD_ARG, "frames_per_pass out of range");
   return create_batch(opts, n_streams, device, frames_per_pass, out);
 }
+// Multi-device batch: streams are cut into contiguous blocks, block k lives on devices[k] as a device batch of its own with a
+// host thread of its own; no data ever moves between devices (SRC:237-258: sessions share nothing).  A device may be listed
+// more than once (two independent pipelines on one GPU, or more streams than one device batch holds).
+int mp3b_batch_create_multi(const mp3b_options *opts, int n_streams, const int *devices, int n_dev, int frames_per_pass, mp3b_batch **out) {
+  if (!opts || !out || !devices || n_dev <= 0 || n_streams < n_dev) return fail(MP3B_ERR_BAD_ARG, "null pointer, n_dev <= 0 or fewer streams than devices");
+  if (frames_per_pass < 0 || frames_per_pass > 16384) return fail(MP3B_ERR_BAD_ARG, "frames_per_pass out of range");
+  Config cfg;
+  int rc = fill_config(*opts, n_streams, cfg);
+  if (rc) return rc;
+  mp3b_batch *b = new mp3b_batch();
+  b->S = n_streams; b->opt = *opts; b->cfg = cfg; b->ch = cfg.channels; b->device = devices[0];
+  b->parts.assign((size_t)n_dev, nullptr);
+  for (int k = 0; k <= n_dev; ++k) b->part_lo.push_back((int)((long long)n_streams * k / n_dev));
+  for (int k = 0; k < n_dev; ++k) {
+    b->workers.emplace_back(new PartWorker());
+    b->workers.back()->th = std::thread(part_worker_main, b->workers.back().get());
+  }
+  const mp3b_options o = *opts;
+  rc = on_all_parts(b->workers, [&](int k) { return create_batch(&o, b->part_lo[k + 1] - b->part_lo[k], devices[k], frames_per_pass, &b->parts[(size_t)k]); });
+  if (rc) {
+    std::string keep = g_err;
+    b->parts.erase(std::remove(b->parts.begin(), b->parts.end(), nullptr), b->parts.end());
+    if (b->parts.empty()) { stop_workers(b->workers); delete b; } else free_batch(b);
+    g_err = keep;
+    return rc;
+  }
+  b->Fc = b->parts[0]->Fc; b->GC = b->parts[0]->GC; b->max_frame_bytes = b->parts[0]->max_frame_bytes;
+  *out = b;
+  return MP3B_OK;
+}
+int mp3b_batch_device_count(const mp3b_batch *b) { return !b ? 0 : is_multi(b) ? (int)b->parts.size() : 1; }
 void mp3b_batch_destroy(mp3b_batch *b) { free_batch(b); }
 int mp3b_batch_stream_count(const mp3b_batch *b) { return b ? b->S : 0; }
 int mp3b_batch_frames_per_pass(const mp3b_batch *b) { return b ? b->Fc : 0; }
 
+// a call on a parent = the same call on every part, each on its own host thread; afterwards the parent carries the merged
+// measurement fields (stage times: the slowest device; launches: all of them)
+static int multi_call(mp3b_batch *b, const std::function<int(mp3b_batch *, int)> &fn) {
+  if (b->sticky) return fail(b->sticky, "batch is in a failed state");
+  const int rc = on_all_parts(b->workers, [&](int k) { return fn(b->parts[(size_t)k], b->part_lo[(size_t)k]); });
+  if (rc) { std::string keep = g_err; b->sticky = rc; g_err = keep; return rc; }
+  b->out_total = 0; b->launches = 0; b->passes = 0;
+  for (auto &m : b->stage_ms) m = 0.0f;
+  for (mp3b_batch *p : b->parts) {
+    b->out_total += p->out_total; b->launches += p->launches; b->passes = std::max(b->passes, p->passes);
+    for (int i = 0; i < MP3B_STAGE_COUNT; ++i) b->stage_ms[i] = std::max(b->stage_ms[i], p->stage_ms[i]);
+  }
+  return MP3B_OK;
+}
+
 int mp3b_batch_encode(mp3b_batch *b, const float *const *pcm, const size_t *n_floats, int flush, const uint8_t *flush_mask) {
+  if (is_multi(b)) return multi_call(b, [&](mp3b_batch *p, int lo) { return run_call(p, pcm ? pcm + lo : nullptr, n_floats ? n_floats + lo : nullptr, false, flush, flush_mask ? flush_mask + lo : nullptr, true); });
   return run_call(b, pcm, n_floats, false, flush, flush_mask, true);
 }
 int mp3b_batch_encode_strided(mp3b_batch *b, const float *base, size_t pitch_floats, const size_t *n_floats, int flush, const uint8_t *flush_mask) {
   if (!b || !base || !n_floats) return fail(MP3B_ERR_BAD_ARG, "null batch / base / n_floats");
+  if (is_multi(b)) return multi_call(b, [&](mp3b_batch *p, int lo) { return mp3b_batch_encode_strided(p, base + (size_t)lo * pitch_floats, pitch_floats, n_floats + lo, flush, flush_mask ? flush_mask + lo : nullptr); });
   std::vector<const float *> rows((size_t)b->S);
   for (int s = 0; s < b->S; ++s) {
     if (n_floats[s] > pitch_floats) return fail(MP3B_ERR_BAD_ARG, "stream %d: n_floats exceeds the row pitch", s);
@@ -652,29 +778,48 @@ int mp3b_batch_encode_strided(mp3b_batch *b, const float *base, size_t pitch_flo
   return run_call(b, rows.data(), n_floats, false, flush, flush_mask, true, pitch_floats);
 }
 int mp3b_batch_encode_i16(mp3b_batch *b, const int16_t *const *pcm, const size_t *n_samples, int flush, const uint8_t *flush_mask) {
+  if (is_multi(b)) return multi_call(b, [&](mp3b_batch *p, int lo) { return mp3b_batch_encode_i16(p, pcm ? pcm + lo : nullptr, n_samples ? n_samples + lo : nullptr, flush, flush_mask ? flush_mask + lo : nullptr); });
   return run_call(b, reinterpret_cast<const float *const *>(pcm), n_samples, false, flush, flush_mask, true, 0, 2);
 }
 int mp3b_batch_encode_device(mp3b_batch *b, const float *const *d_pcm, const size_t *n_floats, int flush, int download) {
+  // multi-device: d_pcm[i] must live on the device that owns stream i (mp3b_batch_stream_device)
+  if (is_multi(b)) return multi_call(b, [&](mp3b_batch *p, int lo) { return run_call(p, d_pcm ? d_pcm + lo : nullptr, n_floats ? n_floats + lo : nullptr, true, flush, nullptr, download != 0); });
   return run_call(b, d_pcm, n_floats, true, flush, nullptr, download != 0);
 }
 int mp3b_batch_output(const mp3b_batch *b, int stream, const uint8_t **data, size_t *len) {
   if (!b || stream < 0 || stream >= b->S || !data || !len) return fail(MP3B_ERR_BAD_ARG, "bad stream index or null pointer");
+  if (is_multi(b)) { int l; const mp3b_batch *p = part_of(b, stream, &l); return mp3b_batch_output(p, l, data, len); }
   if (!b->have_host_out) return fail(MP3B_ERR_BAD_ARG, "the last call did not download its output");
   *data = b->h_out ? b->h_out + (b->h_pitch ? (size_t)stream * b->h_pitch : (size_t)b->h_offsets[stream]) : nullptr; *len = b->out_len[stream];
   return MP3B_OK;
 }
 int mp3b_batch_output_device(const mp3b_batch *b, int stream, const uint8_t **d_data, size_t *len) {
   if (!b || stream < 0 || stream >= b->S || !d_data || !len) return fail(MP3B_ERR_BAD_ARG, "bad stream index or null pointer");
+  if (is_multi(b)) { int l; const mp3b_batch *p = part_of(b, stream, &l); return mp3b_batch_output_device(p, l, d_data, len); }
   *d_data = b->pb.out + (size_t)stream * b->pb.out_stride; *len = b->out_len[stream];
   return MP3B_OK;
 }
 size_t mp3b_batch_output_total(const mp3b_batch *b) { return b ? b->out_total : 0; }
 int mp3b_batch_xing_header(const mp3b_batch *b, int stream, uint8_t *out, size_t cap, size_t *written) {
   if (!b || stream < 0 || stream >= b->S) return fail(MP3B_ERR_BAD_ARG, "bad stream index");
+  if (is_multi(b)) { int l; const mp3b_batch *p = part_of(b, stream, &l); return xing_header(p, l, out, cap, written); }
   return xing_header(b, stream, out, cap, written);
 }
-uint32_t mp3b_batch_frame_count(const mp3b_batch *b, int stream) { return (b && stream >= 0 && stream < b->S) ? b->frame_count[stream] : 0; }
-uint32_t mp3b_batch_byte_count(const mp3b_batch *b, int stream) { return (b && stream >= 0 && stream < b->S) ? b->byte_count[stream] : 0; }
+uint32_t mp3b_batch_frame_count(const mp3b_batch *b, int stream) {
+  if (!b || stream < 0 || stream >= b->S) return 0;
+  if (is_multi(b)) { int l; const mp3b_batch *p = part_of(b, stream, &l); return p->frame_count[l]; }
+  return b->frame_count[stream];
+}
+uint32_t mp3b_batch_byte_count(const mp3b_batch *b, int stream) {
+  if (!b || stream < 0 || stream >= b->S) return 0;
+  if (is_multi(b)) { int l; const mp3b_batch *p = part_of(b, stream, &l); return p->byte_count[l]; }
+  return b->byte_count[stream];
+}
+int mp3b_batch_stream_device(const mp3b_batch *b, int stream) {
+  if (!b || stream < 0 || stream >= b->S) return fail(MP3B_ERR_BAD_ARG, "bad stream index");
+  if (is_multi(b)) { int l; return part_of(b, stream, &l)->device; }
+  return b->device;
+}
 
 // ---- session plane: a batch of one ------------------------------------------------------------------------
 int mp3b_session_create(const mp3b_options *opts, int device, mp3b_session **out) {
@@ -794,9 +939,14 @@ int mp3b_batch_stage_ms(const mp3b_batch *b, float *ms, int n) {
 }
 int mp3b_batch_launch_count(const mp3b_batch *b) { return b ? b->launches : 0; }
 int mp3b_batch_pass_count(const mp3b_batch *b) { return b ? b->passes : 0; }
-void *mp3b_batch_stream(const mp3b_batch *b) { return b ? (void *)b->st : nullptr; }
+void *mp3b_batch_stream(const mp3b_batch *b) { return !b ? nullptr : is_multi(b) ? (void *)b->parts[0]->st : (void *)b->st; }
 int mp3b_batch_reset(mp3b_batch *b) {
   if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");
+  if (is_multi(b)) {
+    const int rc = on_all_parts(b->workers, [&](int k) { return mp3b_batch_reset(b->parts[(size_t)k]); });
+    if (rc == MP3B_OK) { b->sticky = 0; b->out_total = 0; }
+    return rc;
+  }
   CU(cudaSetDevice(b->device));
   const size_t S = b->S;
   CU(cudaMemsetAsync(b->pb.state, 0, S * sizeof(StreamState), b->st));
@@ -819,6 +969,26 @@ int mp3b_batch_reset(mp3b_batch *b) {
 int mp3b_batch_clone(const mp3b_batch *src, mp3b_batch **out) {
   if (!src || !out) return fail(MP3B_ERR_BAD_ARG, "null batch / out");
   if (src->sticky) return fail(src->sticky, "cannot clone a batch in a failed state");
+  if (is_multi(src)) {                                            // part by part, each on a host thread of the clone
+    mp3b_batch *c = new mp3b_batch();
+    c->S = src->S; c->opt = src->opt; c->cfg = src->cfg; c->ch = src->ch; c->device = src->device; c->Fc = src->Fc; c->GC = src->GC;
+    c->max_frame_bytes = src->max_frame_bytes; c->part_lo = src->part_lo;
+    c->parts.assign(src->parts.size(), nullptr);
+    for (size_t k = 0; k < src->parts.size(); ++k) {
+      c->workers.emplace_back(new PartWorker());
+      c->workers.back()->th = std::thread(part_worker_main, c->workers.back().get());
+    }
+    const int rc = on_all_parts(c->workers, [&](int k) { return mp3b_batch_clone(src->parts[(size_t)k], &c->parts[(size_t)k]); });
+    if (rc) {
+      std::string keep = g_err;
+      c->parts.erase(std::remove(c->parts.begin(), c->parts.end(), nullptr), c->parts.end());
+      if (c->parts.empty()) { stop_workers(c->workers); delete c; } else free_batch(c);
+      g_err = keep;
+      return rc;
+    }
+    *out = c;
+    return MP3B_OK;
+  }
   mp3b_batch *b = nullptr;
   int rc = create_batch(&src->opt, src->S, src->device, src->Fc, &b);
   if (rc) return rc;
@@ -850,6 +1020,7 @@ int mp3b_session_clone(const mp3b_session *s, mp3b_session **out) {
 }
 int mp3b_batch_reset_stream(mp3b_batch *b, int stream) {
   if (!b || stream < 0 || stream >= b->S) return fail(MP3B_ERR_BAD_ARG, "bad batch / stream");
+  if (is_multi(b)) { int l; mp3b_batch *p = part_of(b, stream, &l); return mp3b_batch_reset_stream(p, l); }
   CU(cudaSetDevice(b->device));
   const size_t s = (size_t)stream, fsc2 = 2 * (size_t)b->cfg.fsc, ch = (size_t)b->cfg.channels;
   CU(cudaMemsetAsync(b->pb.state + s, 0, sizeof(StreamState), b->st));
@@ -860,18 +1031,26 @@ int mp3b_batch_reset_stream(mp3b_batch *b, int stream) {
   b->pending[s] = 0; b->out_len[s] = 0; b->frame_count[s] = 0; b->byte_count[s] = 0; b->frame_sizes[s].clear();
   return MP3B_OK;
 }
-int mp3b_batch_set_trace(mp3b_batch *b, int flags) { if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch"); b->trace = flags ? (flags | 8) : 0; return MP3B_OK; }
+int mp3b_batch_set_trace(mp3b_batch *b, int flags) {
+  if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");
+  for (mp3b_batch *p : b->parts) p->trace = flags ? (flags | 8) : 0;
+  b->trace = flags ? (flags | 8) : 0;
+  return MP3B_OK;
+}
 int mp3b_batch_trace_frames(const mp3b_batch *b, int stream) {
+  if (is_multi(b) && stream >= 0 && stream < b->S) { int l; const mp3b_batch *p = part_of(b, stream, &l); return mp3b_batch_trace_frames(p, l); }
   if (!b || stream < 0 || stream >= b->S || (size_t)stream >= b->tr_frames.size()) return 0;
   return (int)b->tr_frames[stream].size();
 }
 int mp3b_batch_trace_frame_records(const mp3b_batch *b, int stream, mp3b_frame_record *out, int cap) {
+  if (is_multi(b) && stream >= 0 && stream < b->S) { int l; const mp3b_batch *p = part_of(b, stream, &l); return mp3b_batch_trace_frame_records(p, l, out, cap); }
   int n = mp3b_batch_trace_frames(b, stream);
   if (n > cap) return fail(MP3B_ERR_BUFFER_TOO_SMALL, "need %d records", n);
   if (n) memcpy(out, b->tr_frames[stream].data(), (size_t)n * sizeof *out);
   return n;
 }
 int mp3b_batch_trace_gc_records(const mp3b_batch *b, int stream, mp3b_gc_record *out, int cap) {
+  if (is_multi(b) && stream >= 0 && stream < b->S) { int l; const mp3b_batch *p = part_of(b, stream, &l); return mp3b_batch_trace_gc_records(p, l, out, cap); }
   if (!b || stream < 0 || (size_t)stream >= b->tr_gc.size()) return 0;
   int n = (int)b->tr_gc[stream].size();
   if (n > cap) return fail(MP3B_ERR_BUFFER_TOO_SMALL, "need %d records", n);
@@ -879,6 +1058,7 @@ int mp3b_batch_trace_gc_records(const mp3b_batch *b, int stream, mp3b_gc_record 
   return n;
 }
 int mp3b_batch_trace_gc_array(const mp3b_batch *b, int stream, int kind, void *out, int cap_gc) {
+  if (is_multi(b) && stream >= 0 && stream < b->S) { int l; const mp3b_batch *p = part_of(b, stream, &l); return mp3b_batch_trace_gc_array(p, l, kind, out, cap_gc); }
   if (!b || stream < 0 || (size_t)stream >= b->tr_gc.size() || !out) return fail(MP3B_ERR_BAD_ARG, "bad stream or null out");
   const void *src; size_t elems;
   if (kind == 0) { src = b->tr_spec[stream].data(); elems = b->tr_spec[stream].size(); }

@@ -570,3 +570,43 @@ def test_encode_to_file_layout(mp3, orc, tmp_path):
     id3 = orc.id3_build(title="t", artist="a")
     assert data == id3 + rs.xing_header() + frames
     assert len(rs.xing_header()) == 417 == mp3.lib().mp3b_xing_frame_size(__import__("ctypes").byref(o._c()))
+
+
+def test_multi_device_batch_equals_single(mp3, orc):
+    """mp3b_batch_create_multi: the batch partitioned by stream over a device list (here the same GPU three times, plus GPUs 0
+    and 1 when the box has two): ragged streams fed in two calls and flushed give, stream for stream, the bytes of the
+    single-device batch and of the oracle; counters, Xing headers, reset, clone and the device plane route by global index."""
+    import ctypes as C
+    import torch
+    S = 11
+    pcms = [signals.sine_noise(0.25 + 0.07 * i, seed=900 + i, f_left=180.0 + 31 * i, f_right=333.0 + 17 * i) for i in range(S)]
+    pcms[4] = pcms[4][:0]                                            # an empty stream in the middle block
+    cut = [p.size // 3 for p in pcms]
+    single = mp3.EncoderBatch(_opts(mp3), S, 0, 6)
+    want = [a + z for a, z in zip(single.encode([p[:c] for p, c in zip(pcms, cut)]), single.encode([p[c:] for p, c in zip(pcms, cut)], flush=True))]
+    lists = [[0, 0, 0]] + ([[0, 1], [1, 0, 1]] if mp3.device_count() >= 2 else [])
+    for devices in lists:
+        m = mp3.EncoderBatch(_opts(mp3), S, frames_per_pass=6, devices=devices)
+        assert m.device_count == len(devices) and [m.stream_device(i) for i in (0, S - 1)] == [devices[0], devices[-1]]
+        got = [a + z for a, z in zip(m.encode([p[:c] for p, c in zip(pcms, cut)]), m.encode([p[c:] for p, c in zip(pcms, cut)], flush=True))]
+        assert got == want, devices
+        assert orc.compare_streams(pcms, got) == []
+        for i in range(S):
+            assert m.frame_count(i) == single.frame_count(i) and m.byte_count(i) == single.byte_count(i)
+            assert m.xing_header(i) == single.xing_header(i)
+        assert m.output_total == sum(len(z) for z in m.outputs())
+        # clone mid-stream, then both continue identically; reset gives fresh sessions
+        m.reset()
+        head = m.encode([p[:c] for p, c in zip(pcms, cut)])
+        c2 = m.clone()
+        assert c2.encode([p[c:] for p, c in zip(pcms, cut)], flush=True) == m.encode([p[c:] for p, c in zip(pcms, cut)], flush=True)
+        assert [a + z for a, z in zip(head, m.outputs())] == want
+        # device plane: every stream's PCM on the device that owns the stream
+        m.reset()
+        keep = [torch.from_numpy(p.copy()).to("cuda:%d" % m.stream_device(i)) if p.size else torch.zeros(1, device="cuda:%d" % m.stream_device(i)) for i, p in enumerate(pcms)]
+        for d in set(devices):
+            torch.cuda.synchronize(d)
+        m.encode_device((C.c_void_p * S)(*[t.data_ptr() for t in keep]), (C.c_size_t * S)(*[p.size for p in pcms]), flush=True, download=True)
+        assert m.outputs() == want
+        m.close(); c2.close()
+    single.close()

@@ -24,7 +24,7 @@ for r in rows[2:]:
     rd, wr = num(r, "dram__bytes_read.sum") * scale, num(r, "dram__bytes_write.sum") * scale
     out[stage_of[name]] = {
         "kernel": name, "gc_per_launch": gc, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_gc": (rd + wr) / gc,
-        "duration_us_under_ncu": num(r, "gpu__time_duration.sum"),
+        "duration_us_under_ncu": num(r, "gpu__time_duration.sum") * {"s": 1e6, "ms": 1e3, "us": 1.0, "ns": 1e-3}.get(rows[1][col["gpu__time_duration.sum"]], 1.0),
         "inst_executed": num(r, "smsp__inst_executed.sum"), "inst_executed_per_gc": (num(r, "smsp__inst_executed.sum") or 0) / gc,
         "dram_throughput_pct": num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
         "issue_active_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),

@@ -60,7 +60,8 @@ with open(os.path.join(P, TAG + "_filterbank_lds.txt"), "w") as f:
 for a, b in (("bench.json", TAG + "_bench.json"), ("bench_ref.json", TAG + "_bench_reference.json")):
     line = [l for l in open(os.path.join(G, a)) if l.startswith("{")][-1]
     json.dump(json.loads(line), open(os.path.join(P, b), "w"), indent=1)
-c5 = {"batch_call": json.loads([l for l in open(os.path.join(G, "c5.json")) if l.startswith("{")][-1])}
+bench_line = json.loads([l for l in open(os.path.join(G, "bench.json")) if l.startswith("{")][-1])
+c5 = {"batch_call": bench_line.get("other_configs", {}).get("c5")}       # the C5 leg of the default bench line
 if os.path.exists(os.path.join(G, "c5_pool.json")):
     c5["session_pool_1024_threads"] = json.loads([l for l in open(os.path.join(G, "c5_pool.json")) if l.startswith("{")][-1])
 json.dump(c5, open(os.path.join(P, TAG + "_config5.json"), "w"), indent=1)
