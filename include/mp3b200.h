@@ -142,6 +142,17 @@ int mp3b_batch_xing_header(const mp3b_batch *b, int stream, uint8_t *out, size_t
 uint32_t mp3b_batch_frame_count(const mp3b_batch *b, int stream);
 uint32_t mp3b_batch_byte_count(const mp3b_batch *b, int stream);
 
+/* ---- ISO mode (extension, default off: with it off every byte equals the reference's) ------------------------------------
+ * What north_star lists beyond the reference's live code — its dead stubs HuffmanEncoder.encode / writePair / selectTable
+ * (SRC:1740-1806) and Huffman tables 1-13 (SRC:2288-2398) — done the ISO 11172-3 way: the ISO quantizer law on the decoder's
+ * scale, global_gain by bit-count search, rzero / count1 / big_values partition, three regions with the cheapest of tables
+ * 1-3, 5-13, 15, 16-31 (linbits escapes) each, count1 table A or B, a real main_data_begin back pointer with stuffing, M/S
+ * signalled per frame with 1/sqrt(2) scaling, the ISO CRC.  An independent decoder then reconstructs the INPUT signal.  Long
+ * blocks only, no scalefactors / psychoacoustic model (next slice).  Only on fresh sessions (after create / reset). */
+int mp3b_batch_set_iso_mode(mp3b_batch *b, int on);
+int mp3b_batch_iso_mode(const mp3b_batch *b);
+int mp3b_session_set_iso_mode(mp3b_session *s, int on);
+
 /* ---- session pool: many threads, one step ------------------------------------------------------------- */
 /* n_sessions EncoderSessions (SRC:237-350) driven from concurrent threads — one blocking call per session at a time,
  * like N reference sessions on N threads — and advanced on the GPU together: the calls that arrive within max_wait_us of
@@ -194,6 +205,7 @@ typedef struct mp3b_gc_record {
   int32_t part23_length, big_values, global_gain, gain_used, block_type, subblock_gain[3];
   int32_t region0, region1, preflag, g0, max_bits, iterations;
   float energy;
+  int32_t table_select[3], count1table_select;   /* 15, 15, 15 and 0 unless ISO mode is on */
 } mp3b_gc_record;
 typedef struct mp3b_frame_record {
   int32_t bitrate_index, padding, frame_size, main_data_size, main_data_begin, reservoir_bits, huff_bytes, ms, is_final;

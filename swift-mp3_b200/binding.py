@@ -36,7 +36,8 @@ class _ID3(C.Structure):
 
 GC_RECORD = np.dtype([("part23_length", "<i4"), ("big_values", "<i4"), ("global_gain", "<i4"), ("gain_used", "<i4"),
                       ("block_type", "<i4"), ("subblock_gain", "<i4", 3), ("region0", "<i4"), ("region1", "<i4"),
-                      ("preflag", "<i4"), ("g0", "<i4"), ("max_bits", "<i4"), ("iterations", "<i4"), ("energy", "<f4")])
+                      ("preflag", "<i4"), ("g0", "<i4"), ("max_bits", "<i4"), ("iterations", "<i4"), ("energy", "<f4"),
+                      ("table_select", "<i4", 3), ("count1table_select", "<i4")])
 FRAME_RECORD = np.dtype([("bitrate_index", "<i4"), ("padding", "<i4"), ("frame_size", "<i4"), ("main_data_size", "<i4"),
                          ("main_data_begin", "<i4"), ("reservoir_bits", "<i4"), ("huff_bytes", "<i4"), ("ms", "<i4"),
                          ("is_final", "<i4"), ("frame_energy", "<f4")])
@@ -78,6 +79,7 @@ def lib():
         "mp3b_batch_create_ex": (i32, [C.POINTER(_Options), i32, i32, i32, C.POINTER(vp)]),
         "mp3b_batch_frames_per_pass": (i32, [vp]),
         "mp3b_batch_create_multi": (i32, [C.POINTER(_Options), i32, C.POINTER(i32), i32, i32, C.POINTER(vp)]),
+        "mp3b_batch_set_iso_mode": (i32, [vp, i32]), "mp3b_batch_iso_mode": (i32, [vp]), "mp3b_session_set_iso_mode": (i32, [vp, i32]),
         "mp3b_batch_device_count": (i32, [vp]), "mp3b_batch_stream_device": (i32, [vp, i32]),
         "mp3b_batch_destroy": (None, [vp]), "mp3b_batch_stream_count": (i32, [vp]),
         "mp3b_batch_encode": (i32, [vp, C.POINTER(vp), szp, i32, vp]),
@@ -224,6 +226,9 @@ class EncoderSession:
         _check(fn(self._h, *head, buf, cap, C.byref(n)))
         return bytes(memoryview(buf)[:n.value])
 
+    def set_iso_mode(self, on=True):
+        _check(lib().mp3b_session_set_iso_mode(self._h, int(on)))
+
     def clone(self):
         """`var copy = session`: an independent snapshot (the reference's EncoderSession is a value type)."""
         c = object.__new__(EncoderSession)
@@ -277,6 +282,10 @@ class EncoderBatch:
     @property
     def device_count(self):
         return lib().mp3b_batch_device_count(self._h)
+
+    def set_iso_mode(self, on=True):
+        """Opt-in ISO mode (include/mp3b200.h): ISO quantizer, table selection, count1, real main_data_begin."""
+        _check(lib().mp3b_batch_set_iso_mode(self._h, int(on)))
 
     def stream_device(self, stream):
         return _check(lib().mp3b_batch_stream_device(self._h, stream))

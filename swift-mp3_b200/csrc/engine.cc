@@ -188,6 +188,7 @@ int fill_config(const mp3b_options &o, int n_streams, Config &c) {
   if (o.mode == 0) { c.mode_bits = 3; c.mode_ext = 0; } else if (o.mode == 2) { c.mode_bits = 1; c.mode_ext = 2; } else { c.mode_bits = 0; c.mode_ext = 0; }
   c.cbr_index = bitrate_index(o.bitrate_kbps, o.sample_rate);
   c.f_one = 1.0f; c.f_neg0 = -0.0f;
+  c.iso = 0; c.ms_scale = 0.5f;                                  // SRC:2148-2154; mp3b_batch_set_iso_mode changes both
   for (int i = 0; i < 16; ++i) {
     long long num = 144LL * bitrate_value(i) * 1000;             // SRC:490-495
     c.frame_base[i] = (int)(num / o.sample_rate); c.frame_rem[i] = (int)(num % o.sample_rate);
@@ -509,10 +510,11 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
           for (int j = 0; j < ngc; ++j) {
             const GcSide &g = r.gc[j];
             mp3b_gc_record q{};
-            q.part23_length = g.part23; q.big_values = g.big_values; q.global_gain = g.global_gain; q.gain_used = g.gain_used;
+            q.part23_length = g.part23; q.big_values = g.big_values; q.global_gain = g.global_gain; q.gain_used = g.gain_used + g.pad;
             q.block_type = g.block_type; q.subblock_gain[0] = g.sbg[0]; q.subblock_gain[1] = g.sbg[1]; q.subblock_gain[2] = g.sbg[2];
             q.region0 = g.region0; q.region1 = g.region1; q.preflag = g.preflag; q.g0 = g.g0; q.max_bits = g.max_bits;
             q.iterations = g.iterations; q.energy = g.energy;
+            q.table_select[0] = g.tsel[0]; q.table_select[1] = g.tsel[1]; q.table_select[2] = g.tsel[2]; q.count1table_select = g.c1sel;
             b->tr_gc[s].push_back(q);
           }
         }
@@ -560,6 +562,7 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
     if (b->trace & 4) LAUNCH(launch_thresholds(cfg, pb, st));
     CU(cudaEventRecord(ev[4], st));
     LAUNCH(launch_scan(cfg, pb, st));
+    if (cfg.iso) LAUNCH(launch_clear_md(cfg, pb, st));             // stuffing bytes of the reservoir are never written: start from zeros
     CU(cudaEventRecord(ev[5], st));
     LAUNCH(launch_pack(cfg, pb, st));
     CU(cudaEventRecord(ev[6], st));
@@ -603,7 +606,7 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
   }
   b->out_total = 0;
   for (int s = 0; s < S; ++s) b->out_total += b->out_len[s];
-  if (err) { b->sticky = MP3B_ERR_INTERNAL; return fail(MP3B_ERR_INTERNAL, "engine limit exceeded (flags 0x%x: 1 curve, 2 main-data buffer, 4 output buffer, 8 backlog > %d bytes)", err, kMdCarryCap); }
+  if (err) { b->sticky = MP3B_ERR_INTERNAL; return fail(MP3B_ERR_INTERNAL, "engine limit exceeded (flags 0x%x: 1 curve, 2 main-data buffer, 4 output buffer, 8 backlog > %d bytes, 16 ISO-mode bit count mismatch)", err, kMdCarryCap); }
   if (progressive) {
     CU(cudaStreamSynchronize(b->st_d2h));
     b->h_pitch = b->pb.out_stride;
@@ -1004,7 +1007,7 @@ int mp3b_batch_clone(const mp3b_batch *src, mp3b_batch **out) {
   A(cudaMemcpyAsync(b->pb.md_carry, src->pb.md_carry, S * kMdCarryCap, cudaMemcpyDeviceToDevice, b->st));
   A(cudaStreamSynchronize(b->st));
   if (e != cudaSuccess) { free_batch(b); return fail(MP3B_ERR_CUDA, "clone failed: %s", cudaGetErrorString(e)); }
-  b->head_sel = src->head_sel;
+  b->head_sel = src->head_sel; b->cfg.iso = src->cfg.iso; b->cfg.ms_scale = src->cfg.ms_scale;
   b->pending = src->pending; b->frame_count = src->frame_count; b->byte_count = src->byte_count; b->frame_sizes = src->frame_sizes;
   b->trace = src->trace;
   *out = b;
@@ -1031,6 +1034,22 @@ int mp3b_batch_reset_stream(mp3b_batch *b, int stream) {
   b->pending[s] = 0; b->out_len[s] = 0; b->frame_count[s] = 0; b->byte_count[s] = 0; b->frame_sizes[s].clear();
   return MP3B_OK;
 }
+// Opt-in ISO mode (iso_mode.cuh).  Only on fresh sessions: the two modes do not share reservoir semantics.
+int mp3b_batch_set_iso_mode(mp3b_batch *b, int on) {
+  if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");
+  if (is_multi(b)) {
+    for (mp3b_batch *p : b->parts) { const int rc = mp3b_batch_set_iso_mode(p, on); if (rc) return rc; }
+    b->cfg.iso = on ? 1 : 0;
+    return MP3B_OK;
+  }
+  for (int s = 0; s < b->S; ++s)
+    if (b->pending[(size_t)s] || b->frame_count[(size_t)s]) return fail(MP3B_ERR_BAD_ARG, "iso mode can only be changed on fresh sessions (after create or reset)");
+  b->cfg.iso = on ? 1 : 0;
+  b->cfg.ms_scale = on ? 0.70710678118654752440f : 0.5f;
+  return MP3B_OK;
+}
+int mp3b_batch_iso_mode(const mp3b_batch *b) { return b ? b->cfg.iso : 0; }
+int mp3b_session_set_iso_mode(mp3b_session *s, int on) { return s ? mp3b_batch_set_iso_mode(s->b, on) : fail(MP3B_ERR_BAD_ARG, "null session"); }
 int mp3b_batch_set_trace(mp3b_batch *b, int flags) {
   if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");
   for (mp3b_batch *p : b->parts) p->trace = flags ? (flags | 8) : 0;

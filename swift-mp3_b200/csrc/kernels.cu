@@ -22,8 +22,12 @@ extern const float *host_inv_step();    // tables.cc
 extern const double *host_gain_thr();
 extern const int *host_sfb_cum();
 
+extern const float *host_inv_step_iso();
+cudaError_t upload_iso_tables(const float *inv_step_iso);   // iso_mode.cuh
+
 cudaError_t upload_tables() {
   cudaError_t e;
+  if ((e = upload_iso_tables(host_inv_step_iso()))) return e;
   if ((e = cudaMemcpyToSymbol(c_inv_step, host_inv_step(), sizeof(float) * 256))) return e;
   if ((e = cudaMemcpyToSymbol(c_gain_thr, host_gain_thr(), sizeof(double) * 256))) return e;
   if ((e = cudaMemcpyToSymbol(c_sfb_cum, host_sfb_cum(), sizeof(int) * 63))) return e;
@@ -106,6 +110,10 @@ __device__ __forceinline__ float div_exact(float a, float d, float r) {
   const float e = __fmaf_rn(d, q, -a);
   return __fmaf_rn(-e, r, q);
 }
+
+}  // namespace mp3b
+#include "iso_mode.cuh"   // opt-in ISO mode: quantizer, partition, table selection (needs the warp helpers above)
+namespace mp3b {
 
 // ------------------------------------------------------------------------------------------------------------
 // K0: pre-pass.  One warp per frame: frame energy (SRC:477), stereo decision (SRC:2140-2162), granule energies
@@ -376,7 +384,7 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
           const int fr = nrow >= 0 ? nrow / 1152 : -1;
           const bool ms = joint && (fr < 0 ? ms_prev != 0 : msrow[1 + fr] != 0);
           if (!ms) v = c == 0 ? l : rr;
-          else v = c == 0 ? __fmul_rn(__fadd_rn(l, rr), 0.5f) : __fmul_rn(__fsub_rn(l, rr), 0.5f);   // SRC:2148-2154
+          else v = c == 0 ? __fmul_rn(__fadd_rn(l, rr), cfg.ms_scale) : __fmul_rn(__fsub_rn(l, rr), cfg.ms_scale);   // SRC:2148-2154 (0.5; ISO mode: 1 / sqrt 2)
         }
         *dstp = v;
       }
@@ -557,8 +565,10 @@ __device__ __forceinline__ int lo_bits_of(const Config &cfg, int bri) {
 constexpr int kGranulePerWarp = 1;   // 4 measured slower (6.0 vs 5.7 ms): one granule-channel per warp keeps the tail short
 // TRACE: also leave the MDCT spectrum behind.  PRE: no k_prepass ran (CBR, not joint stereo, no trace: nothing but the block
 // type is needed from the PCM) — the warp reads its granule's 576 samples itself and decides the block type (SRC:1944-1968).
-template <bool TRACE, bool PRE> __global__ void __launch_bounds__(256, 4) k_granule(Config cfg, PassBuffers pb) {
-  __shared__ __align__(16) uint8_t len31[31 * 32];   // table-15 code length of a pair + its sign bits (SRC:828-853), indexed by quant30
+template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256, 4) k_granule(Config cfg, PassBuffers pb) {
+  __shared__ __align__(16) uint8_t len31[ISO ? 16 : 31 * 32];   // table-15 code length of a pair + its sign bits (SRC:828-853), indexed by quant30
+  __shared__ __align__(16) uint8_t iso_len[ISO ? (kHuffEntries + 15) / 16 * 16 : 16];   // ISO mode: all Huffman length tables
+  __shared__ uint8_t iso_c[ISO ? 8 : 1][ISO ? 288 : 1];
   __shared__ __align__(8) float smg[8][576];
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ch = cfg.channels, chs = ch - 1;         // channels = 1 or 2: / ch is >> chs
@@ -593,7 +603,8 @@ template <bool TRACE, bool PRE> __global__ void __launch_bounds__(256, 4) k_gran
     }
   }
   if (rep == 0) {
-    if (threadIdx.x < 31 * 32 / 4) reinterpret_cast<uint32_t *>(len31)[threadIdx.x] = reinterpret_cast<const uint32_t *>(tab::kLen31s)[threadIdx.x];
+    if (ISO) { for (int i = threadIdx.x; i < kHuffEntries; i += 256) iso_len[i] = kHuffLenFlat[i]; }
+    else if (threadIdx.x < 31 * 32 / 4) reinterpret_cast<uint32_t *>(len31)[threadIdx.x] = reinterpret_cast<const uint32_t *>(tab::kLen31s)[threadIdx.x];
     __syncthreads();
   }
   if (gci >= (int)pb.plan[s].n_frames * 2 * ch) return;
@@ -614,6 +625,9 @@ template <bool TRACE, bool PRE> __global__ void __launch_bounds__(256, 4) k_gran
       }
       transient_decide(e3, bt, sbg);
       if (lane == 0) pb.gc_bt[gslot] = (uint16_t)(bt | sbg[0] << 2 | sbg[1] << 5 | sbg[2] << 8);
+    } else if (ISO) {
+      bt = 0;                                                     // ISO mode: long blocks only (see iso_mode.cuh)
+      if (lane == 0) pb.gc_bt[gslot] = 0;
     } else bt = pb.gc_bt[gslot] & 3;
     float *X = smg[warp];
     const int sb = lane;
@@ -701,9 +715,49 @@ template <bool TRACE, bool PRE> __global__ void __launch_bounds__(256, 4) k_gran
   float mx[9], my[9];
 #pragma unroll
   for (int j = 0; j < 9; ++j) { float2 v = reinterpret_cast<const float2 *>(smg[warp])[lane + 32 * j]; mx[j] = v.x; my[j] = v.y; }
+  uint16_t *bits_out = pb.gc_bits + gslot * kMaxEntries, *bv_out = pb.gc_bv + gslot * kMaxEntries;
+  if (ISO) {
+    // global_gain search (north_star stage 4).  The bit count falls as the gain rises, so: binary search for the smallest gain
+    // that fits the LARGEST budget this frame can have (full reservoir, padded), then the curve gain by gain until the count
+    // fits the smallest (no reservoir, no padding); the serial scan, which knows the reservoir, picks the first entry that
+    // fits.  If the two are more than 18 steps apart, the last entry is the binary-searched gain of the smallest budget.
+    const int f2 = gci >> (chs + 1);
+    const int bri = pb.frame_br[(size_t)s * pb.Fc + f2];
+    const int mds1 = cfg.frame_base[bri] + 1 - cfg.header_bytes;
+    const int hi_bits = min(4095, (mds1 * 8 + (min(511, mds1) * 8 * 9) / 10) >> cfg.channels);
+    const int lo_fit = min(lo_bits, 4095);
+    const int *sfb = c_sfb_cum[cfg.sfb_index];
+    auto eval = [&](int G) {
+      const float inv = c_inv_step_iso[G];
+      int qx[9], qy[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) { qx[j] = iso_quant(mx[j], inv); qy[j] = iso_quant(my[j], inv); }
+      return iso_evaluate(qx, qy, lane, iso_len, iso_c[warp], sfb);
+    };
+    int lo = 0, hi = kIsoGainMax;                     // invariant: the count at `hi` fits (at kIsoGainMax every line quantizes to 0)
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (eval(mid).bits <= hi_bits) hi = mid; else lo = mid + 1; }
+    const int g_first = hi;
+    int n = 0, g_last = g_first, fitted = 0;
+    for (int e = 0; e < kMaxEntries - 1 && !fitted; ++e) {
+      const int G = min(g_first + e, kIsoGainMax);
+      const IsoChoice c = eval(G);
+      if (lane == 0) { bits_out[e] = (uint16_t)min(c.bits, 65535); bv_out[e] = (uint16_t)c.bv; }
+      n = e + 1; g_last = G;
+      fitted = c.bits <= lo_fit || G == kIsoGainMax;
+    }
+    if (!fitted) {
+      lo = min(g_first + kMaxEntries - 1, kIsoGainMax); hi = kIsoGainMax;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (eval(mid).bits <= lo_fit) hi = mid; else lo = mid + 1; }
+      const IsoChoice c = eval(hi);
+      if (lane == 0) { bits_out[kMaxEntries - 1] = (uint16_t)min(c.bits, 65535); bv_out[kMaxEntries - 1] = (uint16_t)c.bv; }
+      n = kMaxEntries; g_last = hi;
+    }
+    if (lane == 0) pb.gc_meta[gslot] = (uint32_t)g_first | (uint32_t)n << 9 | (uint32_t)g_last << 14;   // 9 + 5 + 9 bits
+    __syncwarp();
+    continue;
+  }
   const int g0 = meta & 255;
   int gain = g0, n = 0, restart = 0;
-  uint16_t *bits_out = pb.gc_bits + gslot * kMaxEntries, *bv_out = pb.gc_bv + gslot * kMaxEntries;
   for (int it = 0; it < kMaxEntries; ++it) {
     const float inv2 = __fmul_rn(c_inv_step[gain], 2.0f);
     int total = 0, last = 0;
@@ -800,8 +854,10 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
         pad_rem += cfg.frame_rem[bri];
         if (pad_rem >= cfg.sample_rate) { pad_rem -= cfg.sample_rate; padding = 1; }
         const int mds = cfg.frame_base[bri] + padding - cfg.header_bytes;   // SRC:497
-        const int mdb = is_final ? 0 : (int)min(W - R, 511u);        // SRC:499, 2099-2101
-        const int res_bits = is_final ? 0 : avail * 8;               // SRC:500
+        // ISO mode: `avail` IS the back pointer (start of this slot minus start of this frame's data; the stuffing below keeps
+        // the FIFO and the counter in step), and the final frame keeps its reservoir like any other
+        const int mdb = cfg.iso ? avail : is_final ? 0 : (int)min(W - R, 511u);        // SRC:499, 2099-2101
+        const int res_bits = (is_final && !cfg.iso) ? 0 : avail * 8; // SRC:500
         const int bpg = (mds * 8 + (res_bits * 9) / 10) >> ngc_shift;  // SRC:647-650: / (2 * channels)
         // every group of ngc lanes mirrors lanes 0..ngc-1 (lane L walks the curve of gc L mod ngc), so the butterfly below
         // leaves the frame's bit total in every lane without a broadcast
@@ -809,9 +865,18 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
         {
           const int j = lane & (ngc - 1);
           const uint32_t meta = sh_meta[l * ngc + j];
-          const int g0 = meta & 255, n = (meta >> 8) & 255, restart = (meta >> 16) & 1;
+          const int g0 = cfg.iso ? (int)(meta & 511u) : (int)(meta & 255u), n = cfg.iso ? (int)((meta >> 9) & 31u) : (int)((meta >> 8) & 255u);
+          const int restart = cfg.iso ? 0 : (int)((meta >> 16) & 1u);
           const uint16_t *cb = sh_bits + (l * ngc + j) * kMaxEntries;
           int gain = g0, chosen = n - 1, gain_out = g0, gain_used = g0, iters = n, bits = -1;
+          if (cfg.iso) {                                             // first entry whose count fits the budget and the 12-bit field
+            const int fit = min(bpg, 4095);
+            for (int e = 0; e < n; ++e) if ((int)cb[e] <= fit) { chosen = e; break; }
+            bits = cb[chosen]; iters = chosen + 1;
+            gain_used = chosen == kMaxEntries - 1 ? (int)((meta >> 14) & 511u) : min(g0 + chosen, kIsoGainMax);   // the search gain
+            gain_out = gain_used = min(gain_used, 255);              // what the side info can say (iso_mode.cuh)
+            if (bits > fit) err |= 1;
+          } else
           for (int e = 0; e < n; ++e) {                              // quantizeToFitBudget SRC:745-776
             gain_used = gain;
             if (e == 0 && restart) { gain = max(gain - 40, 0); continue; }
@@ -834,6 +899,10 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
         o.padding = padding; o.mdb = mdb; o.res_bits = res_bits; o.bpg = bpg; o.huff = huff; o.is_final = is_final;
         o.w_off = W;
         W += (uint32_t)huff;                                         // appendHuffmanData SRC:511
+        if (cfg.iso) {                                               // stuffing: the reservoir may hold 511 bytes (9-bit pointer) and,
+          const int over = avail + mds - huff - min(511, mds);       // with the one-frame delay of the FIFO, at most one slot
+          if (over > 0) W += (uint32_t)over;                         // (zero bytes after the frame's data: ancillary to a decoder)
+        }
         if (W > pb.md_stride) { err |= 2; W = (uint32_t)pb.md_stride; }
         o.e_take = 0xFFFFFFFFu; o.e_src = 0; o.e_out = 0;
         if (prev_slot >= 0) {                                        // emit the buffered frame, SRC:548-556 + fillSlot 2110-2121
@@ -847,6 +916,7 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
         prev_slot = mds;
         int a = avail + mds - huff;                                  // updateReservoir SRC:565, 2125-2128
         avail = a < 0 ? 0 : a > 511 ? 511 : a;
+        if (cfg.iso) avail = min(avail, mds);
       }
     }
     __syncwarp();
@@ -873,11 +943,17 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
         g.global_gain = sh_sel[lane * ngc + j][1]; g.gain_used = sh_sel[lane * ngc + j][2];
         const uint16_t btw = pb.gc_bt[gslot];
         g.block_type = btw & 3; g.sbg[0] = (btw >> 2) & 7; g.sbg[1] = (btw >> 5) & 7; g.sbg[2] = (btw >> 8) & 7;
-        int r0, r1; region_counts(cfg, bv, r0, r1);
-        g.region0 = (uint8_t)r0; g.region1 = (uint8_t)r1; g.preflag = (uint8_t)((meta >> 17) & 1); g.g0 = (uint8_t)(meta & 255);
+        int r0 = 0, r1 = 0;
+        if (!cfg.iso) region_counts(cfg, bv, r0, r1);                // ISO mode: k_pack_iso fills regions, table_select, count1table
+        g.region0 = (uint8_t)r0; g.region1 = (uint8_t)r1; g.preflag = cfg.iso ? 0 : (uint8_t)((meta >> 17) & 1); g.g0 = (uint8_t)(meta & 255);
         g.iterations = sh_sel[lane * ngc + j][3]; g.pad = 0; g.max_bits = (uint16_t)o.bpg;
+        g.tsel[0] = g.tsel[1] = g.tsel[2] = 15; g.c1sel = 0;
         g.energy = pb.gc_energy[(size_t)s * (10 + pb.GC) + 10 + gci];
-        pb.gc_sel[gslot] = (uint32_t)g.gain_used | (uint32_t)bv << 8;
+        if (cfg.iso) {                                                // the search gain (may exceed 255) | big_values << 9
+          const int G = chosen == kMaxEntries - 1 ? (int)((meta >> 14) & 511u) : min((int)(meta & 511u) + chosen, kIsoGainMax);
+          pb.gc_sel[gslot] = (uint32_t)G | (uint32_t)bv << 9;
+          g.g0 = (uint8_t)min((int)(meta & 511u), 255); g.pad = (uint8_t)max(G - 255, 0);   // trace: gain_used + pad = the search gain
+        } else pb.gc_sel[gslot] = (uint32_t)g.gain_used | (uint32_t)bv << 8;
         pb.gc_bitoff[gslot] = (uint32_t)total;
         total += bits;
       }
@@ -1002,6 +1078,129 @@ template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// K5 in ISO mode (north_star stage 5; supersedes the reference's dead HuffmanEncoder.encode / writePair / selectTable,
+// SRC:1740-1806): the frame's granule-channels are quantized with the ISO law at the gain the scan chose, partitioned and
+// table-selected by the same iso_evaluate the curve used (so the bit count is the one the scan budgeted — checked), then coded:
+// big_values pairs with the region's table (+ linbits escapes, + sign bits), count1 quadruples with table A or B.  One warp per
+// frame; lane L codes pairs 9L...9L+8 and quadruples 5L...5L+4, bit positions from warp prefix sums.  The choices (regions,
+// table_select, count1table_select, big_values) go into the frame record for k_frames' side info.
+__device__ __forceinline__ void put_bits64(uint32_t *buf, uint32_t pos, unsigned long long v, int len) {   // len in 1...64, MSB first
+  const unsigned long long top = v << (64 - len);
+  const uint32_t w = pos >> 5, off = pos & 31;
+  const uint32_t a = (uint32_t)(top >> (32 + off)), b = (uint32_t)(top >> off), c = off ? (uint32_t)(top << (32 - off)) : 0u;
+  if (a) atomicOr(&buf[w], a);
+  if (b) atomicOr(&buf[w + 1], b);
+  if (c) atomicOr(&buf[w + 2], c);
+}
+template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta) k_pack_iso(Config cfg, PassBuffers pb) {
+  __shared__ uint32_t bufs[kPackFramesPerCta][552];
+  __shared__ uint32_t s_huff[kHuffEntries];
+  __shared__ __align__(16) uint8_t s_len[(kHuffEntries + 15) / 16 * 16];
+  __shared__ int16_t s_ix[kPackFramesPerCta][576];
+  __shared__ uint8_t s_c[kPackFramesPerCta][288];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ch = cfg.channels, ngc = 2 * ch;
+  const int f = blockIdx.y * kPackFramesPerCta + warp;
+  const int nfr = (int)pb.plan[s].n_frames;
+  const bool active = f < nfr;
+  for (int i = tid; i < kHuffEntries; i += 32 * kPackFramesPerCta) { s_huff[i] = kHuffPacked[i]; s_len[i] = kHuffLenFlat[i]; }
+  uint32_t *buf = bufs[warp];
+  for (int i = lane; i < 552; i += 32) buf[i] = 0;
+  __syncthreads();
+  if (!active) return;
+  const int *sfb = c_sfb_cum[cfg.sfb_index];
+  FrameRec &fr = pb.rec[(size_t)s * (pb.Fc + 1) + 1 + f];
+  for (int g = 0; g < ngc; ++g) {
+    const size_t gslot = (size_t)s * pb.GC + (size_t)f * ngc + g;
+    const uint32_t sel = pb.gc_sel[gslot], bitoff = pb.gc_bitoff[gslot];
+    const float inv = c_inv_step_iso[sel & 511u];
+    const float2 *sm2 = reinterpret_cast<const float2 *>(pb.smag + gslot * 576);
+    int qx[9], qy[9];
+    int16_t *ix = s_ix[warp];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int p = lane + 32 * j;
+      const float2 v = __ldg(sm2 + p);
+      qx[j] = iso_quant(fabsf(v.x), inv); qy[j] = iso_quant(fabsf(v.y), inv);
+      ix[2 * p] = (int16_t)(v.x < 0.0f ? -qx[j] : qx[j]); ix[2 * p + 1] = (int16_t)(v.y < 0.0f ? -qy[j] : qy[j]);
+      if (TRACE) { pb.tr_ix[gslot * 576 + 2 * p] = ix[2 * p]; pb.tr_ix[gslot * 576 + 2 * p + 1] = ix[2 * p + 1]; }
+    }
+    const IsoChoice c = iso_evaluate(qx, qy, lane, s_len, s_c[warp], sfb);
+    __syncwarp();
+    if (lane == 0) {
+      GcSide &gs = fr.gc[g];
+      if (c.bits != (int)gs.part23) atomicOr(&pb.state[s].error, 16);          // the curve and the packer must agree bit for bit
+      gs.big_values = (uint16_t)c.bv; gs.region0 = (uint8_t)c.r0; gs.region1 = (uint8_t)c.r1;
+      gs.tsel[0] = (uint8_t)c.tsel[0]; gs.tsel[1] = (uint8_t)c.tsel[1]; gs.tsel[2] = (uint8_t)c.tsel[2]; gs.c1sel = (uint8_t)c.c1sel;
+      if (f == nfr - 1 && pb.state[s].buffered.valid) {             // the scan has already parked this frame as bufferedFrame
+        GcSide &bs = pb.state[s].buffered.gc[g];
+        bs.big_values = gs.big_values; bs.region0 = gs.region0; bs.region1 = gs.region1;
+        bs.tsel[0] = gs.tsel[0]; bs.tsel[1] = gs.tsel[1]; bs.tsel[2] = gs.tsel[2]; bs.c1sel = gs.c1sel;
+      }
+    }
+    // ---- big_values: lane L codes pairs 9L ... 9L+8
+    const uint32_t d0 = iso_desc(c.tsel[0]), d1 = iso_desc(c.tsel[1]), d2 = iso_desc(c.tsel[2]);
+    unsigned long long val[9]; int len[9]; int mine = 0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int p = 9 * lane + j;
+      val[j] = 0ull; len[j] = 0;
+      if (p < c.bv) {
+        const int x = ix[2 * p], y = ix[2 * p + 1], ax = abs(x), ay = abs(y);
+        const uint32_t dk = 2 * p < c.a1 ? d0 : 2 * p < c.a2 ? d1 : d2;
+        const int dim = (int)((dk >> 16) & 255u), lb = (int)((dk >> 24) & 255u);
+        if (dim) {                                                  // (table 0: the region is all zero, nothing is coded)
+          const uint32_t e = s_huff[(dk & 0xFFFFu) + min(ax, 15) * dim + min(ay, 15)];
+          unsigned long long w = e & 0xFFFFFFu; int l = (int)(e >> 24);
+          if (lb && ax >= 15) { w = w << lb | (unsigned long long)(ax - 15); l += lb; }
+          if (ax) { w = w << 1 | (unsigned long long)(x < 0); ++l; }
+          if (lb && ay >= 15) { w = w << lb | (unsigned long long)(ay - 15); l += lb; }
+          if (ay) { w = w << 1 | (unsigned long long)(y < 0); ++l; }
+          val[j] = w; len[j] = l;
+        }
+      }
+      mine += len[j];
+    }
+    int incl = mine;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, dlt); if (lane >= dlt) incl += t; }
+    const int big_total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t pos = bitoff + (uint32_t)(incl - mine);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) if (len[j]) { put_bits64(buf, pos, val[j], len[j]); pos += len[j]; }
+    // ---- count1: lane L codes quadruples 5L ... 5L+4 (at most 144 of them)
+    uint32_t qv[5]; int ql[5]; int qmine = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int k = 5 * lane + i;
+      qv[i] = 0; ql[i] = 0;
+      if (k < c.c1) {
+        const int16_t *q4 = ix + 2 * c.bv + 4 * k;
+        const int idx = (q4[0] != 0) << 3 | (q4[1] != 0) << 2 | (q4[2] != 0) << 1 | (q4[3] != 0);
+        uint32_t w = c.c1sel ? (uint32_t)(15 - idx) : (uint32_t)((kQuadCodeAPacked >> (4 * idx)) & 15ull);
+        int l = c.c1sel ? 4 : quad_len_a(idx);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) if (q4[m]) { w = w << 1 | (uint32_t)(q4[m] < 0); ++l; }
+        qv[i] = w; ql[i] = l;
+      }
+      qmine += ql[i];
+    }
+    int qincl = qmine;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) { int t = __shfl_up_sync(0xffffffffu, qincl, dlt); if (lane >= dlt) qincl += t; }
+    pos = bitoff + (uint32_t)big_total + (uint32_t)(qincl - qmine);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) if (ql[i]) { put_bits64(buf, pos, qv[i], ql[i]); pos += ql[i]; }
+    __syncwarp();
+  }
+  __syncwarp();
+  const uint32_t off = pb.fr_md[((size_t)s * pb.Fc + f) * 2], nbytes = pb.fr_md[((size_t)s * pb.Fc + f) * 2 + 1];
+  uint8_t *dst = pb.md + (size_t)s * pb.md_stride + off;
+  if (off + nbytes <= pb.md_stride && nbytes <= 552 * 4 - 8)
+    for (uint32_t i = lane; i < nbytes; i += 32) dst[i] = (uint8_t)(buf[i >> 2] >> (24 - 8 * (i & 3)));
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // K_frames: header (SRC:522-544) + side info (SRC:571-625) + slot fill (SRC:2110-2121).  One warp per frame slot.
 struct BitW {   // MSB-first writer into a byte array (BitstreamWriter SRC:2230-2252), single thread
   uint8_t *p; int n; uint32_t acc; int nb;
@@ -1046,13 +1245,16 @@ __global__ void __launch_bounds__(128) k_frames(Config cfg, PassBuffers pb) {
       unsigned long long mid;                                                         // 22 bits at 3
       if (ws) mid = (unsigned long long)(g.block_type & 3) << 20 | (unsigned long long)(g.block_type == 1) << 19 | 15ull << 14 | 15ull << 9 |
                     (unsigned long long)(g.sbg[0] & 7) << 6 | (unsigned long long)(g.sbg[1] & 7) << 3 | (unsigned long long)(g.sbg[2] & 7);
-      else mid = 15ull << 17 | 15ull << 12 | 15ull << 7 | (unsigned long long)(g.region0 & 15) << 3 | (unsigned long long)(g.region1 & 7);
-      v |= mid << 3 | (unsigned long long)(g.preflag & 1) << 2;                       // scalefac_scale = count1table_select = 0
+      else mid = (unsigned long long)(g.tsel[0] & 31) << 17 | (unsigned long long)(g.tsel[1] & 31) << 12 | (unsigned long long)(g.tsel[2] & 31) << 7 |
+                 (unsigned long long)(g.region0 & 15) << 3 | (unsigned long long)(g.region1 & 7);   // table_select = 15, 15, 15 outside ISO mode (SRC:717)
+      v |= mid << 3 | (unsigned long long)(g.preflag & 1) << 2 | (unsigned long long)(g.c1sel & 1);   // scalefac_scale = 0; count1table_select = 0 outside ISO mode
       c = 59; o = 32 + crc_bits + prefix_bits + 59 * lane;
     } else if (lane == 4) {                                                           // header SRC:522-536, CRC SRC:538-543
       uint32_t h = 0x7FFu;
       h = h << 2 | 3u; h = h << 2 | 1u; h = h << 1 | (cfg.crc ? 0u : 1u); h = h << 4 | (fr.br_index & 15u); h = h << 2 | (uint32_t)cfg.sr_index;
-      h = h << 1 | (fr.padding & 1u); h = h << 1; h = h << 2 | (uint32_t)cfg.mode_bits; h = h << 2 | (uint32_t)cfg.mode_ext;
+      // mode_extension: the reference writes 0b10 on every joint-stereo frame; ISO mode signals M/S per frame
+      const uint32_t mode_ext = cfg.iso ? (cfg.mode == 2 && fr.ms ? 2u : 0u) : (uint32_t)cfg.mode_ext;
+      h = h << 1 | (fr.padding & 1u); h = h << 1; h = h << 2 | (uint32_t)cfg.mode_bits; h = h << 2 | mode_ext;
       h = h << 1 | (cfg.copyright ? 1u : 0u); h = h << 1 | (cfg.original ? 1u : 0u); h = h << 2;
       v = h; c = 32; o = 0;
       if (cfg.crc) {
@@ -1071,6 +1273,14 @@ __global__ void __launch_bounds__(128) k_frames(Config cfg, PassBuffers pb) {
       if (b2) atomicOr(&hw[w + 1], b2);
       if (d) atomicOr(&hw[w + 2], d);
     }
+  }
+  __syncwarp();
+  if (cfg.iso && cfg.crc && lane == 0) {                         // ISO 11172-3 CRC: header bytes 2-3 and the side info (the reference: the 4 header bytes)
+    uint8_t bytes[2 + 32];
+    bytes[0] = (uint8_t)(hw[0] >> 8); bytes[1] = (uint8_t)hw[0];
+    for (int i = 0; i < cfg.side_bytes; ++i) { const int k = 6 + i; bytes[2 + i] = (uint8_t)(hw[k >> 2] >> (24 - 8 * (k & 3))); }
+    const uint32_t crc = crc16_mpeg(bytes, 2 + cfg.side_bytes);
+    hw[1] = (hw[1] & 0x0000FFFFu) | crc << 16;
   }
   __syncwarp();
   uint8_t *dst = pb.out + (size_t)s * pb.out_stride + em.out_off;
@@ -1350,19 +1560,28 @@ int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
 int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st, bool fused_prepass) {
   if (pb.max_frames <= 0) return 0;
   dim3 grid(cfg.n_streams, (pb.max_frames * 2 * cfg.channels + 8 * kGranulePerWarp - 1) / (8 * kGranulePerWarp));
-  if (pb.spec) k_granule<true, false><<<grid, 256, 0, st>>>(cfg, pb);
-  else if (fused_prepass) k_granule<false, true><<<grid, 256, 0, st>>>(cfg, pb);
-  else k_granule<false, false><<<grid, 256, 0, st>>>(cfg, pb);
+  if (cfg.iso) { if (pb.spec) k_granule<true, false, true><<<grid, 256, 0, st>>>(cfg, pb); else k_granule<false, false, true><<<grid, 256, 0, st>>>(cfg, pb); }
+  else if (pb.spec) k_granule<true, false, false><<<grid, 256, 0, st>>>(cfg, pb);
+  else if (fused_prepass) k_granule<false, true, false><<<grid, 256, 0, st>>>(cfg, pb);
+  else k_granule<false, false, false><<<grid, 256, 0, st>>>(cfg, pb);
   return check(1);
 }
 int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   k_scan<<<cfg.n_streams, 32, 0, st>>>(cfg, pb);
   return check(1);
 }
+int launch_clear_md(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(pb.md, 0, (size_t)cfg.n_streams * pb.md_stride + 16, st);
+  return e == cudaSuccess ? 0 : -(int)e;
+}
 int launch_pack(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   if (pb.max_frames <= 0) return 0;
   dim3 grid(cfg.n_streams, (pb.max_frames + kPackFramesPerCta - 1) / kPackFramesPerCta);
   const int nt = 32 * kPackFramesPerCta;
+  if (cfg.iso) {
+    if (pb.tr_ix) k_pack_iso<true><<<grid, nt, 0, st>>>(cfg, pb); else k_pack_iso<false><<<grid, nt, 0, st>>>(cfg, pb);
+    return check(1);
+  }
   if (pb.tr_ix) k_pack<true><<<grid, nt, 0, st>>>(cfg, pb); else k_pack<false><<<grid, nt, 0, st>>>(cfg, pb);
   return check(1);
 }

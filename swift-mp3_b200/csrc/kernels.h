@@ -21,6 +21,8 @@ struct Config {              // constant for the lifetime of a batch; passed to 
   int sr_index, sfb_index, side_bytes, header_bytes /* 4 + crc + side */;
   int mode_bits, mode_ext, cbr_index;
   float f_one, f_neg0;                // 1.0f and -0.0f as run-time values (see k_spectrum phase A)
+  int iso;                            // opt-in ISO mode (iso_mode.cuh): ISO quantizer, table selection, count1, real main_data_begin
+  float ms_scale;                     // mid / side = (L +- R) * ms_scale: 0.5 like the reference (SRC:2148-2154), 1/sqrt(2) in ISO mode
   int frame_base[16], frame_rem[16];  // 144*kbps*1000 / sr and % sr per bitrate index
   uint8_t vbr_idx_of_kbps[324];       // bitrateIndex(kbps) for every VBR target 0...320
 };
@@ -41,9 +43,10 @@ struct GcSide {              // side-info fields of one gc (GranuleInfo, SRC:207
   uint8_t global_gain, gain_used;
   uint8_t block_type;        // 0 long, 1 mixed, 2 short (raw values SRC:1923-1927)
   uint8_t sbg[3];
-  uint8_t region0, region1, preflag, g0, iterations, pad;
+  uint8_t region0, region1, preflag, g0, iterations, pad;   // pad: ISO mode, search gain above 255 (gain_used + pad = the gain that quantized)
   uint16_t max_bits;
   float energy;
+  uint8_t tsel[3], c1sel;    // ISO mode: table_select per region, count1table_select (the reference writes 15, 15, 15 and 0)
 };
 struct FrameRec {            // everything needed to emit a frame later (one-frame delay, SRC:546-562)
   uint8_t valid, br_index, padding, ms;
@@ -87,7 +90,7 @@ struct PassBuffers {         // device arrays for one pass; Fc = frame capacity 
   int sub_rows;              // 18 * (1 + 2 * Fc)
   float *spec;               // [S][GC][576] MDCT spectrum — trace plane only (nullptr otherwise)
   float *smag;               // [S][GC][576] sign(x) * |x|^0.75 (K4 output, K5 input)
-  uint32_t *gc_meta;         // [S][GC] g0 | n_entries<<8 | restart<<16 | preflag<<17
+  uint32_t *gc_meta;         // [S][GC] g0 | n_entries<<8 | restart<<16 | preflag<<17   (ISO mode: first gain | n_entries<<8 | gain of entry 19<<24)
   uint16_t *gc_bits;         // [S][GC][20]
   uint16_t *gc_bv;           // [S][GC][20]
   uint32_t *gc_bitoff;       // [S][GC] bit offset inside the frame's main data
@@ -114,6 +117,8 @@ cudaError_t upload_tables();   // __constant__ tables for the current device
 int launch_prepass(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st, bool fused_prepass);   // fused_prepass: launch_prepass did not run
+// ISO mode: the main-data FIFO of a pass must start out zeroed (stuffing bytes are never written)
+int launch_clear_md(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_pack(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_frames(const Config &cfg, const PassBuffers &pb, cudaStream_t st);

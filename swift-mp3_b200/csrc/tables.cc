@@ -8,7 +8,7 @@
 
 namespace mp3b {
 
-static float g_inv_step[256];
+static float g_inv_step[256], g_inv_step_iso[320];
 static double g_gain_thr[256];
 static int g_sfb_cum[3][21];
 static std::once_flag g_once;
@@ -20,10 +20,14 @@ static void build() {
     float step = (float)(p > 0.0001 ? p : 0.0001);
     g_inv_step[g] = 1.0f / step;
   }
+  // ISO mode: ix = nint((|xr| * 32768 / 2^((G - 210) / 4))^0.75 - 0.0946) for the written global_gain G (the decoder's PCM scale
+  // is 32768 times the [-1, 1] floats the encoder is fed), i.e. |xr|^0.75 * 2^((180 - 3 (G - 210)) / 16); 320 entries: iso_mode.cuh
+  for (int g = 0; g < 320; ++g) g_inv_step_iso[g] = (float)std::pow(2.0, (180.0 - 3.0 * (double)(g - 210)) / 16.0);
   for (int r = 0; r < 3; ++r) { int c = 0; for (int i = 0; i < 21; ++i) { c += tab::kSfbLong[r][i]; g_sfb_cum[r][i] = c; } }
 }
 
 const float *host_inv_step() { std::call_once(g_once, build); return g_inv_step; }
+const float *host_inv_step_iso() { std::call_once(g_once, build); return g_inv_step_iso; }
 const double *host_gain_thr() { std::call_once(g_once, build); return g_gain_thr; }
 const uint8_t *host_len15() { return tab::kHuff15Len; }
 const uint8_t *host_code15() { return tab::kHuff15Code; }

@@ -7,6 +7,7 @@
 namespace mp3b {
 
 const float *host_inv_step();   // [256] 1 / Float(max(2^((g-210)/4), 1e-4)), SRC:798-800
+const float *host_inv_step_iso();   // [320] ISO-mode quantizer scale per search gain (iso_mode.cuh)
 const double *host_gain_thr();  // [256] 2^((g-210)/4): thresholds that replace log2 in computeGlobalGain (SRC:1004)
 const int *host_sfb_cum();      // [3][21] cumulative long sfb widths for 44.1 / 48 / 32 kHz, SRC:1814-1820
 

