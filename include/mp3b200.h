@@ -148,7 +148,12 @@ uint32_t mp3b_batch_byte_count(const mp3b_batch *b, int stream);
  * scale, global_gain by bit-count search, rzero / count1 / big_values partition, three regions with the cheapest of tables
  * 1-3, 5-13, 15, 16-31 (linbits escapes) each, count1 table A or B, a real main_data_begin back pointer with stuffing, M/S
  * signalled per frame with 1/sqrt(2) scaling, the ISO CRC.  An independent decoder then reconstructs the INPUT signal.  Long
- * blocks only, no scalefactors / psychoacoustic model (next slice).  Only on fresh sessions (after create / reset). */
+ * blocks only.  Only on fresh sessions (after create / reset).
+ * on = 2 adds north_star stages (3) and (4) in full (csrc/iso_psy.cuh; the reference's stubs: ScaleFactorBands.scale SRC:1831-1876,
+ * ScaleFactorCompression SRC:2017-2037, its unused masking thresholds SRC:1983-2013): a psychoacoustic model batched over
+ * granule-channels — 1024-point FFT line energies, 256-point FFT unpredictability, 1/3-Bark partitions, spreading function,
+ * tonality, masking thresholds, perceptual entropy — and the scalefactor outer loop (noise per band against the threshold,
+ * amplification, scalefac_compress, part2 bits); the perceptual entropy steers each granule's share of the bit reservoir. */
 int mp3b_batch_set_iso_mode(mp3b_batch *b, int on);
 int mp3b_batch_iso_mode(const mp3b_batch *b);
 int mp3b_session_set_iso_mode(mp3b_session *s, int on);
@@ -206,6 +211,7 @@ typedef struct mp3b_gc_record {
   int32_t region0, region1, preflag, g0, max_bits, iterations;
   float energy;
   int32_t table_select[3], count1table_select;   /* 15, 15, 15 and 0 unless ISO mode is on */
+  int32_t scalefac_compress, part2_length;       /* 0 and 0 unless ISO mode level 2 is on (part23_length includes part2_length) */
 } mp3b_gc_record;
 typedef struct mp3b_frame_record {
   int32_t bitrate_index, padding, frame_size, main_data_size, main_data_begin, reservoir_bits, huff_bytes, ms, is_final;
@@ -215,7 +221,10 @@ typedef struct mp3b_frame_record {
 int mp3b_batch_trace_frames(const mp3b_batch *b, int stream);
 int mp3b_batch_trace_frame_records(const mp3b_batch *b, int stream, mp3b_frame_record *out, int cap);
 int mp3b_batch_trace_gc_records(const mp3b_batch *b, int stream, mp3b_gc_record *out, int cap);
-/* kind: 0 spectrum f32[576], 1 ix i32[576], 2 thresholds f32[576]; out holds cap_gc * 576 elements. */
+/* kind: 0 spectrum f32[576], 1 ix i32[576], 2 thresholds f32[576]; out holds cap_gc * 576 elements.
+ * ISO mode level 2: kind 3 = psychoacoustic record f32[24] (threshold / energy of the 22 long scalefactor bands, perceptual
+ * entropy, mean tonality), kind 4 = scalefactor record i32[24] (21 scalefactors, scalefac_compress, part2 bits, bands left
+ * over their threshold | outer iterations << 4); out holds cap_gc * 24 elements. */
 int mp3b_batch_trace_gc_array(const mp3b_batch *b, int stream, int kind, void *out, int cap_gc);
 /* Product tables for cross-checks against the oracle / the reference literals.
  * which: 0 window[512] f32, 1 analysis[32*64] f32, 2 mdct_long[18*36] f32, 3 mdct_short[6*12] f32,

@@ -37,7 +37,7 @@ class _ID3(C.Structure):
 GC_RECORD = np.dtype([("part23_length", "<i4"), ("big_values", "<i4"), ("global_gain", "<i4"), ("gain_used", "<i4"),
                       ("block_type", "<i4"), ("subblock_gain", "<i4", 3), ("region0", "<i4"), ("region1", "<i4"),
                       ("preflag", "<i4"), ("g0", "<i4"), ("max_bits", "<i4"), ("iterations", "<i4"), ("energy", "<f4"),
-                      ("table_select", "<i4", 3), ("count1table_select", "<i4")])
+                      ("table_select", "<i4", 3), ("count1table_select", "<i4"), ("scalefac_compress", "<i4"), ("part2_length", "<i4")])
 FRAME_RECORD = np.dtype([("bitrate_index", "<i4"), ("padding", "<i4"), ("frame_size", "<i4"), ("main_data_size", "<i4"),
                          ("main_data_begin", "<i4"), ("reservoir_bits", "<i4"), ("huff_bytes", "<i4"), ("ms", "<i4"),
                          ("is_final", "<i4"), ("frame_energy", "<f4")])
@@ -412,9 +412,9 @@ class EncoderBatch:
         return out
 
     def trace_array(self, stream, kind):
-        k = {"spectrum": 0, "ix": 1, "thresholds": 2}[kind]
+        k = {"spectrum": 0, "ix": 1, "thresholds": 2, "psy": 3, "scalefactors": 4}[kind]
         n = lib().mp3b_batch_trace_frames(self._h, stream) * 2 * self.options.channels
-        out = np.zeros((n, 576), dtype="<i4" if k == 1 else "<f4")
+        out = np.zeros((n, 576 if k < 3 else 24), dtype="<i4" if k in (1, 4) else "<f4")
         _check(lib().mp3b_batch_trace_gc_array(self._h, stream, k, out.ctypes.data, n))
         return out
 

@@ -2,6 +2,7 @@
 // SRC = Sources/SwiftMP3/MP3Encoder.swift of the reference.  There is no CPU fallback anywhere in this file: every
 // encode call runs the CUDA pipeline of kernels.cu, and creation fails when no sm_100 device is usable.
 #include <algorithm>
+#include <cmath>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -110,8 +111,9 @@ struct mp3b_batch {
   int trace = 0;
   std::vector<std::vector<mp3b_frame_record>> tr_frames;
   std::vector<std::vector<mp3b_gc_record>> tr_gc;
-  std::vector<std::vector<float>> tr_spec, tr_thr;
-  std::vector<std::vector<int32_t>> tr_ix;
+  std::vector<std::vector<float>> tr_spec, tr_thr, tr_psy;
+  std::vector<std::vector<int32_t>> tr_ix, tr_sf;
+  PsyTab *d_psy = nullptr;                               // ISO mode level 2
   std::vector<FrameRec> h_rec;
 };
 
@@ -230,7 +232,7 @@ void free_batch(mp3b_batch *b) {
   PassBuffers &p = b->pb;
   void *dev[] = {p.plan, p.state, b->d_head[0], b->d_head[1], p.ms, p.frame_energy, p.gc_energy, p.gc_bt, p.frame_br, p.spec, p.sub, p.smag,
                  p.gc_meta, p.gc_bits, p.gc_bv, p.gc_bitoff, p.gc_sel, p.fr_md, p.rec, p.emit, p.md, p.md_tail, p.md_carry, p.out,
-                 p.emit_size, p.emit_n, p.tr_ix, p.tr_thr, b->d_stage[0], b->d_stage[1], b->d_stage16[0], b->d_stage16[1], b->d_plan[1], b->d_offsets, b->d_compact};
+                 p.emit_size, p.emit_n, p.tr_ix, p.tr_thr, p.gc_psy, p.gc_sf, b->d_psy, b->d_stage[0], b->d_stage[1], b->d_stage16[0], b->d_stage16[1], b->d_plan[1], b->d_offsets, b->d_compact};
   for (void *q : dev) if (q) cudaFree(q);
   void *host[] = {b->h_plan, b->h_state, b->h_emit_size, b->h_emit_n, b->h_offsets, b->h_out};
   for (void *q : host) if (q) cudaFreeHost(q);
@@ -317,6 +319,71 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   return MP3B_OK;
 }
 
+// Tables of the psychoacoustic model (iso_psy.cuh; restated by tests/psymodel.py).  ISO 11172-3 Annex D gives its partition tables
+// as literals per sample rate; here they are derived from the same ingredients: a Bark scale (Zwicker / Terhardt), partitions of
+// 1/3 Bark, the ISO model-2 spreading function, a minimum SNR that falls from 24.5 dB at the lowest partitions to 4.5 dB, and the
+// absolute threshold of hearing (Terhardt) with a full-scale sine at 96 dB SPL.
+double bark_of(double f) { return 13.0 * atan(0.00076 * f) + 3.5 * atan((f / 7500.0) * (f / 7500.0)); }
+void build_psy_tab(int sample_rate, int sfb_index, PsyTab &t) {
+  memset(&t, 0, sizeof t);
+  const double fs = sample_rate, pi = 3.14159265358979323846;
+  int np = 0, lo = 0;
+  while (lo < 512 && np < kPsyMaxPart) {
+    int hi = lo + 1;
+    while (hi < 512 && bark_of(hi * fs / 1024.0) - bark_of(lo * fs / 1024.0) < 1.0 / 3.0) ++hi;
+    if (np == kPsyMaxPart - 1) hi = 512;
+    t.part_lo[np] = (uint16_t)lo; t.part_n[np] = (uint16_t)(hi - lo);
+    for (int k = lo; k < hi; ++k) t.line_part[k] = (uint8_t)np;
+    lo = hi; ++np;
+  }
+  t.n_part = np;
+  double bval[kPsyMaxPart];
+  for (int b = 0; b < np; ++b) bval[b] = bark_of((t.part_lo[b] + 0.5 * (t.part_n[b] - 1)) * fs / 1024.0);
+  for (int i = 0; i < np; ++i) {                       // i = target, j = source
+    double sum = 0.0;
+    for (int j = 0; j < np; ++j) {
+      double tx = (j >= i ? 3.0 : 1.5) * (bval[i] - bval[j]);
+      double x = 0.0;
+      if (tx >= 0.5 && tx <= 2.5) { const double u = tx - 0.5; x = 8.0 * (u * u - 2.0 * u); }
+      tx += 0.474;
+      const double ty = 15.811389 + 7.5 * tx - 17.5 * sqrt(1.0 + tx * tx);
+      const double v = ty <= -60.0 ? 0.0 : pow(10.0, (x + ty) / 10.0);
+      t.s3t[j * kPsyMaxPart + i] = (float)v;
+      sum += v;
+    }
+    t.rnorm[i] = (float)(1.0 / sum);
+    t.minval[i] = (float)std::min(24.5, std::max(4.5, 24.5 - 2.0 * bval[i]));
+    double q = 0.0;
+    for (int k = t.part_lo[i]; k < t.part_lo[i] + t.part_n[i]; ++k) {
+      const double f = std::max(k * fs / 1024.0, 20.0) / 1000.0;
+      const double ath = std::min(3.64 * pow(f, -0.8) - 6.5 * exp(-0.6 * (f - 3.3) * (f - 3.3)) + 1e-3 * f * f * f * f, 80.0);
+      q += (32768.0 * 256.0) * (32768.0 * 256.0) * pow(10.0, (ath - 96.0) / 10.0);
+    }
+    t.qthr[i] = (float)q;
+  }
+  const int *cum = host_sfb_cum() + 21 * sfb_index;
+  t.sfb_line[0] = 0;
+  for (int i = 0; i < 21; ++i) t.sfb_line[i + 1] = (cum[i] * 8 + 4) / 9;
+  t.sfb_line[22] = 512;
+  for (int n = 0; n < 1024; ++n) t.hann1024[n] = (float)(0.5 * (1.0 - cos(2.0 * pi * (n + 0.5) / 1024.0)));
+  for (int n = 0; n < 256; ++n) t.hann256[n] = (float)(0.5 * (1.0 - cos(2.0 * pi * (n + 0.5) / 256.0)));
+  for (int j = 0; j < 768; ++j) { t.tw[j].x = (float)cos(2.0 * pi * j / 1024.0); t.tw[j].y = (float)-sin(2.0 * pi * j / 1024.0); }
+}
+int ensure_iso2(mp3b_batch *b) {
+  PassBuffers &p = b->pb;
+  if (p.gc_psy) return MP3B_OK;
+  CU(cudaSetDevice(b->device));
+  const size_t n = (size_t)b->S * b->GC * 24;
+  CU(dalloc(p.gc_psy, n)); CU(dalloc(p.gc_sf, n));
+  std::unique_ptr<PsyTab> t(new PsyTab);
+  build_psy_tab(b->cfg.sample_rate, b->cfg.sfb_index, *t);
+  CU(cudaMalloc((void **)&b->d_psy, sizeof(PsyTab)));
+  CU(cudaMemcpy(b->d_psy, t.get(), sizeof(PsyTab), cudaMemcpyHostToDevice));
+  p.psy = b->d_psy;
+  CU(cudaStreamSynchronize(cudaStreamLegacy));
+  return MP3B_OK;
+}
+
 int ensure_out(mp3b_batch *b, size_t stride) {
   stride = round_up<size_t>(stride, 16);
   size_t need = stride * b->S;
@@ -392,6 +459,7 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
   b->have_host_out = false;
   if (b->trace) {
     b->tr_frames.assign(S, {}); b->tr_gc.assign(S, {}); b->tr_spec.assign(S, {}); b->tr_ix.assign(S, {}); b->tr_thr.assign(S, {});
+    b->tr_psy.assign(S, {}); b->tr_sf.assign(S, {});
   }
   cudaStream_t st = b->st, stc = b->st_copy;
   // Pass pipeline: while the kernels of pass p run on `st`, the PCM of pass p + 1 crosses PCIe on `st_copy` into the
@@ -515,6 +583,7 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
             q.region0 = g.region0; q.region1 = g.region1; q.preflag = g.preflag; q.g0 = g.g0; q.max_bits = g.max_bits;
             q.iterations = g.iterations; q.energy = g.energy;
             q.table_select[0] = g.tsel[0]; q.table_select[1] = g.tsel[1]; q.table_select[2] = g.tsel[2]; q.count1table_select = g.c1sel;
+            q.scalefac_compress = g.sfc; q.part2_length = g.part2;
             b->tr_gc[s].push_back(q);
           }
         }
@@ -523,6 +592,14 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
           if (b->trace & 1) { size_t o = b->tr_spec[s].size(); b->tr_spec[s].resize(o + cnt); CU(cudaMemcpy(b->tr_spec[s].data() + o, pb.spec + off, cnt * 4, cudaMemcpyDeviceToHost)); }
           if (b->trace & 2) { size_t o = b->tr_ix[s].size(); b->tr_ix[s].resize(o + cnt); CU(cudaMemcpy(b->tr_ix[s].data() + o, pb.tr_ix + off, cnt * 4, cudaMemcpyDeviceToHost)); }
           if (b->trace & 4) { size_t o = b->tr_thr[s].size(); b->tr_thr[s].resize(o + cnt); CU(cudaMemcpy(b->tr_thr[s].data() + o, pb.tr_thr + off, cnt * 4, cudaMemcpyDeviceToHost)); }
+          if (cfg.iso >= 2) {                                       // psychoacoustic ratios / PE and the scalefactors, 24 values per gc
+            const size_t c24 = (size_t)nf * ngc * 24, o24 = (size_t)s * b->GC * 24;
+            size_t o = b->tr_psy[s].size(); b->tr_psy[s].resize(o + c24);
+            CU(cudaMemcpy(b->tr_psy[s].data() + o, pb.gc_psy + o24, c24 * 4, cudaMemcpyDeviceToHost));
+            std::vector<uint8_t> tmp(c24);
+            CU(cudaMemcpy(tmp.data(), pb.gc_sf + o24, c24, cudaMemcpyDeviceToHost));
+            b->tr_sf[s].insert(b->tr_sf[s].end(), tmp.begin(), tmp.end());
+          }
         }
       }
     }
@@ -558,7 +635,9 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
     CU(cudaEventRecord(ev[2], st));
     LAUNCH(launch_spectrum(cfg, pb, st));
     CU(cudaEventRecord(ev[3], st));
+    if (cfg.iso >= 2) LAUNCH(launch_psy(cfg, pb, st));             // ISO mode level 2: thresholds and PE from the PCM ...
     LAUNCH(launch_curve(cfg, pb, st, fused_prepass));
+    if (cfg.iso >= 2) LAUNCH(launch_outer(cfg, pb, st));           // ... and the scalefactor outer loop on k_granule's magnitudes
     if (b->trace & 4) LAUNCH(launch_thresholds(cfg, pb, st));
     CU(cudaEventRecord(ev[4], st));
     LAUNCH(launch_scan(cfg, pb, st));
@@ -1008,6 +1087,7 @@ int mp3b_batch_clone(const mp3b_batch *src, mp3b_batch **out) {
   A(cudaStreamSynchronize(b->st));
   if (e != cudaSuccess) { free_batch(b); return fail(MP3B_ERR_CUDA, "clone failed: %s", cudaGetErrorString(e)); }
   b->head_sel = src->head_sel; b->cfg.iso = src->cfg.iso; b->cfg.ms_scale = src->cfg.ms_scale;
+  if (b->cfg.iso >= 2 && ensure_iso2(b) != MP3B_OK) { free_batch(b); return MP3B_ERR_CUDA; }
   b->pending = src->pending; b->frame_count = src->frame_count; b->byte_count = src->byte_count; b->frame_sizes = src->frame_sizes;
   b->trace = src->trace;
   *out = b;
@@ -1039,12 +1119,14 @@ int mp3b_batch_set_iso_mode(mp3b_batch *b, int on) {
   if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");
   if (is_multi(b)) {
     for (mp3b_batch *p : b->parts) { const int rc = mp3b_batch_set_iso_mode(p, on); if (rc) return rc; }
-    b->cfg.iso = on ? 1 : 0;
+    b->cfg.iso = on < 0 ? 0 : on > 2 ? 2 : on;
     return MP3B_OK;
   }
   for (int s = 0; s < b->S; ++s)
     if (b->pending[(size_t)s] || b->frame_count[(size_t)s]) return fail(MP3B_ERR_BAD_ARG, "iso mode can only be changed on fresh sessions (after create or reset)");
-  b->cfg.iso = on ? 1 : 0;
+  const int level = on < 0 ? 0 : on > 2 ? 2 : on;
+  if (level >= 2) { const int rc = ensure_iso2(b); if (rc) return rc; }
+  b->cfg.iso = level;
   b->cfg.ms_scale = on ? 0.70710678118654752440f : 0.5f;
   return MP3B_OK;
 }
@@ -1083,7 +1165,13 @@ int mp3b_batch_trace_gc_array(const mp3b_batch *b, int stream, int kind, void *o
   if (kind == 0) { src = b->tr_spec[stream].data(); elems = b->tr_spec[stream].size(); }
   else if (kind == 1) { src = b->tr_ix[stream].data(); elems = b->tr_ix[stream].size(); }
   else if (kind == 2) { src = b->tr_thr[stream].data(); elems = b->tr_thr[stream].size(); }
-  else return fail(MP3B_ERR_BAD_ARG, "kind must be 0, 1 or 2");
+  else if (kind == 3 || kind == 4) {                               // 24 values per gc: psychoacoustic record f32 / scalefactor record i32
+    const size_t n24 = kind == 3 ? b->tr_psy[stream].size() : b->tr_sf[stream].size();
+    if (n24 > (size_t)cap_gc * 24) return fail(MP3B_ERR_BUFFER_TOO_SMALL, "need %zu granule-channels", n24 / 24);
+    if (n24) memcpy(out, kind == 3 ? (const void *)b->tr_psy[stream].data() : (const void *)b->tr_sf[stream].data(), n24 * 4);
+    return (int)(n24 / 24);
+  }
+  else return fail(MP3B_ERR_BAD_ARG, "kind must be 0 ... 4");
   if (elems > (size_t)cap_gc * 576) return fail(MP3B_ERR_BUFFER_TOO_SMALL, "need %zu granule-channels", elems / 576);
   if (elems) memcpy(out, src, elems * 4);
   return (int)(elems / 576);

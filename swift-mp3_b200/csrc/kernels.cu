@@ -24,10 +24,12 @@ extern const int *host_sfb_cum();
 
 extern const float *host_inv_step_iso();
 cudaError_t upload_iso_tables(const float *inv_step_iso);   // iso_mode.cuh
+cudaError_t upload_psy_constants();                         // iso_psy.cuh
 
 cudaError_t upload_tables() {
   cudaError_t e;
   if ((e = upload_iso_tables(host_inv_step_iso()))) return e;
+  if ((e = upload_psy_constants())) return e;
   if ((e = cudaMemcpyToSymbol(c_inv_step, host_inv_step(), sizeof(float) * 256))) return e;
   if ((e = cudaMemcpyToSymbol(c_gain_thr, host_gain_thr(), sizeof(double) * 256))) return e;
   if ((e = cudaMemcpyToSymbol(c_sfb_cum, host_sfb_cum(), sizeof(int) * 63))) return e;
@@ -716,6 +718,7 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
 #pragma unroll
   for (int j = 0; j < 9; ++j) { float2 v = reinterpret_cast<const float2 *>(smg[warp])[lane + 32 * j]; mx[j] = v.x; my[j] = v.y; }
   uint16_t *bits_out = pb.gc_bits + gslot * kMaxEntries, *bv_out = pb.gc_bv + gslot * kMaxEntries;
+  if (ISO && cfg.iso >= 2) { __syncwarp(); continue; }   // level 2: k_outer (iso_psy.cuh) takes it from the magnitudes
   if (ISO) {
     // global_gain search (north_star stage 4).  The bit count falls as the gain rises, so: binary search for the smallest gain
     // that fits the LARGEST budget this frame can have (full reservoir, padded), then the curve gain by gain until the count
@@ -782,6 +785,10 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
   }
 }
 
+}  // namespace mp3b
+#include "iso_psy.cuh"    // ISO mode level 2: psychoacoustic model (k_psy) and scalefactor outer loop (k_outer)
+namespace mp3b {
+
 // ------------------------------------------------------------------------------------------------------------
 // K_scan: the serial part of a stream (SRC:475-568): padding, reservoir, per-gc gain choice, main_data_begin,
 // slot filling bookkeeping.  One thread per stream.
@@ -807,6 +814,8 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
   __shared__ __align__(4) uint8_t sh_sel[32 * 4][4];       // chosen entry, gain_out, gain_used, iterations
   __shared__ ScanFrame sh_fr[32];
   __shared__ int sh_state[8];
+  __shared__ float sh_pe[32 * 4];                            // ISO mode level 2: perceptual entropy per gc
+  __shared__ uint16_t sh_bpg[32 * 4];                        // the budget each gc was given
   const int s = blockIdx.x, lane = threadIdx.x;
   const StreamPlan plan = pb.plan[s];
   StreamState &st = pb.state[s];
@@ -839,6 +848,7 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
       for (int i = n16 * 8 + lane; i < cnt * ngc * kMaxEntries; i += 32) sh_bits[i] = pb.gc_bits[g0s * kMaxEntries + i];
       for (int i = lane; i < cnt * ngc; i += 32) sh_meta[i] = pb.gc_meta[g0s + i];
       if (lane < cnt) sh_bri[lane] = pb.frame_br[(size_t)s * pb.Fc + base + lane];
+      if (cfg.iso >= 2) for (int i = lane; i < cnt * ngc; i += 32) sh_pe[i] = pb.gc_psy[(g0s + i) * 24 + 22];
     }
     __syncwarp();
     {  // (2) the serial chain, SRC:475-568.  Every lane carries the scalar recurrences (padding, reservoir, cursors)
@@ -864,13 +874,29 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
         int total;
         {
           const int j = lane & (ngc - 1);
+          int my_bpg = bpg;
+          if (cfg.iso >= 2) {
+            // The granule's share of the reservoir follows its perceptual entropy (ISO 11172-3 C.1.5.4.5 in spirit): demand =
+            // 3.1 PE bits beyond the mean; the granule-channels of a frame share at most 60 % of the reservoir in proportion to
+            // their demand, what exceeds 80 % of the reservoir's capacity is spent anyway, nobody gets more than twice the mean
+            // (k_outer's curve starts there).
+            const int mean = (mds * 8) >> ngc_shift;
+            const int want = max((int)fminf(sh_pe[l * ngc + j] * 3.1f, 60000.0f) - mean, 0);
+            int sumwant = want + __shfl_xor_sync(0xffffffffu, want, 1);
+            if (ngc == 4) sumwant += __shfl_xor_sync(0xffffffffu, sumwant, 2);
+            const int pool = (res_bits * 6) / 10;
+            const int give = sumwant > pool ? (int)((long long)want * pool / sumwant) : want;
+            const int over = max(res_bits - (min(511, mds) * 64) / 10 - min(sumwant, pool), 0);
+            my_bpg = min(min(mean + give + (over >> ngc_shift), 2 * mean), 4095);
+          }
+          if (lane < ngc) sh_bpg[l * ngc + j] = (uint16_t)min(my_bpg, 65535);
           const uint32_t meta = sh_meta[l * ngc + j];
           const int g0 = cfg.iso ? (int)(meta & 511u) : (int)(meta & 255u), n = cfg.iso ? (int)((meta >> 9) & 31u) : (int)((meta >> 8) & 255u);
           const int restart = cfg.iso ? 0 : (int)((meta >> 16) & 1u);
           const uint16_t *cb = sh_bits + (l * ngc + j) * kMaxEntries;
           int gain = g0, chosen = n - 1, gain_out = g0, gain_used = g0, iters = n, bits = -1;
           if (cfg.iso) {                                             // first entry whose count fits the budget and the 12-bit field
-            const int fit = min(bpg, 4095);
+            const int fit = min(my_bpg, 4095);
             for (int e = 0; e < n; ++e) if ((int)cb[e] <= fit) { chosen = e; break; }
             bits = cb[chosen]; iters = chosen + 1;
             gain_used = chosen == kMaxEntries - 1 ? (int)((meta >> 14) & 511u) : min(g0 + chosen, kIsoGainMax);   // the search gain
@@ -946,7 +972,7 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
         int r0 = 0, r1 = 0;
         if (!cfg.iso) region_counts(cfg, bv, r0, r1);                // ISO mode: k_pack_iso fills regions, table_select, count1table
         g.region0 = (uint8_t)r0; g.region1 = (uint8_t)r1; g.preflag = cfg.iso ? 0 : (uint8_t)((meta >> 17) & 1); g.g0 = (uint8_t)(meta & 255);
-        g.iterations = sh_sel[lane * ngc + j][3]; g.pad = 0; g.max_bits = (uint16_t)o.bpg;
+        g.iterations = sh_sel[lane * ngc + j][3]; g.pad = 0; g.max_bits = sh_bpg[lane * ngc + j]; g.sfc = 0; g.part2 = 0;
         g.tsel[0] = g.tsel[1] = g.tsel[2] = 15; g.c1sel = 0;
         g.energy = pb.gc_energy[(size_t)s * (10 + pb.GC) + 10 + gci];
         if (cfg.iso) {                                                // the search gain (may exceed 255) | big_values << 9
@@ -1098,12 +1124,19 @@ template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta) 
   __shared__ __align__(16) uint8_t s_len[(kHuffEntries + 15) / 16 * 16];
   __shared__ int16_t s_ix[kPackFramesPerCta][576];
   __shared__ uint8_t s_c[kPackFramesPerCta][288];
+  __shared__ uint8_t s_band[288];                                  // scalefactor band of pair p (level 2)
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ch = cfg.channels, ngc = 2 * ch;
   const int f = blockIdx.y * kPackFramesPerCta + warp;
   const int nfr = (int)pb.plan[s].n_frames;
   const bool active = f < nfr;
+  const bool lv2 = cfg.iso >= 2;
   for (int i = tid; i < kHuffEntries; i += 32 * kPackFramesPerCta) { s_huff[i] = kHuffPacked[i]; s_len[i] = kHuffLenFlat[i]; }
+  for (int i = tid; i < 288; i += 32 * kPackFramesPerCta) {
+    int b = 0;
+    for (int k = 0; k < 21; ++k) b += c_sfb_cum[cfg.sfb_index][k] <= 2 * i;
+    s_band[i] = (uint8_t)b;
+  }
   uint32_t *buf = bufs[warp];
   for (int i = lane; i < 552; i += 32) buf[i] = 0;
   __syncthreads();
@@ -1115,13 +1148,18 @@ template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta) 
     const uint32_t sel = pb.gc_sel[gslot], bitoff = pb.gc_bitoff[gslot];
     const float inv = c_inv_step_iso[sel & 511u];
     const float2 *sm2 = reinterpret_cast<const float2 *>(pb.smag + gslot * 576);
+    // level 2: the scalefactors k_outer chose amplify |xr|^0.75 band by band (sf[21] = 0: the last band has none)
+    const uint8_t *sfp = lv2 ? pb.gc_sf + gslot * 24 : nullptr;
+    const int part2 = lv2 ? sfp[22] : 0, sfc = lv2 ? sfp[21] : 0;
     int qx[9], qy[9];
     int16_t *ix = s_ix[warp];
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
       const int p = lane + 32 * j;
       const float2 v = __ldg(sm2 + p);
-      qx[j] = iso_quant(fabsf(v.x), inv); qy[j] = iso_quant(fabsf(v.y), inv);
+      float m0 = fabsf(v.x), m1 = fabsf(v.y);
+      if (lv2) { const int b = s_band[p]; const float a = c_amp34[b < 21 ? sfp[b] : 0]; m0 = __fmul_rn(m0, a); m1 = __fmul_rn(m1, a); }
+      qx[j] = iso_quant(m0, inv); qy[j] = iso_quant(m1, inv);
       ix[2 * p] = (int16_t)(v.x < 0.0f ? -qx[j] : qx[j]); ix[2 * p + 1] = (int16_t)(v.y < 0.0f ? -qy[j] : qy[j]);
       if (TRACE) { pb.tr_ix[gslot * 576 + 2 * p] = ix[2 * p]; pb.tr_ix[gslot * 576 + 2 * p + 1] = ix[2 * p + 1]; }
     }
@@ -1129,14 +1167,21 @@ template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta) 
     __syncwarp();
     if (lane == 0) {
       GcSide &gs = fr.gc[g];
-      if (c.bits != (int)gs.part23) atomicOr(&pb.state[s].error, 16);          // the curve and the packer must agree bit for bit
+      if (c.bits + part2 != (int)gs.part23) atomicOr(&pb.state[s].error, 16);  // the curve and the packer must agree bit for bit
+      gs.sfc = (uint8_t)sfc; gs.part2 = (uint8_t)part2;
       gs.big_values = (uint16_t)c.bv; gs.region0 = (uint8_t)c.r0; gs.region1 = (uint8_t)c.r1;
       gs.tsel[0] = (uint8_t)c.tsel[0]; gs.tsel[1] = (uint8_t)c.tsel[1]; gs.tsel[2] = (uint8_t)c.tsel[2]; gs.c1sel = (uint8_t)c.c1sel;
       if (f == nfr - 1 && pb.state[s].buffered.valid) {             // the scan has already parked this frame as bufferedFrame
         GcSide &bs = pb.state[s].buffered.gc[g];
         bs.big_values = gs.big_values; bs.region0 = gs.region0; bs.region1 = gs.region1;
         bs.tsel[0] = gs.tsel[0]; bs.tsel[1] = gs.tsel[1]; bs.tsel[2] = gs.tsel[2]; bs.c1sel = gs.c1sel;
+        bs.sfc = gs.sfc; bs.part2 = gs.part2;
       }
+    }
+    if (part2 && lane < 21) {                                       // part 2: 11 scalefactors of slen1 bits, 10 of slen2 (scfsi = 0)
+      const int l1 = c_slen1[sfc], l2 = c_slen2[sfc];
+      const int len = lane < 11 ? l1 : l2;
+      if (len) put_bits64(buf, bitoff + (uint32_t)(lane < 11 ? lane * l1 : 11 * l1 + (lane - 11) * l2), (unsigned long long)sfp[lane], len);
     }
     // ---- big_values: lane L codes pairs 9L ... 9L+8
     const uint32_t d0 = iso_desc(c.tsel[0]), d1 = iso_desc(c.tsel[1]), d2 = iso_desc(c.tsel[2]);
@@ -1165,7 +1210,7 @@ template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta) 
 #pragma unroll
     for (int dlt = 1; dlt < 32; dlt <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, dlt); if (lane >= dlt) incl += t; }
     const int big_total = __shfl_sync(0xffffffffu, incl, 31);
-    uint32_t pos = bitoff + (uint32_t)(incl - mine);
+    uint32_t pos = bitoff + (uint32_t)part2 + (uint32_t)(incl - mine);
 #pragma unroll
     for (int j = 0; j < 9; ++j) if (len[j]) { put_bits64(buf, pos, val[j], len[j]); pos += len[j]; }
     // ---- count1: lane L codes quadruples 5L ... 5L+4 (at most 144 of them)
@@ -1188,7 +1233,7 @@ template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta) 
     int qincl = qmine;
 #pragma unroll
     for (int dlt = 1; dlt < 32; dlt <<= 1) { int t = __shfl_up_sync(0xffffffffu, qincl, dlt); if (lane >= dlt) qincl += t; }
-    pos = bitoff + (uint32_t)big_total + (uint32_t)(qincl - qmine);
+    pos = bitoff + (uint32_t)part2 + (uint32_t)big_total + (uint32_t)(qincl - qmine);
 #pragma unroll
     for (int i = 0; i < 5; ++i) if (ql[i]) { put_bits64(buf, pos, qv[i], ql[i]); pos += ql[i]; }
     __syncwarp();
@@ -1241,7 +1286,7 @@ __global__ void __launch_bounds__(128) k_frames(Config cfg, PassBuffers pb) {
       const GcSide &g = fr.gc[lane];
       const int ws = g.block_type != 0;
       v = (unsigned long long)(g.part23 & 0xFFF) << 47 | (unsigned long long)(g.big_values & 0x1FF) << 38 |
-          (unsigned long long)g.global_gain << 30 | (unsigned long long)ws << 25;   // scalefac_compress = 0 (4 bits at 26)
+          (unsigned long long)g.global_gain << 30 | (unsigned long long)(g.sfc & 15) << 26 | (unsigned long long)ws << 25;   // scalefac_compress = 0 outside ISO mode level 2 (SRC:722)
       unsigned long long mid;                                                         // 22 bits at 3
       if (ws) mid = (unsigned long long)(g.block_type & 3) << 20 | (unsigned long long)(g.block_type == 1) << 19 | 15ull << 14 | 15ull << 9 |
                     (unsigned long long)(g.sbg[0] & 7) << 6 | (unsigned long long)(g.sbg[1] & 7) << 3 | (unsigned long long)(g.sbg[2] & 7);
@@ -1564,6 +1609,18 @@ int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st, bool
   else if (pb.spec) k_granule<true, false, false><<<grid, 256, 0, st>>>(cfg, pb);
   else if (fused_prepass) k_granule<false, true, false><<<grid, 256, 0, st>>>(cfg, pb);
   else k_granule<false, false, false><<<grid, 256, 0, st>>>(cfg, pb);
+  return check(1);
+}
+int launch_psy(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  if (pb.max_frames <= 0) return 0;
+  dim3 grid(cfg.n_streams, (pb.max_frames * 2 * cfg.channels + kPsyWarps - 1) / kPsyWarps);
+  k_psy<<<grid, 32 * kPsyWarps, 0, st>>>(cfg, pb);
+  return check(1);
+}
+int launch_outer(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  if (pb.max_frames <= 0) return 0;
+  dim3 grid(cfg.n_streams, (pb.max_frames * 2 * cfg.channels + kOuterWarps - 1) / kOuterWarps);
+  k_outer<<<grid, 32 * kOuterWarps, 0, st>>>(cfg, pb);
   return check(1);
 }
 int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {

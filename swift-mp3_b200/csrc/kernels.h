@@ -14,6 +14,19 @@ namespace mp3b {
 
 constexpr int kMaxEntries = 20;     // gain-loop iterations, SRC:745
 constexpr int kMdCarryCap = 8192;   // bytes of reservoir backlog that may cross a pass boundary
+constexpr int kPsyMaxPart = 80;     // threshold-calculation partitions of the psychoacoustic model (ISO mode level 2)
+
+// Tables of the psychoacoustic model (iso_psy.cuh) for one sample rate; built on the host (engine.cc: build_psy_tab), device resident.
+struct PsyTab {
+  int n_part;
+  int sfb_line[23];                          // FFT-line boundaries of the 22 long scalefactor bands (MDCT line * 8 / 9)
+  uint16_t part_lo[kPsyMaxPart], part_n[kPsyMaxPart];   // first FFT line and number of lines of a partition (1/3 Bark each)
+  float rnorm[kPsyMaxPart], minval[kPsyMaxPart] /* dB */, qthr[kPsyMaxPart] /* absolute threshold, energy */;
+  float s3t[kPsyMaxPart * kPsyMaxPart];      // spreading function, [source][target]
+  uint8_t line_part[512];
+  float hann1024[1024], hann256[256];
+  float2 tw[768];                            // exp(-2 pi i j / 1024)
+};
 
 struct Config {              // constant for the lifetime of a batch; passed to kernels by value
   int n_streams, channels, fsc /* floats per frame = 1152*channels */;
@@ -21,7 +34,7 @@ struct Config {              // constant for the lifetime of a batch; passed to 
   int sr_index, sfb_index, side_bytes, header_bytes /* 4 + crc + side */;
   int mode_bits, mode_ext, cbr_index;
   float f_one, f_neg0;                // 1.0f and -0.0f as run-time values (see k_spectrum phase A)
-  int iso;                            // opt-in ISO mode (iso_mode.cuh): ISO quantizer, table selection, count1, real main_data_begin
+  int iso;                            // opt-in ISO mode (iso_mode.cuh): 1 = ISO quantizer, table selection, count1, real main_data_begin; 2 = + psychoacoustic model and scalefactor outer loop (iso_psy.cuh)
   float ms_scale;                     // mid / side = (L +- R) * ms_scale: 0.5 like the reference (SRC:2148-2154), 1/sqrt(2) in ISO mode
   int frame_base[16], frame_rem[16];  // 144*kbps*1000 / sr and % sr per bitrate index
   uint8_t vbr_idx_of_kbps[324];       // bitrateIndex(kbps) for every VBR target 0...320
@@ -45,6 +58,7 @@ struct GcSide {              // side-info fields of one gc (GranuleInfo, SRC:207
   uint8_t sbg[3];
   uint8_t region0, region1, preflag, g0, iterations, pad;   // pad: ISO mode, search gain above 255 (gain_used + pad = the gain that quantized)
   uint16_t max_bits;
+  uint8_t sfc, part2;        // ISO mode level 2: scalefac_compress and the scalefactor bits inside part23 (0 otherwise)
   float energy;
   uint8_t tsel[3], c1sel;    // ISO mode: table_select per region, count1table_select (the reference writes 15, 15, 15 and 0)
 };
@@ -106,6 +120,10 @@ struct PassBuffers {         // device arrays for one pass; Fc = frame capacity 
   size_t out_stride;
   uint16_t *emit_size;       // [S][Fc+1] sizes of the frames emitted by this pass, in order
   uint32_t *emit_n;          // [S]
+  // ISO mode level 2 (iso_psy.cuh)
+  const PsyTab *psy;
+  float *gc_psy;             // [S][GC][24] threshold / energy per long scalefactor band (22), perceptual entropy, mean tonality
+  uint8_t *gc_sf;            // [S][GC][24] scalefactors (21), scalefac_compress, part2 bits, bands over | outer iterations << 4
   // optional traces
   int32_t *tr_ix;            // same
   float *tr_thr;             // same
@@ -117,6 +135,9 @@ cudaError_t upload_tables();   // __constant__ tables for the current device
 int launch_prepass(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st, bool fused_prepass);   // fused_prepass: launch_prepass did not run
+// ISO mode level 2: psychoacoustic model (needs the PCM and the pre-pass's M/S decision) and the outer loop (after launch_curve)
+int launch_psy(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
+int launch_outer(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 // ISO mode: the main-data FIFO of a pass must start out zeroed (stuffing bytes are never written)
 int launch_clear_md(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st);

@@ -1,4 +1,4 @@
-"""Test-only ISO 11172-3 Layer III main-data parser (long blocks, no scalefactors — what the engine's ISO mode writes): finds
+"""Test-only ISO 11172-3 Layer III main-data parser (long blocks, scalefactors without scfsi — what the engine's ISO mode writes): finds
 every frame's main data through the main_data_begin back pointer, decodes big_values with the region's table_select
 (tables 1-3, 5-13, 15, 16-31 with linbits), then count1 quadruples with table A / B until part2_3_length is used up, and returns
 ix[576] per granule-channel.  Tables: tests/iso_huffman.json (tools/gen_huffman_tables.py).  Band tables: ISO 11172-3 Table B.8."""
@@ -12,6 +12,9 @@ from mp3parse import Bits, parse_frames
 SFB_LONG = {0: [0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 52, 62, 74, 90, 110, 134, 162, 196, 238, 288, 342, 418, 576],      # 44.1 kHz
             1: [0, 4, 8, 12, 16, 20, 24, 30, 36, 42, 50, 60, 72, 88, 106, 128, 156, 190, 230, 276, 330, 384, 576],      # 48 kHz
             2: [0, 4, 8, 12, 16, 20, 24, 30, 36, 44, 54, 66, 82, 102, 126, 156, 194, 240, 296, 364, 448, 550, 576]}     # 32 kHz
+
+SLEN1 = [0, 0, 0, 0, 3, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4]       # ISO 11172-3 2.4.2.7: scalefac_compress -> slen1, slen2
+SLEN2 = [0, 1, 2, 3, 0, 1, 2, 3, 1, 2, 3, 1, 2, 3, 2, 3]
 
 _T = None
 
@@ -55,8 +58,12 @@ def decode_stream(stream):
         assert begin >= 0, "frame %d: main_data_begin %d points before the start of the stream" % (n, f["mdb"])
         b = Bits(cat, begin * 8)
         for g in f["gc"]:
-            assert g["ws"] == 0 and g["scalefac_compress"] == 0 and g["preflag"] == 0, "ISO mode writes long blocks without scalefactors"
+            assert g["ws"] == 0 and g["preflag"] == 0, "ISO mode writes long blocks without preflag"
             start, ix = b.p, np.zeros(576, np.int32)
+            # part 2 (ISO mode level 2): 11 scalefactors of slen1 bits, 10 of slen2 (long blocks, scfsi = 0)
+            l1, l2 = SLEN1[g["scalefac_compress"]], SLEN2[g["scalefac_compress"]]
+            sf = [b.get(l1) if l1 else 0 for _ in range(11)] + [b.get(l2) if l2 else 0 for _ in range(10)]
+            part2 = b.p - start
             bv2 = 2 * g["big_values"]
             assert bv2 <= 576
             sfb = SFB_LONG[f["sr_index"]]
@@ -67,7 +74,7 @@ def decode_stream(stream):
                     continue
                 src = t if t < 16 else 16 if t < 24 else 24
                 ix[i], ix[i + 1] = _pair(b, luts[src], linbits.get(t, 0))
-            big_bits, i, quads = b.p - start, bv2, 0
+            big_bits, i, quads = b.p - start - part2, bv2, 0
             while b.p < start + g["part23"] and i <= 572:
                 lut = quad[g["count1table"]]
                 code, k = 0, 0
@@ -82,7 +89,7 @@ def decode_stream(stream):
                         ix[i + m] = -1 if b.get(1) else 1
                 i += 4; quads += 1
             assert b.p == start + g["part23"], "frame %d: part2_3_length %d, decoded %d bits" % (n, g["part23"], b.p - start)
-            out.append(ix); info.append(dict(big_bits=big_bits, count1_bits=b.p - start - big_bits, quads=quads))
+            out.append(ix); info.append(dict(big_bits=big_bits, count1_bits=b.p - start - big_bits - part2, quads=quads, part2=part2, scalefac=sf))
         # the next frame's data must not start before this one's ended
         if n + 1 < len(frames):
             assert int(starts[n + 1]) - frames[n + 1]["mdb"] >= (b.p + 7) // 8 - 0 or True
