@@ -384,6 +384,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=30.0)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-tc", action="store_true", help="skip the tensor-core matrixing leg (reported beside value)")
     ap.add_argument("--i16", action="store_true", help="also time the 16-bit-input extension end to end (reported as e2e_i16, not the headline)")
     ap.add_argument("--workload", default="c4", choices=["c4", "c1", "c2", "c3", "c5"],
                     help="c4 (default, the headline): batch of 30 s streams; c1 / c2 / c3: the single-stream configs; "
@@ -614,6 +615,36 @@ def main():
                                 "instruction issue (MDCT with immediate coefficients, FP64 |x|^0.75, integer bit counting); see DESIGN.md section 4",
                      "stages": stage_table, "stage_ms_per_step": {k: v / a.steps for k, v in stages.items()}})
 
+    # ---- beside `value`, never instead of it: the same device-plane step with the filterbank's matrixing on the tensor cores
+    # (tcgen05, three-term TF32 split; opt-in because its subband samples differ from the FP32 path in the last bits)
+    tc = None
+    if not a.no_tc:
+        b.set_matrixing(1)
+        b.reset(); b.encode_device(dptrs, ns, flush=True, download=True)
+        tc_digests = stream_digests(L, b, S)
+        for _ in range(2):
+            step_device()
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record(ext)
+        tc_stages = {k: 0.0 for k in mp3.STAGES}
+        tc_steps = max(2, min(a.steps, 5))
+        for _ in range(tc_steps):
+            step_device()
+            for k, v in b.stage_ms().items():
+                tc_stages[k] += v
+        t1e.record(ext)
+        barrier()
+        tc_ms = max_over_ranks(t0e.elapsed_time(t1e)) / tc_steps
+        same = int(sum_over_ranks(sum(1 for x, y in zip(tc_digests, device_digests) if x == y)))
+        tc = {"value": world * audio_per_step / (tc_ms / 1000.0), "unit": "x realtime", "ms_per_step": tc_ms, "steps": tc_steps,
+              "stage_ms_per_step": {k: v / tc_steps for k, v in tc_stages.items()},
+              "filterbank_tensor_TFLOPs": gc_per_step * 6 * 73728 / (tc_stages["filterbank"] / tc_steps / 1000.0) / 1e12,
+              "streams_byte_identical_to_fp32_path": "%d/%d" % (same, S * world),
+              "note": "mp3b_batch_set_matrixing(b, 1): k_filterbank_tc (tcgen05.mma kind::tf32, 6 products of a 3-term split, TMEM accumulators); "
+                      "tier 1 (1e-5) holds with a 10x margin, see tests/test_gpu_parity.py::test_tensor_core_matrixing"}
+        b.set_matrixing(0)
+
     # ---- e2e: host plane (pinned PCM in, MP3 bytes out), wall clock
     e2e_steps = a.e2e_steps or min(a.steps, 5)
     hp = C.c_void_p()
@@ -700,6 +731,8 @@ def main():
             line["other_configs"] = others
         if e2e_i16 is not None:
             line["e2e_i16"] = e2e_i16
+        if tc is not None:
+            line["tensor_core_matrixing"] = tc
         emit(line)
     if dist is not None:
         dist.barrier()

@@ -158,6 +158,15 @@ int mp3b_batch_set_iso_mode(mp3b_batch *b, int on);
 int mp3b_batch_iso_mode(const mp3b_batch *b);
 int mp3b_session_set_iso_mode(mp3b_session *s, int on);
 
+/* ---- matrixing of the polyphase filterbank (extension, default 0) -----------------------------------------------------------
+ * north_star stage (1): the 32 x 64 cosine matrixing (PolyphaseFilterbank.analyze, SRC:1402-1408) "runs on tensor cores only if
+ * 3xTF32 split-precision stays inside tolerance, and on FP32 FMA otherwise".  0 = FP32 FMA in the reference's summation order
+ * (the default: every byte equals the oracle's); 1 = tcgen05 tensor cores, every FP32 operand split exactly into three TF32
+ * terms, six products accumulated in FP32 — the subband samples then differ from the FP32 path in the last bits (tier 1 holds
+ * with a wide margin; how many granules change their quantized values is measured by the tests and reported under profiles/). */
+int mp3b_batch_set_matrixing(mp3b_batch *b, int mode);
+int mp3b_batch_matrixing(const mp3b_batch *b);
+
 /* ---- session pool: many threads, one step ------------------------------------------------------------- */
 /* n_sessions EncoderSessions (SRC:237-350) driven from concurrent threads — one blocking call per session at a time,
  * like N reference sessions on N threads — and advanced on the GPU together: the calls that arrive within max_wait_us of

@@ -80,6 +80,7 @@ def lib():
         "mp3b_batch_frames_per_pass": (i32, [vp]),
         "mp3b_batch_create_multi": (i32, [C.POINTER(_Options), i32, C.POINTER(i32), i32, i32, C.POINTER(vp)]),
         "mp3b_batch_set_iso_mode": (i32, [vp, i32]), "mp3b_batch_iso_mode": (i32, [vp]), "mp3b_session_set_iso_mode": (i32, [vp, i32]),
+        "mp3b_batch_set_matrixing": (i32, [vp, i32]), "mp3b_batch_matrixing": (i32, [vp]),
         "mp3b_batch_device_count": (i32, [vp]), "mp3b_batch_stream_device": (i32, [vp, i32]),
         "mp3b_batch_destroy": (None, [vp]), "mp3b_batch_stream_count": (i32, [vp]),
         "mp3b_batch_encode": (i32, [vp, C.POINTER(vp), szp, i32, vp]),
@@ -286,6 +287,10 @@ class EncoderBatch:
     def set_iso_mode(self, on=True):
         """Opt-in ISO mode (include/mp3b200.h): ISO quantizer, table selection, count1, real main_data_begin."""
         _check(lib().mp3b_batch_set_iso_mode(self._h, int(on)))
+
+    def set_matrixing(self, mode):
+        """0 = FP32 FMA (default, bit-exact with the oracle), 1 = 3xTF32 on the tensor cores (include/mp3b200.h)."""
+        _check(lib().mp3b_batch_set_matrixing(self._h, int(mode)))
 
     def stream_device(self, stream):
         return _check(lib().mp3b_batch_stream_device(self._h, stream))

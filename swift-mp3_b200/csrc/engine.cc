@@ -114,6 +114,7 @@ struct mp3b_batch {
   std::vector<std::vector<float>> tr_spec, tr_thr, tr_psy;
   std::vector<std::vector<int32_t>> tr_ix, tr_sf;
   PsyTab *d_psy = nullptr;                               // ISO mode level 2
+  float *d_tc_b = nullptr;                               // tensor-core matrixing: split + swizzled analysis matrix
   std::vector<FrameRec> h_rec;
 };
 
@@ -232,7 +233,7 @@ void free_batch(mp3b_batch *b) {
   PassBuffers &p = b->pb;
   void *dev[] = {p.plan, p.state, b->d_head[0], b->d_head[1], p.ms, p.frame_energy, p.gc_energy, p.gc_bt, p.frame_br, p.spec, p.sub, p.smag,
                  p.gc_meta, p.gc_bits, p.gc_bv, p.gc_bitoff, p.gc_sel, p.fr_md, p.rec, p.emit, p.md, p.md_tail, p.md_carry, p.out,
-                 p.emit_size, p.emit_n, p.tr_ix, p.tr_thr, p.gc_psy, p.gc_sf, b->d_psy, b->d_stage[0], b->d_stage[1], b->d_stage16[0], b->d_stage16[1], b->d_plan[1], b->d_offsets, b->d_compact};
+                 p.emit_size, p.emit_n, p.tr_ix, p.tr_thr, p.gc_psy, p.gc_sf, b->d_psy, b->d_tc_b, b->d_stage[0], b->d_stage[1], b->d_stage16[0], b->d_stage16[1], b->d_plan[1], b->d_offsets, b->d_compact};
   for (void *q : dev) if (q) cudaFree(q);
   void *host[] = {b->h_plan, b->h_state, b->h_emit_size, b->h_emit_n, b->h_offsets, b->h_out};
   for (void *q : host) if (q) cudaFreeHost(q);
@@ -1088,6 +1089,7 @@ int mp3b_batch_clone(const mp3b_batch *src, mp3b_batch **out) {
   if (e != cudaSuccess) { free_batch(b); return fail(MP3B_ERR_CUDA, "clone failed: %s", cudaGetErrorString(e)); }
   b->head_sel = src->head_sel; b->cfg.iso = src->cfg.iso; b->cfg.ms_scale = src->cfg.ms_scale;
   if (b->cfg.iso >= 2 && ensure_iso2(b) != MP3B_OK) { free_batch(b); return MP3B_ERR_CUDA; }
+  if (src->pb.tc_b && mp3b_batch_set_matrixing(b, 1) != MP3B_OK) { free_batch(b); return MP3B_ERR_CUDA; }
   b->pending = src->pending; b->frame_count = src->frame_count; b->byte_count = src->byte_count; b->frame_sizes = src->frame_sizes;
   b->trace = src->trace;
   *out = b;
@@ -1131,6 +1133,40 @@ int mp3b_batch_set_iso_mode(mp3b_batch *b, int on) {
   return MP3B_OK;
 }
 int mp3b_batch_iso_mode(const mp3b_batch *b) { return b ? b->cfg.iso : 0; }
+// Matrixing of the filterbank: 0 = FP32 FMA in the reference's order (default, bit-exact with the oracle), 1 = tensor cores with
+// a three-term TF32 split (filterbank_tc.cuh).  May be switched at any time: it changes how S = M Y is summed, nothing else.
+int mp3b_batch_set_matrixing(mp3b_batch *b, int mode) {
+  if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");
+  if (mode != 0 && mode != 1) return fail(MP3B_ERR_BAD_ARG, "matrixing must be 0 (FP32 FMA) or 1 (3xTF32 on the tensor cores)");
+  if (is_multi(b)) {
+    for (mp3b_batch *p : b->parts) { const int rc = mp3b_batch_set_matrixing(p, mode); if (rc) return rc; }
+    return MP3B_OK;
+  }
+  if (mode == 1 && !b->d_tc_b) {
+    CU(cudaSetDevice(b->device));
+    // [2 n halves][96 rows = hi | mid | lo term of the 32 subbands][32 n], rows of 128 bytes in 1024-byte atoms whose 16-byte
+    // chunks are XOR-swizzled with the row number: the shared-memory image of a K-major SWIZZLE_128B operand
+    std::vector<float> img(2 * 96 * 32);
+    const uint32_t mask = 0xFFFFE000u;
+    for (int H = 0; H < 2; ++H)
+      for (int r = 0; r < 96; ++r)
+        for (int k = 0; k < 32; ++k) {
+          const float m = tab::kAnalysis[r & 31][32 * H + k];
+          uint32_t u; float hi, mid, lo, rest;
+          memcpy(&u, &m, 4); u &= mask; memcpy(&hi, &u, 4);
+          rest = m - hi; memcpy(&u, &rest, 4); u &= mask; memcpy(&mid, &u, 4);
+          lo = rest - mid;
+          const size_t off = (size_t)H * 96 * 128 + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 + (size_t)((((k >> 2) ^ (r & 7)) << 4) | ((k & 3) << 2));
+          img[off / 4] = r < 32 ? hi : r < 64 ? mid : lo;
+        }
+    CU(cudaMalloc((void **)&b->d_tc_b, img.size() * sizeof(float)));
+    CU(cudaMemcpy(b->d_tc_b, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(cudaStreamLegacy));
+  }
+  b->pb.tc_b = mode ? b->d_tc_b : nullptr;
+  return MP3B_OK;
+}
+int mp3b_batch_matrixing(const mp3b_batch *b) { return b ? (is_multi(b) ? mp3b_batch_matrixing(b->parts[0]) : b->pb.tc_b != nullptr) : 0; }
 int mp3b_session_set_iso_mode(mp3b_session *s, int on) { return s ? mp3b_batch_set_iso_mode(s->b, on) : fail(MP3B_ERR_BAD_ARG, "null session"); }
 int mp3b_batch_set_trace(mp3b_batch *b, int flags) {
   if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");

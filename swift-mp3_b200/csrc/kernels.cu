@@ -554,6 +554,10 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
   }
 }
 
+}  // namespace mp3b
+#include "filterbank_tc.cuh"   // K1 with the matrixing on the tensor cores (tcgen05, opt-in)
+namespace mp3b {
+
 // ------------------------------------------------------------------------------------------------------------
 // K2+K4: MDCT / alias reduction (SRC:1512-1662), then the bits-vs-gain curve of quantizeToFitBudget (SRC:734-794).
 // One warp per gc, everything between the subband samples and the curve stays in the warp.  The loop's gain sequence does not
@@ -1599,6 +1603,19 @@ int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   dim3 grid(cfg.channels, cfg.n_streams, (ngr + R - 1) / R);
   static int dbg = -1;
   if (dbg < 0) { const char *v = getenv("MP3B_FB_DEBUG"); dbg = v ? atoi(v) : 0; }
+  if (pb.tc_b) {                                                   // opt-in: matrixing on the tensor cores (filterbank_tc.cuh)
+    static bool tc_attr[64] = {};
+    if (dev < 64 && !tc_attr[dev]) {
+      cudaFuncSetAttribute(k_filterbank_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes(1));
+      cudaFuncSetAttribute(k_filterbank_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes(2));
+      cudaFuncSetAttribute(k_filterbank_tc<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(k_filterbank_tc<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      tc_attr[dev] = true;
+    }
+    if (cfg.channels == 2) k_filterbank_tc<2><<<grid, kTcThreads, kTcSmemBytes(2), st>>>(cfg, pb, R | dbg << 16);
+    else k_filterbank_tc<1><<<grid, kTcThreads, kTcSmemBytes(1), st>>>(cfg, pb, R | dbg << 16);
+    return check(1);
+  }
   k_filterbank<<<grid, kFbThreads, kFbSmemBytes, st>>>(cfg, pb, R | dbg << 16);
   return check(1);
 }

@@ -120,6 +120,7 @@ struct PassBuffers {         // device arrays for one pass; Fc = frame capacity 
   size_t out_stride;
   uint16_t *emit_size;       // [S][Fc+1] sizes of the frames emitted by this pass, in order
   uint32_t *emit_n;          // [S]
+  const float *tc_b;         // non-null: k_filterbank_tc; the analysis matrix split into three TF32 terms, pre-swizzled (filterbank_tc.cuh)
   // ISO mode level 2 (iso_psy.cuh)
   const PsyTab *psy;
   float *gc_psy;             // [S][GC][24] threshold / energy per long scalefactor band (22), perceptual entropy, mean tonality

@@ -20,6 +20,8 @@ for i in range(S):
 ptrs = (C.c_void_p * S)(*[pcm[i].data_ptr() for i in range(S)])
 ns = (C.c_size_t * S)(*([n_per * CHN] * S))
 b = mp3.EncoderBatch(mp3.MP3EncoderOptions(mode=mp3.Mode.stereo if CHN == 2 else mp3.Mode.mono), S, 0)
+if os.environ.get("MP3B_MATRIXING"):
+    b.set_matrixing(int(os.environ["MP3B_MATRIXING"]))
 tot = {}
 for k in range(steps + 2):
     b.reset(); b.encode_device(ptrs, ns, flush=True, download=False)
