@@ -85,6 +85,11 @@ struct mp3b_batch {
   StreamPlan *h_plan = nullptr;                          // pinned [2][S]
   StreamPlan *d_plan[2] = {nullptr, nullptr};
   cudaStream_t st_copy = nullptr, st_d2h = nullptr;
+  // The tail of a pass (scan, pack, frames: latency- and issue-bound, FMA pipe idle) runs on st_tail beside the head of the next
+  // pass (filterbank, granule) on st.  What the head writes for the tail exists twice, selected by pass parity (alt = parity 1).
+  cudaStream_t st_tail = nullptr;
+  cudaEvent_t ev_head_done[2] = {}, ev_tail_done[2] = {};
+  PassBuffers alt{};                                      // only the head -> tail arrays are set
   size_t h_pitch = 0;                                    // > 0: h_out is [S][h_pitch] (progressive download), else compact at h_offsets
   cudaEvent_t ev_h2d[2][2] = {}, ev_consumed[2] = {};
   StreamState *h_state = nullptr;                        // pinned [S]
@@ -106,7 +111,7 @@ struct mp3b_batch {
   float stage_ms[MP3B_STAGE_COUNT] = {};
   int launches = 0, passes = 0;
   cudaEvent_t ev[MP3B_STAGE_COUNT + 1] = {};
-  cudaEvent_t evp[2][9] = {};                            // per-pass stage boundaries ([8] = the pass's results are on the host)
+  cudaEvent_t evp[2][10] = {};                           // per-pass stage boundaries ([8] = the pass's results are on the host, [9] = end of the head)
   // trace
   int trace = 0;
   std::vector<std::vector<mp3b_frame_record>> tr_frames;
@@ -233,12 +238,16 @@ void free_batch(mp3b_batch *b) {
   PassBuffers &p = b->pb;
   void *dev[] = {p.plan, p.state, b->d_head[0], b->d_head[1], p.ms, p.frame_energy, p.gc_energy, p.gc_bt, p.frame_br, p.spec, p.sub, p.smag,
                  p.gc_meta, p.gc_bits, p.gc_bv, p.gc_bitoff, p.gc_sel, p.fr_md, p.rec, p.emit, p.md, p.md_tail, p.md_carry, p.out,
-                 p.emit_size, p.emit_n, p.tr_ix, p.tr_thr, p.gc_psy, p.gc_sf, b->d_psy, b->d_tc_b, b->d_stage[0], b->d_stage[1], b->d_stage16[0], b->d_stage16[1], b->d_plan[1], b->d_offsets, b->d_compact};
+                 p.emit_size, p.emit_n, p.tr_ix, p.tr_thr, p.gc_psy, p.gc_sf, b->d_psy, b->d_tc_b, b->alt.smag, b->alt.gc_meta, b->alt.gc_bits, b->alt.gc_bv, b->alt.gc_bt, b->alt.gc_energy, b->alt.frame_br,
+                 b->alt.frame_energy, b->alt.ms, b->alt.gc_psy, b->alt.gc_sf, b->d_stage[0], b->d_stage[1], b->d_stage16[0], b->d_stage16[1], b->d_plan[1], b->d_offsets, b->d_compact};
   for (void *q : dev) if (q) cudaFree(q);
   void *host[] = {b->h_plan, b->h_state, b->h_emit_size, b->h_emit_n, b->h_offsets, b->h_out};
   for (void *q : host) if (q) cudaFreeHost(q);
   for (auto &e : b->ev) if (e) cudaEventDestroy(e);
   for (auto &e : b->ev_consumed) if (e) cudaEventDestroy(e);
+  for (auto &e : b->ev_head_done) if (e) cudaEventDestroy(e);
+  for (auto &e : b->ev_tail_done) if (e) cudaEventDestroy(e);
+  if (b->st_tail) { cudaStreamSynchronize(b->st_tail); cudaStreamDestroy(b->st_tail); }
   for (auto &r : b->evp) for (auto &e : r) if (e) cudaEventDestroy(e);
   for (auto &r : b->ev_h2d) for (auto &e : r) if (e) cudaEventDestroy(e);
   if (b->st) cudaStreamDestroy(b->st);
@@ -282,6 +291,13 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   A(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
   A(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
   A(cudaStreamCreateWithFlags(&b->st_d2h, cudaStreamNonBlocking));
+  {
+    int lo_prio = 0, hi_prio = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);          // the tail's short kernels go first whenever an SM has room
+    A(cudaStreamCreateWithPriority(&b->st_tail, cudaStreamNonBlocking, hi_prio));
+  }
+  for (auto &ev : b->ev_head_done) A(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : b->ev_tail_done) A(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   A(dalloc(p.plan, S)); A(dalloc(b->d_plan[1], S)); A(dalloc(p.state, S));
   A(dalloc(b->d_head[0], S * 2 * cfg.fsc)); A(dalloc(b->d_head[1], S * 2 * cfg.fsc));
   A(dalloc(p.ms, S * (Fc + 1))); A(dalloc(p.frame_energy, S * Fc)); A(dalloc(p.gc_energy, S * (10 + GC)));
@@ -290,6 +306,12 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   A(dalloc(p.sub, S * cfg.channels * (size_t)p.sub_rows * 32, false));
   A(cudaMemset2D(p.sub, (size_t)p.sub_rows * 32 * sizeof(float), 0, 576 * sizeof(float), S * cfg.channels));
   A(dalloc(p.gc_meta, S * GC)); A(dalloc(p.gc_bits, S * GC * kMaxEntries)); A(dalloc(p.gc_bv, S * GC * kMaxEntries));
+  if (getenv("MP3B_OVERLAP")) {                                // second copy of what a pass's head hands to its tail (two-stream pipeline, opt-in)
+    PassBuffers &q = b->alt;
+    A(dalloc(q.ms, S * (Fc + 1))); A(dalloc(q.frame_energy, S * Fc)); A(dalloc(q.gc_energy, S * (10 + GC)));
+    A(dalloc(q.gc_bt, S * GC)); A(dalloc(q.frame_br, S * Fc)); A(dalloc(q.smag, S * GC * 576, false));
+    A(dalloc(q.gc_meta, S * GC)); A(dalloc(q.gc_bits, S * GC * kMaxEntries)); A(dalloc(q.gc_bv, S * GC * kMaxEntries));
+  }
   A(dalloc(p.gc_bitoff, S * GC)); A(dalloc(p.gc_sel, S * GC)); A(dalloc(p.fr_md, S * Fc * 2)); A(dalloc(p.rec, S * (Fc + 1))); A(dalloc(p.emit, S * (Fc + 1)));
   p.md_stride = round_up<size_t>(kMdCarryCap + (size_t)Fc * 2 * cfg.channels * 540, 16);
   A(dalloc(p.md, S * p.md_stride + 16, false));   // + one word: k_frames reads aligned word pairs
@@ -309,7 +331,7 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
     free_batch(b);
     return fail(e == cudaErrorMemoryAllocation ? MP3B_ERR_OOM : MP3B_ERR_CUDA, "batch allocation failed: %s", cudaGetErrorString(e));
   }
-  if (!cfg.vbr && cudaMemset(p.frame_br, cfg.cbr_index, S * Fc) != cudaSuccess) { free_batch(b); return fail(MP3B_ERR_CUDA, "batch initialisation failed"); }   // constant for CBR: the pre-pass may be skipped
+  if (!cfg.vbr && (cudaMemset(p.frame_br, cfg.cbr_index, S * Fc) != cudaSuccess || (b->alt.frame_br && cudaMemset(b->alt.frame_br, cfg.cbr_index, S * Fc) != cudaSuccess))) { free_batch(b); return fail(MP3B_ERR_CUDA, "batch initialisation failed"); }   // constant for CBR: the pre-pass may be skipped
   // The zero fills above ran on the legacy default stream; the engine's own streams are non-blocking and never synchronise
   // with it, so the batch is handed out only when they have landed.
   if (cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { free_batch(b); return fail(MP3B_ERR_CUDA, "batch initialisation failed"); }
@@ -376,6 +398,7 @@ int ensure_iso2(mp3b_batch *b) {
   CU(cudaSetDevice(b->device));
   const size_t n = (size_t)b->S * b->GC * 24;
   CU(dalloc(p.gc_psy, n)); CU(dalloc(p.gc_sf, n));
+  if (b->alt.smag) { CU(dalloc(b->alt.gc_psy, n)); CU(dalloc(b->alt.gc_sf, n)); }
   std::unique_ptr<PsyTab> t(new PsyTab);
   build_psy_tab(b->cfg.sample_rate, b->cfg.sfb_index, *t);
   CU(cudaMalloc((void **)&b->d_psy, sizeof(PsyTab)));
@@ -463,6 +486,13 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
     b->tr_psy.assign(S, {}); b->tr_sf.assign(S, {});
   }
   cudaStream_t st = b->st, stc = b->st_copy;
+  // two-stream pass pipeline (see mp3b_batch::st_tail); the trace plane reads per-pass device buffers synchronously and keeps one stream
+  // Opt-in (MP3B_OVERLAP=1 at batch creation) because it measured as a wash on the B200: 107.8 ms per C4 step with, 108.3 ms without
+  // — k_filterbank (165 registers x 128 threads x 3 CTAs) and k_granule (64 x 256 x 4) fill the register file, so tail CTAs displace
+  // head CTAs instead of sharing the SM with them.
+  const bool overlap = !b->trace && b->alt.smag != nullptr;
+  cudaStream_t stt = overlap ? b->st_tail : st;
+  bool tail_used[2] = {false, false};
   // Pass pipeline: while the kernels of pass p run on `st`, the PCM of pass p + 1 crosses PCIe on `st_copy` into the
   // other staging buffer.  Planning is pure host arithmetic (it never needs device results), so it runs one pass ahead.
   std::vector<const float *> src[2] = {std::vector<const float *>(S), std::vector<const float *>(S)};
@@ -523,6 +553,7 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
           if (hp[s].cur_n) CU(cudaMemcpyAsync(stage + (size_t)s * b->stage_stride * eb, src[slot][s], hp[s].cur_n * eb, cudaMemcpyHostToDevice, stc));
       }
     }
+    if (tail_used[slot]) CU(cudaStreamWaitEvent(stc, b->ev_tail_done[slot], 0));   // the tail that last read this plan slot (slot == pass parity)
     CU(cudaMemcpyAsync(b->d_plan[slot], hp, (size_t)S * sizeof(StreamPlan), cudaMemcpyHostToDevice, stc));
     if (!device_ptrs && elem_bytes == 2) {                             // widen on the copy stream, behind the previous pass's kernels
       int k = launch_widen_i16(b->d_stage16[slot], b->d_stage[slot], b->stage_stride, b->d_plan[slot], S, stc);
@@ -542,7 +573,11 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
     if (se != cudaSuccess) { b->sticky = MP3B_ERR_CUDA; return fail(MP3B_ERR_CUDA, "device pipeline failed: %s", cudaGetErrorString(se)); }
     {
       static const int stage_of[7] = {MP3B_STAGE_H2D, MP3B_STAGE_PREPASS, MP3B_STAGE_SPECTRUM, MP3B_STAGE_CURVE, MP3B_STAGE_SCAN, MP3B_STAGE_PACK, MP3B_STAGE_FRAMES};
-      for (int i = 1; i < 7; ++i) { float ms = 0; cudaEventElapsedTime(&ms, b->evp[par][i], b->evp[par][i + 1]); b->stage_ms[stage_of[i]] += ms; }
+      for (int i = 1; i < 7; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, b->evp[par][i], b->evp[par][i == 3 ? 9 : i + 1]);   // the head ends at [9]; [4] is the start of the tail on its own stream
+        b->stage_ms[stage_of[i]] += ms;
+      }
       { float ms = 0; cudaEventElapsedTime(&ms, b->ev_h2d[slot][0], b->ev_h2d[slot][1]); b->stage_ms[MP3B_STAGE_H2D] += ms; }
       float ms = 0; cudaEventElapsedTime(&ms, b->evp[par][0], b->evp[par][7]); b->stage_ms[MP3B_STAGE_TOTAL] += ms;
     }
@@ -614,11 +649,18 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
   while (have) {
     const StreamPlan *hplan = b->h_plan + (size_t)slot * S;
     CU(cudaStreamWaitEvent(st, b->ev_h2d[slot][1], 0));
+    if (tail_used[par]) CU(cudaStreamWaitEvent(st, b->ev_tail_done[par], 0));   // the tail two passes back has let go of this parity's arrays
     cudaEvent_t *ev = b->evp[par];
     CU(cudaEventRecord(ev[0], st));
     CU(cudaEventRecord(ev[1], st));
     // ---- device pipeline
     PassBuffers pb = b->pb;
+    if (par && overlap) {
+      const PassBuffers &q = b->alt;
+      pb.ms = q.ms; pb.frame_energy = q.frame_energy; pb.gc_energy = q.gc_energy; pb.gc_bt = q.gc_bt; pb.frame_br = q.frame_br; pb.smag = q.smag;
+      pb.gc_meta = q.gc_meta; pb.gc_bits = q.gc_bits; pb.gc_bv = q.gc_bv;
+      if (q.gc_psy) { pb.gc_psy = q.gc_psy; pb.gc_sf = q.gc_sf; }
+    }
     pb.plan = b->d_plan[slot];
     pb.max_frames = 0;
     for (int s = 0; s < S; ++s) pb.max_frames = std::max<int>(pb.max_frames, (int)hplan[s].n_frames);
@@ -632,6 +674,7 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
     // CBR without joint stereo needs nothing from the pre-pass but the block type, which k_granule then derives from the PCM
     // itself (one pass less over the input); the trace plane keeps the pre-pass for its energy records
     const bool fused_prepass = !cfg.vbr && cfg.mode != 2 && !b->trace;
+    // ---- head (stream st): everything that depends on the PCM alone
     if (!fused_prepass) LAUNCH(launch_prepass(cfg, pb, st));
     CU(cudaEventRecord(ev[2], st));
     LAUNCH(launch_spectrum(cfg, pb, st));
@@ -640,25 +683,32 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
     LAUNCH(launch_curve(cfg, pb, st, fused_prepass));
     if (cfg.iso >= 2) LAUNCH(launch_outer(cfg, pb, st));           // ... and the scalefactor outer loop on k_granule's magnitudes
     if (b->trace & 4) LAUNCH(launch_thresholds(cfg, pb, st));
-    CU(cudaEventRecord(ev[4], st));
-    LAUNCH(launch_scan(cfg, pb, st));
-    if (cfg.iso) LAUNCH(launch_clear_md(cfg, pb, st));             // stuffing bytes of the reservoir are never written: start from zeros
-    CU(cudaEventRecord(ev[5], st));
-    LAUNCH(launch_pack(cfg, pb, st));
-    CU(cudaEventRecord(ev[6], st));
-    LAUNCH(launch_frames(cfg, pb, st));
-    LAUNCH(launch_carry(cfg, pb, st));
-    CU(cudaEventRecord(ev[7], st));
-    CU(cudaEventRecord(b->ev_consumed[slot], st));
-    b->passes += 1;
+    LAUNCH(launch_carry_head(cfg, pb, st));
+    CU(cudaEventRecord(ev[9], st));
+    CU(cudaEventRecord(b->ev_consumed[slot], st));                 // the staging buffer is free (the tail does not read PCM)
+    CU(cudaEventRecord(b->ev_head_done[par], st));
     b->head_sel ^= 1;
-    CU(cudaMemcpyAsync(b->h_emit_n + (size_t)par * S, pb.emit_n, (size_t)S * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(b->h_emit_size + (size_t)par * S * (Fc + 1), pb.emit_size, (size_t)S * (Fc + 1) * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    // ---- tail (stream stt): the serial scan and what hangs on it; in order on its stream, so scan(p + 1) follows carry_tail(p)
+    CU(cudaStreamWaitEvent(stt, b->ev_head_done[par], 0));
+    CU(cudaEventRecord(ev[4], stt));
+    LAUNCH(launch_scan(cfg, pb, stt));
+    if (cfg.iso) LAUNCH(launch_clear_md(cfg, pb, stt));            // stuffing bytes of the reservoir are never written: start from zeros
+    CU(cudaEventRecord(ev[5], stt));
+    LAUNCH(launch_pack(cfg, pb, stt));
+    CU(cudaEventRecord(ev[6], stt));
+    LAUNCH(launch_frames(cfg, pb, stt));
+    LAUNCH(launch_carry_tail(cfg, pb, stt));
+    CU(cudaEventRecord(ev[7], stt));
+    CU(cudaEventRecord(b->ev_tail_done[par], stt));
+    tail_used[par] = true;
+    b->passes += 1;
+    CU(cudaMemcpyAsync(b->h_emit_n + (size_t)par * S, pb.emit_n, (size_t)S * sizeof(uint32_t), cudaMemcpyDeviceToHost, stt));
+    CU(cudaMemcpyAsync(b->h_emit_size + (size_t)par * S * (Fc + 1), pb.emit_size, (size_t)S * (Fc + 1) * sizeof(uint16_t), cudaMemcpyDeviceToHost, stt));
     if (b->trace) {
       b->h_rec.resize((size_t)S * (Fc + 1));
-      CU(cudaMemcpyAsync(b->h_rec.data(), pb.rec, b->h_rec.size() * sizeof(FrameRec), cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(b->h_rec.data(), pb.rec, b->h_rec.size() * sizeof(FrameRec), cudaMemcpyDeviceToHost, stt));
     }
-    CU(cudaEventRecord(ev[8], st));
+    CU(cudaEventRecord(ev[8], stt));
     // the previous pass: its kernels finished before this one's started, so this wait is short and the device stays busy
     if (open_slot >= 0) { rc = finish_pass(open_slot, open_par); open_slot = -1; if (rc) return rc; }
     open_slot = slot; open_par = par;
@@ -673,6 +723,7 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
   }
   if (open_slot >= 0) { rc = finish_pass(open_slot, open_par); if (rc) return rc; }
   // ---- results: counters, lengths, optional download
+  if (overlap) for (int k = 0; k < 2; ++k) if (tail_used[k]) CU(cudaStreamWaitEvent(st, b->ev_tail_done[k], 0));
   CU(cudaEventRecord(b->ev[0], st));
   LAUNCH(launch_compact(cfg, b->pb, b->d_offsets, nullptr, 0, st));
   CU(cudaMemcpyAsync(b->h_state, b->pb.state, (size_t)S * sizeof(StreamState), cudaMemcpyDeviceToHost, st));

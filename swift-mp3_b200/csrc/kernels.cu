@@ -1371,8 +1371,11 @@ __global__ void __launch_bounds__(128) k_frames(Config cfg, PassBuffers pb) {
 // ------------------------------------------------------------------------------------------------------------
 // K_carry: state that crosses the pass boundary: last frame + pending partial PCM, reservoir backlog bytes, VBR
 // history, stereo decision of the carried frame.  One CTA per stream.
-__global__ void __launch_bounds__(256) k_carry(Config cfg, PassBuffers pb) {
-  __shared__ uint8_t tail[kMdCarryCap];
+// The pass boundary in two halves, so that the tail of a pass (scan, pack, frames) can run beside the head of the next one
+// (filterbank, granule) on a second stream: what the NEXT HEAD needs is known once k_granule is done — the carried PCM frame and
+// pending samples, the MDCT overlap rows, the VBR energy history and the stereo decision of the last frame (k_carry_head) —,
+// what the next SCAN needs comes out of this pass's scan — the main-data backlog (k_carry_tail).
+__global__ void __launch_bounds__(256) k_carry_head(Config cfg, PassBuffers pb) {
   const int s = blockIdx.x, tid = threadIdx.x;
   const StreamPlan plan = pb.plan[s];
   const PcmView pv = pcm_view(cfg, pb, s);
@@ -1382,12 +1385,6 @@ __global__ void __launch_bounds__(256) k_carry(Config cfg, PassBuffers pb) {
   const int keep = cfg.fsc + (int)left;
   float *dst = pb.head_out + (size_t)s * 2 * cfg.fsc;
   for (int i = tid; i < keep && i < 2 * cfg.fsc; i += 256) dst[i] = pv.at(start + i);
-  const uint32_t R = pb.md_tail[(size_t)s * 4], len = pb.md_tail[(size_t)s * 4 + 1], B0 = pb.md_tail[(size_t)s * 4 + 2];
-  uint8_t *carry = pb.md_carry + (size_t)s * kMdCarryCap;
-  const uint8_t *md = pb.md + (size_t)s * pb.md_stride;
-  for (uint32_t i = tid; i < len; i += 256) { uint32_t o = R + i; tail[i] = o < B0 ? carry[o] : md[o]; }
-  __syncthreads();
-  for (uint32_t i = tid; i < len; i += 256) carry[i] = tail[i];
   // MDCT overlap (SRC:1534-1535): the last granule's subband rows become rows 0..17 of the next pass
   if (plan.n_frames) {
     const int ngr = 2 * (int)plan.n_frames;
@@ -1407,6 +1404,16 @@ __global__ void __launch_bounds__(256) k_carry(Config cfg, PassBuffers pb) {
     st.vbr_n = count;
     st.ms_prev = pb.ms[(size_t)s * (pb.Fc + 1) + plan.n_frames];
   }
+}
+__global__ void __launch_bounds__(256) k_carry_tail(Config cfg, PassBuffers pb) {
+  __shared__ uint8_t tail[kMdCarryCap];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const uint32_t R = pb.md_tail[(size_t)s * 4], len = pb.md_tail[(size_t)s * 4 + 1], B0 = pb.md_tail[(size_t)s * 4 + 2];
+  uint8_t *carry = pb.md_carry + (size_t)s * kMdCarryCap;
+  const uint8_t *md = pb.md + (size_t)s * pb.md_stride;
+  for (uint32_t i = tid; i < len; i += 256) { uint32_t o = R + i; tail[i] = o < B0 ? carry[o] : md[o]; }
+  __syncthreads();
+  for (uint32_t i = tid; i < len; i += 256) carry[i] = tail[i];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1664,8 +1671,12 @@ int launch_frames(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   k_frames<<<grid, 128, 0, st>>>(cfg, pb);
   return check(1);
 }
-int launch_carry(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
-  k_carry<<<cfg.n_streams, 256, 0, st>>>(cfg, pb);
+int launch_carry_head(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  k_carry_head<<<cfg.n_streams, 256, 0, st>>>(cfg, pb);
+  return check(1);
+}
+int launch_carry_tail(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  k_carry_tail<<<cfg.n_streams, 256, 0, st>>>(cfg, pb);
   return check(1);
 }
 int launch_thresholds(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {

@@ -144,7 +144,9 @@ int launch_clear_md(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_scan(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_pack(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_frames(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
-int launch_carry(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
+// the pass boundary: what the next pass's head needs (after launch_curve) / what its scan needs (after launch_frames)
+int launch_carry_head(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
+int launch_carry_tail(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_thresholds(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 // out_len[s] = state[s].out_pos; offsets = exclusive prefix sum; compact = gather of out rows
 int launch_compact(const Config &cfg, const PassBuffers &pb, uint64_t *offsets /* [S+1] */, uint8_t *compact, int gather,
