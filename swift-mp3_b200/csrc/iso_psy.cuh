@@ -12,7 +12,7 @@
 //     bit reservoir; thresholds mapped onto the 22 long scalefactor bands as ratio = threshold / energy.
 // k_outer then runs the ISO outer loop, one warp per granule-channel: quantize at the smallest global_gain that fits the
 // granule's nominal budget, measure the quantization noise per band (warp-reduced), amplify every band whose noise exceeds
-// ratio * band energy by one scalefactor step, repeat until no band is over, all are amplified or a scalefactor would exceed
+// ratio * band energy (by one scalefactor step per factor of two it is over, at most three), repeat until no band is over, all are amplified or a scalefactor would exceed
 // its field; the best set (fewest bands over) is kept, scalefac_compress chosen, and the bits-vs-gain curve is produced with
 // those scalefactors, exactly as in level 1.  Long blocks only.  Included by kernels.cu.
 #pragma once
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(32 * kPsyWarps) k_psy(Config cfg, PassBuffers 
 __device__ __forceinline__ float pow43_fast(float x) { return x > 0.0f ? exp2f(log2f(x) * (4.0f / 3.0f)) : 0.0f; }
 
 constexpr int kOuterWarps = 4;
-constexpr int kOuterMaxIter = 24;
+constexpr int kOuterMaxIter = 12;
 __device__ __forceinline__ int slen_need(int m) { return m == 0 ? 0 : m < 2 ? 1 : m < 4 ? 2 : m < 8 ? 3 : 4; }
 // scalefac_compress -> (slen1, slen2), ISO 11172-3 2.4.2.7
 __constant__ uint8_t c_slen1[16] = {0, 0, 0, 0, 3, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4};
@@ -255,23 +255,37 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
       if (c_slen1[k] >= n1 && c_slen2[k] >= n2 && 11 * c_slen1[k] + 10 * c_slen2[k] < bits) { bits = 11 * c_slen1[k] + 10 * c_slen2[k]; sfc = k; }
     return bits;
   };
-  // smallest gain >= from whose count fits `budget` (the count falls as the gain rises)
-  auto search = [&](int from, int budget) {
-    int lo = from, hi = kIsoGainMax;
-    for (int stp = 1; lo + stp < hi; stp <<= 1) {                 // gallop: the answer is usually a step or two above `from`
-      if (eval(lo + stp - 1).bits <= budget) { hi = lo + stp - 1; break; }
-      lo = lo + stp;
-    }
+  // smallest gain whose count fits `budget` (the count falls as the gain rises).  Every evaluation costs several hundred
+  // instructions, so the searches start where the answer is expected: search_up gallops upwards from a known lower bound (the
+  // previous outer iteration's gain: amplifying bands only adds bits), search_down downwards from a gain known to fit (the curve
+  // starts below the outer loop's gain: its budget is larger), and only the very first search bisects the whole range.
+  auto bisect = [&](int lo, int hi, int budget) {                  // invariant: gains < lo do not fit, hi fits
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (eval(mid).bits <= budget) hi = mid; else lo = mid + 1; }
     return hi;
   };
+  auto search_up = [&](int from, int budget) {
+    int lo = from, hi = kIsoGainMax;
+    for (int stp = 1; lo + stp < hi; stp <<= 1) {
+      if (eval(lo + stp - 1).bits <= budget) { hi = lo + stp - 1; break; }
+      lo = lo + stp;
+    }
+    return bisect(lo, hi, budget);
+  };
+  auto search_down = [&](int fits, int budget) {
+    int hi = fits, lo = 0;
+    for (int stp = 1; hi - stp > 0; stp <<= 1) {
+      if (eval(hi - stp).bits > budget) { lo = hi - stp + 1; break; }
+      hi = hi - stp;
+    }
+    return bisect(lo, hi, budget);
+  };
   // ---- outer loop at the granule's nominal budget
-  int G = 0, best_over = 99, n_iter = 0;
+  int G = 0, best_over = 99, n_iter = 0, best_G = 0;
   for (int it = 0; it < kOuterMaxIter; ++it) {
     load_amp(sf);
     int sfc;
     const int part2 = part2_of(sf, sfc);
-    G = search(G, max(lo_bits - part2, 0));
+    G = it == 0 ? bisect(0, kIsoGainMax, max(lo_bits - part2, 0)) : search_up(G, max(lo_bits - part2, 0));
     const float inv = c_inv_step_iso[G], step = c_step_iso[G];
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
@@ -286,13 +300,16 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
     const unsigned over = __ballot_sync(0xffffffffu, lane < 21 && noise > xmin);
     const int n_over = __popc(over) + (int)((__ballot_sync(0xffffffffu, lane == 21 && noise > xmin) >> 21) & 1u);
     n_iter = it + 1;
-    if (n_over < best_over) { best_over = n_over; if (lane < 21) best[lane] = sf[lane]; __syncwarp(); }
+    if (n_over < best_over) { best_over = n_over; best_G = G; if (lane < 21) best[lane] = sf[lane]; __syncwarp(); }
     if (over == 0u) break;
-    // amplify the bands over their threshold; stop when a scalefactor would leave its field or every band is amplified
+    // amplify the bands over their threshold — by one step per factor of two the noise is above it (a step takes 1.5 dB off the
+    // band's noise at equal gain), at most three at once; stop when a scalefactor would leave its field or every band is amplified
     const bool mine = lane < 21 && ((over >> lane) & 1u);
     const int lim = lane < 11 ? 15 : 7;
-    if (__ballot_sync(0xffffffffu, mine && sf[lane] + 1 > lim)) break;
-    if (mine) sf[lane] += 1;
+    int add = 1;
+    if (mine) { const float r = noise / fmaxf(xmin, 1e-30f); add = r >= 4.0f ? 3 : r >= 2.0f ? 2 : 1; add = min(add, max(lim - sf[lane], 1)); }
+    if (__ballot_sync(0xffffffffu, mine && sf[lane] + add > lim)) break;
+    if (mine) sf[lane] += add;
     __syncwarp();
     if (__ballot_sync(0xffffffffu, lane < 21 && sf[lane] > 0) == 0x1FFFFFu) break;
   }
@@ -301,7 +318,7 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
   int sfc;
   const int part2 = part2_of(best, sfc);
   uint16_t *bits_out = pb.gc_bits + gslot * kMaxEntries, *bv_out = pb.gc_bv + gslot * kMaxEntries;
-  const int g_first = search(0, max(hi_bits - part2, 0));
+  const int g_first = search_down(max(best_G, 1), max(hi_bits - part2, 0));   // best_G fits the smaller budget lo_bits - part2, so it fits this one
   int n = 0, g_last = g_first, fitted = 0;
   for (int e = 0; e < kMaxEntries - 1 && !fitted; ++e) {
     const int Ge = min(g_first + e, kIsoGainMax);
@@ -311,7 +328,7 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
     fitted = c.bits + part2 <= lo_bits || Ge == kIsoGainMax;
   }
   if (!fitted) {
-    const int Gl = search(min(g_first + kMaxEntries - 1, kIsoGainMax), max(lo_bits - part2, 0));
+    const int Gl = search_up(min(g_first + kMaxEntries - 1, kIsoGainMax), max(lo_bits - part2, 0));
     const IsoChoice c = eval(Gl);
     if (lane == 0) { bits_out[kMaxEntries - 1] = (uint16_t)min(c.bits + part2, 65535); bv_out[kMaxEntries - 1] = (uint16_t)c.bv; }
     n = kMaxEntries; g_last = Gl;

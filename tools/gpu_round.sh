@@ -13,14 +13,22 @@ python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.jso
 [ -x tools/microbench/mb ] && ./tools/microbench/mb > gpurun_out/microbench.txt 2>&1
 if [ "$1" != "noprof" ]; then
 KERN="regex:k_(prepass|bitrate|filterbank|granule|scan|pack|frames|carry|offsets|gather)"
-FULL="python bench.py --steps 1 --warmup 3 --e2e-steps 1 --no-cpu --no-others --parity spot"
+TCK="regex:k_filterbank_tc"
+FULL="python bench.py --steps 1 --warmup 3 --e2e-steps 1 --no-cpu --no-others --no-tc --parity spot"
 $FULL > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERN" -c 400 --csv --log-file gpurun_out/launches.csv $FULL > gpurun_out/ncu1.log 2>&1
 echo ncu1 rc=$?
 # one pass at the bench shape: 4096 streams x 64 frames (1.67 s of audio each) = 1 048 576 granule-channels per launch
-ONE="python bench.py --streams 4096 --seconds 1.67 --steps 1 --warmup 1 --e2e-steps 1 --no-cpu --no-others --parity spot"
+ONE="python bench.py --streams 4096 --seconds 1.67 --steps 1 --warmup 1 --e2e-steps 1 --no-cpu --no-others --no-tc --parity spot"
 $ONE > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k "regex:k_(filterbank|granule|scan|pack|frames|carry)" -s 12 -c 6 -o gpurun_out/prof $ONE > gpurun_out/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:k_(filterbank|granule|scan|pack|frames|carry)" -s 14 -c 7 -o gpurun_out/prof $ONE > gpurun_out/ncu2.log 2>&1
 echo ncu2 rc=$?
+# the opt-in kernels: tensor-core filterbank (one launch at the bench shape), ISO mode psychoacoustic model and outer loop
+MP3B_MATRIXING=1 python tools/stage_times.py 4096 1.671837 1 > gpurun_out/plain3.log 2>&1 && \
+MP3B_MATRIXING=1 ncu --set full --clock-control none --import-source on -k "$TCK" -s 2 -c 1 -o gpurun_out/prof_tc python tools/stage_times.py 4096 1.671837 1 > gpurun_out/ncu3.log 2>&1
+echo ncu3 rc=$?
+python tools/iso_bench.py 1024 10 3 > gpurun_out/iso_bench.json 2> gpurun_out/iso_bench.err; echo iso rc=$?
+ncu --set full --clock-control none --import-source on -k "regex:k_(psy|outer|pack_iso)" -s 3 -c 3 -o gpurun_out/prof_iso python tools/iso_bench.py 256 10 1 > gpurun_out/ncu4.log 2>&1
+echo ncu4 rc=$?
 fi
 ls -la gpurun_out | tail -12
