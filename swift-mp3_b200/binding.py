@@ -288,6 +288,14 @@ class EncoderBatch:
         """Opt-in ISO mode (include/mp3b200.h): ISO quantizer, table selection, count1, real main_data_begin."""
         _check(lib().mp3b_batch_set_iso_mode(self._h, int(on)))
 
+    @property
+    def iso_mode(self):
+        return lib().mp3b_batch_iso_mode(self._h)
+
+    @property
+    def matrixing(self):
+        return lib().mp3b_batch_matrixing(self._h)
+
     def set_matrixing(self, mode):
         """0 = FP32 FMA (default, bit-exact with the oracle), 1 = 3xTF32 on the tensor cores (include/mp3b200.h)."""
         _check(lib().mp3b_batch_set_matrixing(self._h, int(mode)))

@@ -85,7 +85,7 @@ __device__ __forceinline__ void split3(float y, float &hi, float &mid, float &lo
 template <int CH> __global__ void __launch_bounds__(kTcThreads, 2) k_filterbank_tc(Config cfg, PassBuffers pb, int Rdbg) {
   const int R = Rdbg & 0xFFFF, dbg = Rdbg >> 16;     // dbg: timing experiments only (tools/stage_times.py), 0 in production
   extern __shared__ uint8_t tc_raw[];
-  uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *base = tc_raw + ((1024u - (smem_u32(tc_raw) & 1023u)) & 1023u);   // (pointer arithmetic, so that the accesses stay LDS / STS)
   uint8_t *sA = base;                               // [3 terms][128 rows][128 bytes], swizzled
   uint8_t *sB = sA + kTcABytes;                     // [2 halves][96 rows][128 bytes], swizzled (as it lies in pb.tc_b)
   float *P = reinterpret_cast<float *>(sB + kTcBBytes);   // [143][32 * CH] PCM rows of the tile, interleaved as in the input

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(32 * kPsyWarps) k_psy(Config cfg, PassBuffers 
 __device__ __forceinline__ float pow43_fast(float x) { return x > 0.0f ? exp2f(log2f(x) * (4.0f / 3.0f)) : 0.0f; }
 
 constexpr int kOuterWarps = 4;
-constexpr int kOuterMaxIter = 12;
+constexpr int kOuterMaxIter = 8;
 __device__ __forceinline__ int slen_need(int m) { return m == 0 ? 0 : m < 2 ? 1 : m < 4 ? 2 : m < 8 ? 3 : 4; }
 // scalefac_compress -> (slen1, slen2), ISO 11172-3 2.4.2.7
 __constant__ uint8_t c_slen1[16] = {0, 0, 0, 0, 3, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4};
@@ -193,8 +193,10 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
   __shared__ uint8_t s_c[kOuterWarps][288];
   __shared__ float s_val[kOuterWarps][288];
   __shared__ int s_sf[kOuterWarps][2][24];                        // current and best scalefactors
+  __shared__ float s_p43[256];                                    // ix^(4/3) for the values nearly all lines quantize to
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < kHuffEntries; i += 32 * kOuterWarps) s_len[i] = kHuffLenFlat[i];
+  for (int i = threadIdx.x; i < 256; i += 32 * kOuterWarps) s_p43[i] = pow43_fast((float)i);
   __syncthreads();
   const int ch = cfg.channels, chs = ch - 1;
   const int gci = blockIdx.y * kOuterWarps + warp;
@@ -291,7 +293,8 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
     for (int j = 0; j < 9; ++j) {
       const int qx = iso_quant(__fmul_rn(mx[j], a34[j]), inv), qy = iso_quant(__fmul_rn(my[j], a34[j]), inv);
       const float back = step * c_ampinv[sf[bnd[j]]];
-      const float dx = ax[j] - pow43_fast((float)qx) * back, dy = ay[j] - pow43_fast((float)qy) * back;
+      const float px = qx < 256 ? s_p43[qx] : pow43_fast((float)qx), py = qy < 256 ? s_p43[qy] : pow43_fast((float)qy);
+      const float dx = ax[j] - px * back, dy = ay[j] - py * back;
       s_val[warp][lane + 32 * j] = dx * dx + dy * dy;
     }
     __syncwarp();

@@ -852,26 +852,34 @@ def test_iso_level2_psy_and_scalefactors(mp3):
 
 
 def test_iso_mode_session_and_reset_rules(mp3):
-    """The switch is per session / batch, only on fresh sessions; chunked feeding equals one call; the default stays the
-    reference-compatible path."""
+    """The switch is per session / batch, only on fresh sessions; chunked feeding and small passes equal one call (the look-back of
+    the psychoacoustic FFT windows crosses call and pass boundaries); the default stays the reference-compatible path."""
     pcm = signals.sine_noise(0.8, seed=12)
-    s = mp3.MP3Encoder(_opts(mp3)).newSession()
-    s.set_iso_mode(True)
-    one = s.encode(pcm) + s.flush()
-    s.close()
-    s = mp3.MP3Encoder(_opts(mp3)).newSession()
-    s.set_iso_mode(True)
-    parts = s.encode(pcm[:5000]) + s.encode(pcm[5000:30000])
-    with pytest.raises(mp3.MP3BError):
-        s.set_iso_mode(False)                                   # mid-stream
-    parts += s.encode(pcm[30000:]) + s.flush()
-    assert parts == one
-    s.close()
-    b = mp3.EncoderBatch(_opts(mp3), 3, devices=[0, 0])
-    b.set_iso_mode(True)
-    assert b.encode([pcm, pcm[:7777], pcm], flush=True)[0] == one
-    b.reset(); b.set_iso_mode(False)
-    import oracle_binding as orc
-    ref, _ = orc.encode_all(pcm)
-    assert b.encode([pcm, None, None], flush=True)[0] == ref
-    b.close()
+    for level in (1, 2):
+        s = mp3.MP3Encoder(_opts(mp3)).newSession()
+        s.set_iso_mode(level)
+        one = s.encode(pcm) + s.flush()
+        s.close()
+        s = mp3.MP3Encoder(_opts(mp3)).newSession()
+        s.set_iso_mode(level)
+        parts = s.encode(pcm[:5000]) + s.encode(pcm[5000:30000])
+        with pytest.raises(mp3.MP3BError):
+            s.set_iso_mode(0)                                   # mid-stream
+        parts += s.encode(pcm[30000:]) + s.flush()
+        assert parts == one, level
+        s.close()
+        b = mp3.EncoderBatch(_opts(mp3), 3, devices=[0, 0])
+        b.set_iso_mode(level)
+        assert b.encode([pcm, pcm[:7777], pcm], flush=True)[0] == one
+        b.close()
+        b = mp3.EncoderBatch(_opts(mp3), 2, 0, 5)                # 5-frame passes
+        b.set_iso_mode(level)
+        assert b.encode([pcm, pcm], flush=True) == [one, one]
+        c = b.clone()                                           # a clone keeps the mode (and its buffers)
+        assert c.iso_mode == level
+        c.close()
+        b.reset(); b.set_iso_mode(0)
+        import oracle_binding as orc
+        ref, _ = orc.encode_all(pcm)
+        assert b.encode([pcm, None], flush=True)[0] == ref
+        b.close()
