@@ -338,6 +338,20 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   b->pending.assign(S, 0); b->out_len.assign(S, 0); b->frame_count.assign(S, 0); b->byte_count.assign(S, 0);
   b->frame_sizes.resize(S);
   b->d_plan[0] = p.plan;
+  // A small batch (a session is a batch of one) gets its staging, output and pinned download buffers now instead of inside its
+  // first encode call: four allocations, one of them pinned, are most of what a single short stream costs end to end.
+  const size_t stage_bytes = S * (size_t)Fc * cfg.fsc * sizeof(float);
+  if (stage_bytes <= ((size_t)64 << 20)) {
+    b->stage_stride = (size_t)Fc * cfg.fsc;
+    const size_t out_stride = round_up<size_t>((size_t)(Fc + 2) * b->max_frame_bytes, 16), total = S * out_stride;
+    bool ok = cudaMalloc((void **)&b->d_stage[0], stage_bytes) == cudaSuccess && cudaMalloc((void **)&b->d_stage[1], stage_bytes) == cudaSuccess &&
+              cudaMalloc((void **)&b->pb.out, total) == cudaSuccess;
+    if (ok) { b->out_cap_bytes = total; b->pb.out_stride = out_stride; }
+    const size_t cap = round_up<size_t>(total + total / 8 + 4096, 4096);
+    if (ok && cudaMalloc((void **)&b->d_compact, cap) == cudaSuccess) b->compact_cap = cap; else ok = false;
+    if (ok && cudaHostAlloc((void **)&b->h_out, cap, cudaHostAllocDefault) == cudaSuccess) b->h_out_cap = cap; else ok = false;
+    if (!ok) { cudaGetLastError(); free_batch(b); return fail(MP3B_ERR_OOM, "batch allocation failed"); }
+  }
   *out = b;
   return MP3B_OK;
 }
@@ -452,7 +466,10 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
   if (rc) return rc;
   // Host input is bound by PCIe, so the call is cut into about a dozen passes: the kernels and the download of pass p hide
   // behind the upload of pass p + 1 and only the last pass is exposed.  Device input keeps the largest passes.
-  const int Fp = device_ptrs ? Fc : (int)std::min<size_t>((size_t)Fc, std::max<size_t>((max_frames + 11) / 12, (size_t)std::min(Fc, 48)));
+  // ... as long as a pass still uploads some 16 MB: below that the fixed cost of a pass (8 launches, events, a host wake-up) is larger
+  // than the copy it hides, so a single stream of a few seconds goes through in one or two passes (C1: 8 passes -> 1)
+  const size_t min_pass_frames = ((size_t)16 << 20) / ((size_t)S * fsc * (size_t)elem_bytes) + 1;
+  const int Fp = device_ptrs ? Fc : (int)std::min<size_t>((size_t)Fc, std::max<size_t>(std::max<size_t>((max_frames + 11) / 12, (size_t)std::min(Fc, 48)), min_pass_frames));
   // progressive download: after every pass the byte columns that pass produced are copied for all streams with one
   // strided D2H on its own stream into a pitched pinned buffer [S][out_stride]
   bool progressive = download && !device_ptrs && max_frames > (size_t)Fp;   // single-pass calls keep the compact copy
