@@ -288,4 +288,5 @@ template <int CH> __global__ void __launch_bounds__(kTcThreads, 2) k_filterbank_
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_d));
 }
 
+
 }  // namespace mp3b
