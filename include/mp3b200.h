@@ -148,12 +148,16 @@ uint32_t mp3b_batch_byte_count(const mp3b_batch *b, int stream);
  * scale, global_gain by bit-count search, rzero / count1 / big_values partition, three regions with the cheapest of tables
  * 1-3, 5-13, 15, 16-31 (linbits escapes) each, count1 table A or B, a real main_data_begin back pointer with stuffing, M/S
  * signalled per frame with 1/sqrt(2) scaling, the ISO CRC.  An independent decoder then reconstructs the INPUT signal.  Long
- * blocks only.  Only on fresh sessions (after create / reset).
+ * blocks only at levels 1 and 2.  Only on fresh sessions (after create / reset).
  * on = 2 adds north_star stages (3) and (4) in full (csrc/iso_psy.cuh; the reference's stubs: ScaleFactorBands.scale SRC:1831-1876,
  * ScaleFactorCompression SRC:2017-2037, its unused masking thresholds SRC:1983-2013): a psychoacoustic model batched over
  * granule-channels — 1024-point FFT line energies, 256-point FFT unpredictability, 1/3-Bark partitions, spreading function,
  * tonality, masking thresholds, perceptual entropy — and the scalefactor outer loop (noise per band against the threshold,
- * amplification, scalefac_compress, part2 bits); the perceptual entropy steers each granule's share of the bit reservoir. */
+ * amplification, scalefac_compress, part2 bits); the perceptual entropy steers each granule's share of the bit reservoir.
+ * on = 3 adds window switching (north_star stage 2: "block type taken from a transient-detection kernel"): ISO start / short / stop
+ * blocks with the windows the reference defines and never uses (SRC:1470-1503), short-block lines in scalefactor-band order,
+ * two-region side info.  The start window needs one granule of look-ahead: at this level the signal is coded 576 samples late
+ * (one more granule of encoder delay) and joint stereo is coded as L / R. */
 int mp3b_batch_set_iso_mode(mp3b_batch *b, int on);
 int mp3b_batch_iso_mode(const mp3b_batch *b);
 int mp3b_session_set_iso_mode(mp3b_session *s, int on);

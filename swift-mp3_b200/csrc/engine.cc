@@ -693,6 +693,7 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
     const bool fused_prepass = !cfg.vbr && cfg.mode != 2 && !b->trace;
     // ---- head (stream st): everything that depends on the PCM alone
     if (!fused_prepass) LAUNCH(launch_prepass(cfg, pb, st));
+    if (cfg.iso >= 3) LAUNCH(launch_blocktype(cfg, pb, st));       // ISO mode level 3: block types with one granule of look-ahead
     CU(cudaEventRecord(ev[2], st));
     LAUNCH(launch_spectrum(cfg, pb, st));
     CU(cudaEventRecord(ev[3], st));
@@ -1155,7 +1156,7 @@ int mp3b_batch_clone(const mp3b_batch *src, mp3b_batch **out) {
   A(cudaMemcpyAsync(b->pb.md_carry, src->pb.md_carry, S * kMdCarryCap, cudaMemcpyDeviceToDevice, b->st));
   A(cudaStreamSynchronize(b->st));
   if (e != cudaSuccess) { free_batch(b); return fail(MP3B_ERR_CUDA, "clone failed: %s", cudaGetErrorString(e)); }
-  b->head_sel = src->head_sel; b->cfg.iso = src->cfg.iso; b->cfg.ms_scale = src->cfg.ms_scale;
+  b->head_sel = src->head_sel; b->cfg.iso = src->cfg.iso; b->cfg.ms_scale = src->cfg.ms_scale; b->cfg.iso_delay = src->cfg.iso_delay;
   if (b->cfg.iso >= 2 && ensure_iso2(b) != MP3B_OK) { free_batch(b); return MP3B_ERR_CUDA; }
   if (src->pb.tc_b && mp3b_batch_set_matrixing(b, 1) != MP3B_OK) { free_batch(b); return MP3B_ERR_CUDA; }
   b->pending = src->pending; b->frame_count = src->frame_count; b->byte_count = src->byte_count; b->frame_sizes = src->frame_sizes;
@@ -1189,14 +1190,15 @@ int mp3b_batch_set_iso_mode(mp3b_batch *b, int on) {
   if (!b) return fail(MP3B_ERR_BAD_ARG, "null batch");
   if (is_multi(b)) {
     for (mp3b_batch *p : b->parts) { const int rc = mp3b_batch_set_iso_mode(p, on); if (rc) return rc; }
-    b->cfg.iso = on < 0 ? 0 : on > 2 ? 2 : on;
+    b->cfg.iso = on < 0 ? 0 : on > 3 ? 3 : on;
     return MP3B_OK;
   }
   for (int s = 0; s < b->S; ++s)
     if (b->pending[(size_t)s] || b->frame_count[(size_t)s]) return fail(MP3B_ERR_BAD_ARG, "iso mode can only be changed on fresh sessions (after create or reset)");
-  const int level = on < 0 ? 0 : on > 2 ? 2 : on;
+  const int level = on < 0 ? 0 : on > 3 ? 3 : on;
   if (level >= 2) { const int rc = ensure_iso2(b); if (rc) return rc; }
   b->cfg.iso = level;
+  b->cfg.iso_delay = level >= 3 ? 576 : 0;
   b->cfg.ms_scale = on ? 0.70710678118654752440f : 0.5f;
   return MP3B_OK;
 }

@@ -105,7 +105,7 @@ template <int CH> __global__ void __launch_bounds__(kTcThreads, 2) k_filterbank_
   const uint8_t *msrow = pb.ms + (size_t)s * (pb.Fc + 1);
   const uint32_t ms_prev = pb.state[s].ms_prev;
   const bool joint = cfg.mode == 2;
-  const int n_start = 576 * g_begin - 480;
+  const int n_start = 576 * g_begin - 480 - cfg.iso_delay;
   float *out = pb.sub + ((size_t)(s * CH + c) * pb.sub_rows + 18 * (g_begin + 1)) * 32;
   const uint32_t bar_mma = smem_u32(bars), bar_b = smem_u32(bars + 1), bar_p = smem_u32(bars + 2);
 

@@ -64,7 +64,9 @@ struct IsoChoice {            // everything the side info and the bit packer nee
 
 // Bit count and all choices for the quantized pairs (qx[j], qy[j]) = lines 2 p, 2 p + 1 of pair p = lane + 32 j.
 // s_len: the concatenated length tables in shared memory; s_c: 288 bytes of warp scratch; sfb: cumulative band ends (21).
-__device__ __forceinline__ IsoChoice iso_evaluate(const int qx[9], const int qy[9], int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb) {
+// ws: the granule is window-switched (block type start / short / stop): the side info then has two regions only, region 0 = the
+// first 36 lines (ISO 11172-3 2.4.2.7: region0_count 7 resp. 8 and region1_count 13 are implied), two table_selects.
+__device__ __forceinline__ IsoChoice iso_evaluate(const int qx[9], const int qy[9], int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb, bool ws = false) {
   IsoChoice ch;
   int top = 0, big = 0;
 #pragma unroll
@@ -86,6 +88,7 @@ __device__ __forceinline__ IsoChoice iso_evaluate(const int qx[9], const int qy[
   const int k0 = min(max((nb + 1) / 3, 1), 16), k1 = min(max((nb + 1) / 3, 1), 8);
   ch.r0 = k0 - 1; ch.r1 = k1 - 1;
   ch.a1 = sfb[k0 - 1]; ch.a2 = k0 + k1 - 1 < 21 ? sfb[k0 + k1 - 1] : 576;
+  if (ws) { ch.r0 = 0; ch.r1 = 0; ch.a1 = 36; ch.a2 = 576; }
   int m0 = 0, m1 = 0, m2 = 0;
 #pragma unroll
   for (int j = 0; j < 9; ++j) {
@@ -152,6 +155,42 @@ __device__ __forceinline__ IsoChoice iso_evaluate(const int qx[9], const int qy[
   ch.c1sel = cb < ca;
   ch.bits = bits + min(ca, cb);
   return ch;
+}
+
+
+// ---- level 3: window switching ----------------------------------------------------------------------------------------------------
+// ISO 11172-3 block types: 0 normal, 1 start, 2 short (three 12-point windows), 3 stop — the windows the reference defines and never
+// uses (SRC:1470-1503; it switches with plain sine windows).  A short granule needs a start window in the granule
+// BEFORE it, i.e. one granule of look-ahead.  The look-ahead costs no engine change: at level 3 the filterbank (and the
+// psychoacoustic window) read the PCM 576 samples late — inside the carried frame every pass already holds — while the transient
+// detector (the reference's, SRC:1944-1968: thirds of 192 samples, max / min > 6) looks at the newest granule, which for the
+// delayed signal IS the next granule.  With a(j) = attack in PCM granule j of either channel, delayed granule g (current = PCM
+// granule g - 1):  short if a(g-1);  else start if a(g), short instead if a(g-2) too (a granule cannot be stop and start at once);
+// else stop if a(g-2);  else normal.  Pure function of the PCM in [carried frame, this pass], so chunking cannot change it.
+__constant__ float c_iso_win[4][36];               // MDCT windows by block type (type 2 unused: kWinShort)
+__constant__ uint16_t c_short_pos[3][192];         // short blocks: line of (frequency 6 sb + m, window 0) in scalefactor-band order
+__constant__ uint8_t c_short_width[3][192];        // ... + window * width of its short scalefactor band
+
+cudaError_t upload_iso_switch_tables() {
+  float win[4][36];
+  const double pi = 3.14159265358979323846;
+  for (int i = 0; i < 36; ++i) {
+    const double l = sin(pi / 36.0 * (i + 0.5));
+    win[0][i] = (float)l; win[2][i] = 0.0f;
+    win[1][i] = (float)(i < 18 ? l : i < 24 ? 1.0 : i < 30 ? sin(pi / 12.0 * (i - 18 + 0.5)) : 0.0);
+    win[3][i] = (float)(i < 6 ? 0.0 : i < 12 ? sin(pi / 12.0 * (i - 6 + 0.5)) : i < 18 ? 1.0 : l);
+  }
+  static const int sfs[3][14] = {{0, 4, 8, 12, 16, 22, 30, 40, 52, 66, 84, 106, 136, 192},       // 44.1 kHz (ISO 11172-3 Table B.8)
+                                 {0, 4, 8, 12, 16, 22, 28, 38, 50, 64, 80, 100, 126, 192},       // 48 kHz
+                                 {0, 4, 8, 12, 16, 22, 30, 42, 58, 78, 104, 138, 180, 192}};     // 32 kHz
+  uint16_t pos[3][192]; uint8_t wid[3][192];
+  for (int r = 0; r < 3; ++r)
+    for (int b = 0; b < 13; ++b)
+      for (int f = sfs[r][b]; f < sfs[r][b + 1]; ++f) { pos[r][f] = (uint16_t)(3 * sfs[r][b] + (f - sfs[r][b])); wid[r][f] = (uint8_t)(sfs[r][b + 1] - sfs[r][b]); }
+  cudaError_t e;
+  if ((e = cudaMemcpyToSymbol(c_iso_win, win, sizeof win))) return e;
+  if ((e = cudaMemcpyToSymbol(c_short_pos, pos, sizeof pos))) return e;
+  return cudaMemcpyToSymbol(c_short_width, wid, sizeof wid);
 }
 
 }  // namespace mp3b

@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(32 * kPsyWarps) k_psy(Config cfg, PassBuffers 
   const PcmView pv = pcm_view(cfg, pb, s);
   float v[32];
   {
-    const int64_t m0 = (int64_t)576 * g - 768 + lane;
+    // (level 3 codes the signal one granule late; its window is the last 1024 samples the carried frame reaches back to)
+    const int64_t m0 = (int64_t)576 * g - (cfg.iso >= 3 ? 1152 : 768) + lane;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const int64_t q = (int64_t)cfg.fsc + (m0 + 32 * i) * ch;
@@ -203,6 +204,8 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
   if (gci >= (int)pb.plan[s].n_frames * 2 * ch) return;
   const size_t gslot = (size_t)s * pb.GC + gci;
   const int *sfb = c_sfb_cum[cfg.sfb_index];
+  const int bt = pb.gc_bt[gslot] & 3;                            // level 3: 1 start, 2 short, 3 stop
+  const bool ws = bt != 0;
   const int f = gci >> (chs + 1);
   const int bri = pb.frame_br[(size_t)s * pb.Fc + f];
   const int lo_bits = min(lo_bits_of(cfg, bri), 4095);
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
     int qx[9], qy[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) { qx[j] = iso_quant(__fmul_rn(mx[j], a34[j]), inv); qy[j] = iso_quant(__fmul_rn(my[j], a34[j]), inv); }
-    return iso_evaluate(qx, qy, lane, s_len, s_c[warp], sfb);
+    return iso_evaluate(qx, qy, lane, s_len, s_c[warp], sfb, ws);
   };
   auto part2_of = [&](const int *q, int &sfc) {                  // cheapest scalefac_compress that holds the scalefactors
     int m1 = 0, m2 = 0;
@@ -283,7 +286,9 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
   };
   // ---- outer loop at the granule's nominal budget
   int G = 0, best_over = 99, n_iter = 0, best_G = 0;
-  for (int it = 0; it < kOuterMaxIter; ++it) {
+  // short blocks keep their scalefactors at 0: their lines are ordered by short scalefactor band and window, the thresholds are
+  // per long band; one gain search gives best_G for the curve
+  for (int it = 0; it < (bt == 2 ? 1 : kOuterMaxIter); ++it) {
     load_amp(sf);
     int sfc;
     const int part2 = part2_of(sf, sfc);
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
     const int n_over = __popc(over) + (int)((__ballot_sync(0xffffffffu, lane == 21 && noise > xmin) >> 21) & 1u);
     n_iter = it + 1;
     if (n_over < best_over) { best_over = n_over; best_G = G; if (lane < 21) best[lane] = sf[lane]; __syncwarp(); }
-    if (over == 0u) break;
+    if (over == 0u || bt == 2) break;
     // amplify the bands over their threshold — by one step per factor of two the noise is above it (a step takes 1.5 dB off the
     // band's noise at equal gain), at most three at once; stop when a scalefactor would leave its field or every band is amplified
     const bool mine = lane < 21 && ((over >> lane) & 1u);

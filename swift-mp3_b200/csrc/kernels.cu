@@ -25,11 +25,13 @@ extern const int *host_sfb_cum();
 extern const float *host_inv_step_iso();
 cudaError_t upload_iso_tables(const float *inv_step_iso);   // iso_mode.cuh
 cudaError_t upload_psy_constants();                         // iso_psy.cuh
+cudaError_t upload_iso_switch_tables();                     // iso_mode.cuh
 
 cudaError_t upload_tables() {
   cudaError_t e;
   if ((e = upload_iso_tables(host_inv_step_iso()))) return e;
   if ((e = upload_psy_constants())) return e;
+  if ((e = upload_iso_switch_tables())) return e;
   if ((e = cudaMemcpyToSymbol(c_inv_step, host_inv_step(), sizeof(float) * 256))) return e;
   if ((e = cudaMemcpyToSymbol(c_gain_thr, host_gain_thr(), sizeof(double) * 256))) return e;
   if ((e = cudaMemcpyToSymbol(c_sfb_cum, host_sfb_cum(), sizeof(int) * 63))) return e;
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
   const uint8_t *msrow = pb.ms + (size_t)s * (pb.Fc + 1);
   const uint32_t ms_prev = pb.state[s].ms_prev;
   const bool joint = cfg.mode == 2;
-  const int n_start = 576 * g_begin - 480;
+  const int n_start = 576 * g_begin - 480 - cfg.iso_delay;   // (ISO mode level 3 reads the PCM one granule late: iso_mode.cuh)
   float *out = pb.sub + ((size_t)(s * ch + c) * pb.sub_rows + 18 * (g_begin + 1)) * 32;
 
   // PCM rows [ra, rb) of the run -> P rows slot0 ...  Fast path: the rows are contiguous in this pass's PCM and need no
@@ -575,6 +577,8 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
   __shared__ __align__(16) uint8_t len31[ISO ? 16 : 31 * 32];   // table-15 code length of a pair + its sign bits (SRC:828-853), indexed by quant30
   __shared__ __align__(16) uint8_t iso_len[ISO ? (kHuffEntries + 15) / 16 * 16 : 16];   // ISO mode: all Huffman length tables
   __shared__ uint8_t iso_c[ISO ? 8 : 1][ISO ? 288 : 1];
+  __shared__ uint16_t s_spos[ISO ? 192 : 1];                    // ISO short blocks: line order by scalefactor band and window
+  __shared__ uint8_t s_swid[ISO ? 192 : 1];
   __shared__ __align__(8) float smg[8][576];
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ch = cfg.channels, chs = ch - 1;         // channels = 1 or 2: / ch is >> chs
@@ -609,7 +613,10 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
     }
   }
   if (rep == 0) {
-    if (ISO) { for (int i = threadIdx.x; i < kHuffEntries; i += 256) iso_len[i] = kHuffLenFlat[i]; }
+    if (ISO) {
+      for (int i = threadIdx.x; i < kHuffEntries; i += 256) iso_len[i] = kHuffLenFlat[i];
+      if (threadIdx.x < 192) { s_spos[threadIdx.x] = c_short_pos[cfg.sfb_index][threadIdx.x]; s_swid[threadIdx.x] = c_short_width[cfg.sfb_index][threadIdx.x]; }
+    }
     else if (threadIdx.x < 31 * 32 / 4) reinterpret_cast<uint32_t *>(len31)[threadIdx.x] = reinterpret_cast<const uint32_t *>(tab::kLen31s)[threadIdx.x];
     __syncthreads();
   }
@@ -617,6 +624,7 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
   const size_t gslot = (size_t)s * pb.GC + gci;
   const int f = gci >> (chs + 1);
   const int lo_bits = lo_bits_of(cfg, pb.frame_br[(size_t)s * pb.Fc + f]);
+  int bt_gc = 0;
   {
     int bt;
     if (PRE) {
@@ -632,13 +640,14 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
       transient_decide(e3, bt, sbg);
       if (lane == 0) pb.gc_bt[gslot] = (uint16_t)(bt | sbg[0] << 2 | sbg[1] << 5 | sbg[2] << 8);
     } else if (ISO) {
-      bt = 0;                                                     // ISO mode: long blocks only (see iso_mode.cuh)
-      if (lane == 0) pb.gc_bt[gslot] = 0;
+      if (cfg.iso >= 3) bt = pb.gc_bt[gslot] & 3;                 // level 3: ISO block type 0 / 1 start / 2 short / 3 stop from k_iso_blocktype
+      else { bt = 0; if (lane == 0) pb.gc_bt[gslot] = 0; }        // levels 1, 2: long blocks only
     } else bt = pb.gc_bt[gslot] & 3;
+    bt_gc = bt;
     float *X = smg[warp];
     const int sb = lane;
     const bool flip = sb & 1;
-    const bool use_long = bt == 0 || (bt == 1 && sb < 2);      // SRC:1542-1553
+    const bool use_long = ISO ? bt != 2 : (bt == 0 || (bt == 1 && sb < 2));      // SRC:1542-1553 (ISO: start and stop are long transforms)
     if (use_long) {                                             // mdctLong SRC:1619-1636
       float a[18];
 #pragma unroll
@@ -647,7 +656,7 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
       for (int k = 0; k < 36; ++k) {
         float x = v[k];
         if (flip && (k & 1)) x = -x;                            // SRC:1520-1524
-        float w = __fmul_rn(x, tab::kWinLong[k]);
+        float w = __fmul_rn(x, ISO ? c_iso_win[bt][k] : tab::kWinLong[k]);
 #pragma unroll
         for (int m = 0; m < 18; ++m) a[m] = __fmaf_rn(w, tab::kMdctLong[m][k], a[m]);
       }
@@ -670,12 +679,14 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
           float r = 0.0f;
 #pragma unroll
           for (int k = 0; k < 12; ++k) r = __fmaf_rn(sg[k], tab::kMdctShort[m][k], r);
-          X[sb * 18 + w3 + 3 * m] = div_exact(r, 3.0f, 1.0f / 3.0f);
+          // the reference interleaves the windows inside the subband; ISO orders by scalefactor band, then window
+          const int dst = ISO ? s_spos[6 * sb + m] + w3 * s_swid[6 * sb + m] : sb * 18 + w3 + 3 * m;
+          X[dst] = div_exact(r, 3.0f, 1.0f / 3.0f);
         }
       }
     }
     __syncwarp();
-    if (bt == 0 && sb < 31) {                                   // applyAliasingReduction SRC:1581-1616 [OD5]
+    if ((ISO ? bt != 2 : bt == 0) && sb < 31) {                 // applyAliasingReduction SRC:1581-1616 [OD5]
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         int iu = sb * 18 + 17 - i, il = (sb + 1) * 18 + i;
@@ -734,12 +745,13 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
     const int hi_bits = min(4095, (mds1 * 8 + (min(511, mds1) * 8 * 9) / 10) >> cfg.channels);
     const int lo_fit = min(lo_bits, 4095);
     const int *sfb = c_sfb_cum[cfg.sfb_index];
+    const bool ws = bt_gc != 0;
     auto eval = [&](int G) {
       const float inv = c_inv_step_iso[G];
       int qx[9], qy[9];
 #pragma unroll
       for (int j = 0; j < 9; ++j) { qx[j] = iso_quant(mx[j], inv); qy[j] = iso_quant(my[j], inv); }
-      return iso_evaluate(qx, qy, lane, iso_len, iso_c[warp], sfb);
+      return iso_evaluate(qx, qy, lane, iso_len, iso_c[warp], sfb, ws);
     };
     int lo = 0, hi = kIsoGainMax;                     // invariant: the count at `hi` fits (at kIsoGainMax every line quantizes to 0)
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (eval(mid).bits <= hi_bits) hi = mid; else lo = mid + 1; }
@@ -787,6 +799,42 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
   if (lane == 0) pb.gc_meta[gslot] = meta | (uint32_t)n << 8 | (uint32_t)restart << 16;
   __syncwarp();
   }
+}
+
+// ISO mode level 3: block types with one granule of look-ahead (iso_mode.cuh).  One warp per granule of the pass (both
+// channels): attack flags of PCM granules g - 2, g - 1, g, the reference's detector on each channel, either channel switches both.
+__global__ void __launch_bounds__(128) k_iso_blocktype(Config cfg, PassBuffers pb) {
+  const int s = blockIdx.x, lane = threadIdx.x & 31;
+  const int g = blockIdx.y * 4 + (threadIdx.x >> 5);
+  const int nfr = (int)pb.plan[s].n_frames, ch = cfg.channels;
+  if (g >= 2 * nfr) return;
+  const PcmView pv = pcm_view(cfg, pb, s);
+  bool a[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int j = g - 2 + d;                                      // PCM granule of the pass (j = -2, -1: the carried frame)
+    bool att = false;
+    for (int c = 0; c < ch; ++c) {
+      float e3[3];
+#pragma unroll
+      for (int th = 0; th < 3; ++th) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int jj = 0; jj < 6; ++jj) {
+          const float x = pv.at((int64_t)cfg.fsc + ((int64_t)576 * j + 192 * th + 32 * jj + lane) * ch + c);
+          acc = __fmaf_rn(x, x, acc);
+        }
+        e3[th] = __fdiv_rn(lane_tree(acc), 192.0f);
+      }
+      int bt, sbg[3];
+      transient_decide(e3, bt, sbg);
+      att |= bt != 0;
+    }
+    a[d] = att;
+  }
+  const int bt = a[1] ? 2 : a[2] ? (a[0] ? 2 : 1) : a[0] ? 3 : 0;
+  if (lane < ch) pb.gc_bt[(size_t)s * pb.GC + (size_t)g * ch + lane] = (uint16_t)bt;
+  if (lane == 0 && (g & 1) == 0) pb.ms[(size_t)s * (pb.Fc + 1) + 1 + (g >> 1)] = 0;   // level 3 codes L / R (a frame's samples straddle two input frames)
 }
 
 }  // namespace mp3b
@@ -1167,7 +1215,7 @@ template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta) 
       ix[2 * p] = (int16_t)(v.x < 0.0f ? -qx[j] : qx[j]); ix[2 * p + 1] = (int16_t)(v.y < 0.0f ? -qy[j] : qy[j]);
       if (TRACE) { pb.tr_ix[gslot * 576 + 2 * p] = ix[2 * p]; pb.tr_ix[gslot * 576 + 2 * p + 1] = ix[2 * p + 1]; }
     }
-    const IsoChoice c = iso_evaluate(qx, qy, lane, s_len, s_c[warp], sfb);
+    const IsoChoice c = iso_evaluate(qx, qy, lane, s_len, s_c[warp], sfb, (pb.gc_bt[gslot] & 3) != 0);
     __syncwarp();
     if (lane == 0) {
       GcSide &gs = fr.gc[g];
@@ -1292,7 +1340,8 @@ __global__ void __launch_bounds__(128) k_frames(Config cfg, PassBuffers pb) {
       v = (unsigned long long)(g.part23 & 0xFFF) << 47 | (unsigned long long)(g.big_values & 0x1FF) << 38 |
           (unsigned long long)g.global_gain << 30 | (unsigned long long)(g.sfc & 15) << 26 | (unsigned long long)ws << 25;   // scalefac_compress = 0 outside ISO mode level 2 (SRC:722)
       unsigned long long mid;                                                         // 22 bits at 3
-      if (ws) mid = (unsigned long long)(g.block_type & 3) << 20 | (unsigned long long)(g.block_type == 1) << 19 | 15ull << 14 | 15ull << 9 |
+      if (ws && cfg.iso) mid = (unsigned long long)(g.block_type & 3) << 20 | (unsigned long long)(g.tsel[0] & 31) << 14 | (unsigned long long)(g.tsel[1] & 31) << 9;   // ISO mode level 3: mixed_block_flag = 0, subblock_gain = 0
+      else if (ws) mid = (unsigned long long)(g.block_type & 3) << 20 | (unsigned long long)(g.block_type == 1) << 19 | 15ull << 14 | 15ull << 9 |
                     (unsigned long long)(g.sbg[0] & 7) << 6 | (unsigned long long)(g.sbg[1] & 7) << 3 | (unsigned long long)(g.sbg[2] & 7);
       else mid = (unsigned long long)(g.tsel[0] & 31) << 17 | (unsigned long long)(g.tsel[1] & 31) << 12 | (unsigned long long)(g.tsel[2] & 31) << 7 |
                  (unsigned long long)(g.region0 & 15) << 3 | (unsigned long long)(g.region1 & 7);   // table_select = 15, 15, 15 outside ISO mode (SRC:717)
@@ -1633,6 +1682,12 @@ int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st, bool
   else if (pb.spec) k_granule<true, false, false><<<grid, 256, 0, st>>>(cfg, pb);
   else if (fused_prepass) k_granule<false, true, false><<<grid, 256, 0, st>>>(cfg, pb);
   else k_granule<false, false, false><<<grid, 256, 0, st>>>(cfg, pb);
+  return check(1);
+}
+int launch_blocktype(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
+  if (pb.max_frames <= 0) return 0;
+  dim3 grid(cfg.n_streams, (2 * pb.max_frames + 3) / 4);
+  k_iso_blocktype<<<grid, 128, 0, st>>>(cfg, pb);
   return check(1);
 }
 int launch_psy(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {

@@ -34,7 +34,8 @@ struct Config {              // constant for the lifetime of a batch; passed to 
   int sr_index, sfb_index, side_bytes, header_bytes /* 4 + crc + side */;
   int mode_bits, mode_ext, cbr_index;
   float f_one, f_neg0;                // 1.0f and -0.0f as run-time values (see k_spectrum phase A)
-  int iso;                            // opt-in ISO mode (iso_mode.cuh): 1 = ISO quantizer, table selection, count1, real main_data_begin; 2 = + psychoacoustic model and scalefactor outer loop (iso_psy.cuh)
+  int iso;                            // opt-in ISO mode (iso_mode.cuh): 1 = ISO quantizer, table selection, count1, real main_data_begin; 2 = + psychoacoustic model and scalefactor outer loop (iso_psy.cuh); 3 = + window switching (start / short / stop blocks)
+  int iso_delay;                      // ISO mode level 3 (window switching): the filterbank reads the PCM this many samples late (576), 0 otherwise
   float ms_scale;                     // mid / side = (L +- R) * ms_scale: 0.5 like the reference (SRC:2148-2154), 1/sqrt(2) in ISO mode
   int frame_base[16], frame_rem[16];  // 144*kbps*1000 / sr and % sr per bitrate index
   uint8_t vbr_idx_of_kbps[324];       // bitrateIndex(kbps) for every VBR target 0...320
@@ -137,6 +138,7 @@ int launch_prepass(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st, bool fused_prepass);   // fused_prepass: launch_prepass did not run
 // ISO mode level 2: psychoacoustic model (needs the PCM and the pre-pass's M/S decision) and the outer loop (after launch_curve)
+int launch_blocktype(const Config &cfg, const PassBuffers &pb, cudaStream_t st);   // ISO mode level 3: block types, after launch_prepass
 int launch_psy(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 int launch_outer(const Config &cfg, const PassBuffers &pb, cudaStream_t st);
 // ISO mode: the main-data FIFO of a pass must start out zeroed (stuffing bytes are never written)

@@ -58,16 +58,25 @@ def decode_stream(stream):
         assert begin >= 0, "frame %d: main_data_begin %d points before the start of the stream" % (n, f["mdb"])
         b = Bits(cat, begin * 8)
         for g in f["gc"]:
-            assert g["ws"] == 0 and g["preflag"] == 0, "ISO mode writes long blocks without preflag"
+            assert g["preflag"] == 0 and g["mixed"] == 0 and (not g["ws"] or g["sbg"] == [0, 0, 0]), "ISO mode writes no preflag, mixed blocks or subblock_gain"
             start, ix = b.p, np.zeros(576, np.int32)
-            # part 2 (ISO mode level 2): 11 scalefactors of slen1 bits, 10 of slen2 (long blocks, scfsi = 0)
+            # part 2 (ISO mode level 2): 11 scalefactors of slen1 bits, 10 of slen2 (long transforms, scfsi = 0); short blocks
+            # (level 3) would carry 18 + 18, the engine keeps them at scalefac_compress 0 = no bits
             l1, l2 = SLEN1[g["scalefac_compress"]], SLEN2[g["scalefac_compress"]]
-            sf = [b.get(l1) if l1 else 0 for _ in range(11)] + [b.get(l2) if l2 else 0 for _ in range(10)]
+            if g["ws"] and g["block_type"] == 2:
+                sf = [b.get(l1) if l1 else 0 for _ in range(18)] + [b.get(l2) if l2 else 0 for _ in range(18)]
+                assert not any(sf)
+                sf = [0] * 21
+            else:
+                sf = [b.get(l1) if l1 else 0 for _ in range(11)] + [b.get(l2) if l2 else 0 for _ in range(10)]
             part2 = b.p - start
             bv2 = 2 * g["big_values"]
             assert bv2 <= 576
             sfb = SFB_LONG[f["sr_index"]]
-            a1 = min(sfb[min(g["region0"] + 1, 22)], bv2); a2 = min(sfb[min(g["region0"] + g["region1"] + 2, 22)], bv2)
+            if g["ws"]:                                            # window switching: region 0 = 36 lines, region 1 = the rest (2.4.2.7)
+                a1, a2 = min(36, bv2), bv2
+            else:
+                a1 = min(sfb[min(g["region0"] + 1, 22)], bv2); a2 = min(sfb[min(g["region0"] + g["region1"] + 2, 22)], bv2)
             for i in range(0, bv2, 2):
                 t = g["table_select"][0 if i < a1 else 1 if i < a2 else 2]
                 if t == 0:

@@ -851,6 +851,64 @@ def test_iso_level2_psy_and_scalefactors(mp3):
     assert any(r["over_level2"] < r["over_level1"] for r in report.values()), report
 
 
+def test_iso_level3_window_switching(mp3):
+    """ISO mode level 3 (north_star stage 2 for the ISO path): start / short / stop blocks from the transient detector with one
+    granule of look-ahead.  The block types follow the ISO state machine (normal -> start -> short ... -> stop), both channels
+    switch together, the bytes parse back to the coded ix (two-region side info, short-block line order), FFmpeg decodes every
+    frame to the INPUT with the extra granule of delay, the castanet bursts come out with a better SNR than with long blocks only,
+    a steady signal never switches, and chunked feeding / small passes give the same bytes."""
+    import avdecode
+    import isoparse
+    report = {}
+    cases = [("castanets", signals.castanets(3.0), dict(sample_rate=44100, bitrate_kbps=128, mode="stereo")),
+             ("castanets-mono-48k", signals.castanets(2.0)[::2].copy(), dict(sample_rate=48000, bitrate_kbps=96, mode="mono")),
+             ("steady", signals.sine_noise(1.5, seed=21), dict(sample_rate=44100, bitrate_kbps=128, mode="stereo"))]
+    for name, pcm, o in cases:
+        ch = 1 if o["mode"] == "mono" else 2
+        res = {}
+        for level in (2, 3):
+            b = mp3.EncoderBatch(_opts(mp3, **o), 1, 0, 0)
+            b.set_iso_mode(level)
+            b.set_trace(spectrum=True, ix=True)
+            out = b.encode([pcm], flush=True)[0]
+            frames, ix, info = isoparse.decode_stream(out)
+            assert np.array_equal(ix, b.trace_array(0, "ix")), "%s level %d: parsed ix differs from the coded ix" % (name, level)
+            gg = b.trace_gc(0)
+            types = np.array([g["block_type"] if g["ws"] else 0 for f in frames for g in f["gc"]]).reshape(-1, ch)
+            assert np.array_equal(types.reshape(-1), gg["block_type"])
+            dec, ok, bad = avdecode.decode_unit_scale(out)
+            assert bad == 0 and ok == b.frame_count(0)
+            lag = 1057 + (576 if level == 3 else 0)
+            xin = pcm.reshape(-1, ch)[:, 0].astype(np.float64)
+            nn = min(len(dec[0]) - lag, len(xin)) - 1200
+            aa, zz = xin[3000:nn], dec[0][3000 + lag:nn + lag]
+            res[level] = dict(snr=float(10 * np.log10(np.sum(aa * aa) / np.sum((aa - zz) ** 2))), types=types, out=out)
+            if level == 3:
+                assert (types == types[:, :1]).all(), "the channels of a granule switch together"
+                t = types[:, 0]
+                allowed = {0: (0, 1), 1: (2,), 2: (2, 3), 3: (0, 1)}
+                assert all(int(t[k + 1]) in allowed[int(t[k])] for k in range(len(t) - 1)), "%s: block type sequence %r" % (name, t[:60])
+                # chunked feeding and 5-frame passes: same bytes
+                s = mp3.MP3Encoder(_opts(mp3, **o)).newSession()
+                s.set_iso_mode(3)
+                parts = s.encode(pcm[:5000 * ch]) + s.encode(pcm[5000 * ch:23001 * ch]) + s.encode(pcm[23001 * ch:]) + s.flush()
+                s.close()
+                assert parts == out, name
+                b2 = mp3.EncoderBatch(_opts(mp3, **o), 2, 0, 5)
+                b2.set_iso_mode(3)
+                assert b2.encode([pcm, pcm], flush=True) == [out, out]
+                b2.close()
+            b.close()
+        t3 = res[3]["types"][:, 0]
+        report[name] = dict(snr_long_only=round(res[2]["snr"], 2), snr_switching=round(res[3]["snr"], 2), short=int((t3 == 2).sum()), start=int((t3 == 1).sum()),
+                            stop=int((t3 == 3).sum()), granules=len(t3))
+        if name == "steady":
+            assert (t3 == 0).all()
+        else:
+            assert (t3 == 2).sum() > 0 and res[3]["snr"] > res[2]["snr"], report[name]
+    print("ISO level 3:", report)
+
+
 def test_iso_mode_session_and_reset_rules(mp3):
     """The switch is per session / batch, only on fresh sessions; chunked feeding and small passes equal one call (the look-back of
     the psychoacoustic FFT windows crosses call and pass boundaries); the default stays the reference-compatible path."""
