@@ -101,6 +101,7 @@ struct mp3b_batch {
   size_t out_total = 0;
   bool have_host_out = false;
   std::vector<uint32_t> pending;                         // floats waiting after the carried frame, per stream
+  std::vector<uint8_t> fed;                              // the stream has been given samples (ISO mode level 3 flushes its delayed granule)
   std::vector<uint32_t> out_len;
   std::vector<uint32_t> frame_count, byte_count;
   std::vector<std::vector<uint16_t>> frame_sizes;       // SRC:258
@@ -336,6 +337,7 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   // with it, so the batch is handed out only when they have landed.
   if (cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { free_batch(b); return fail(MP3B_ERR_CUDA, "batch initialisation failed"); }
   b->pending.assign(S, 0); b->out_len.assign(S, 0); b->frame_count.assign(S, 0); b->byte_count.assign(S, 0);
+  b->fed.assign(S, 0);
   b->frame_sizes.resize(S);
   b->d_plan[0] = p.plan;
   // A small batch (a session is a batch of one) gets its staging, output and pinned download buffers now instead of inside its
@@ -460,7 +462,8 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
     n[s] = (n_floats && pcm && pcm[s]) ? n_floats[s] : 0;
     want_flush[s] = flush && (!flush_mask || flush_mask[s]);
     size_t avail = b->pending[s] + n[s];
-    max_frames = std::max(max_frames, avail / fsc + 1);
+    max_frames = std::max(max_frames, avail / fsc + 1 + (cfg.iso >= 3 ? 1 : 0));
+    if (n[s]) b->fed[s] = 1;
   }
   int rc = ensure_out(b, (max_frames + 1) * (size_t)b->max_frame_bytes);
   if (rc) return rc;
@@ -526,8 +529,12 @@ int run_call_impl(mp3b_batch *b, const float *const *pcm, const size_t *n_floats
       uint32_t nfr = (uint32_t)(total / fsc), flags = first_plan ? 4u : 0u;
       uint32_t new_pending = (uint32_t)(total % fsc);
       if (remaining == cur_n && want_flush[s] && !flushed[s]) {
-        if (new_pending > 0) {
-          if ((int)nfr < Fc) { nfr += 1; flags |= 3u; new_pending = 0; flushed[s] = 1; }
+        // ISO mode level 3 codes the signal 576 samples late: the last granule of the input still sits in the delay when the
+        // padded frame ends before it does — one more frame (its PCM beyond the input reads as zeros) brings it out
+        const uint32_t tail = cfg.iso >= 3 && b->fed[s] && (new_pending == 0 || new_pending > 576u * (uint32_t)cfg.channels) ? 1u : 0u;
+        if (new_pending > 0 || tail) {
+          const uint32_t add = (new_pending > 0 ? 1u : 0u) + tail;
+          if (nfr + add <= (uint32_t)Fc) { nfr += add; flags |= 3u; new_pending = 0; flushed[s] = 1; b->fed[s] = 0; }   // (flush() stays idempotent)
         } else { flags |= 2u; flushed[s] = 1; }
       }
       src[slot][s] = (pcm && pcm[s]) ? (const float *)((const char *)pcm[s] + cursor[s] * (size_t)elem_bytes) : nullptr;
@@ -1010,7 +1017,7 @@ int mp3b_session_take_output(mp3b_session *s, uint8_t *out, size_t cap, size_t *
 size_t mp3b_session_output_bound(const mp3b_session *s, size_t n_floats) {
   if (!s) return 0;
   const mp3b_batch *b = s->b;
-  return ((b->pending[0] + n_floats) / b->cfg.fsc + 2) * (size_t)b->max_frame_bytes;
+  return ((b->pending[0] + n_floats) / b->cfg.fsc + 2 + (b->cfg.iso >= 3 ? 1 : 0)) * (size_t)b->max_frame_bytes;
 }
 int mp3b_session_xing_header(const mp3b_session *s, uint8_t *out, size_t cap, size_t *written) {
   if (!s) return fail(MP3B_ERR_BAD_ARG, "null session");
@@ -1106,7 +1113,7 @@ int mp3b_batch_reset(mp3b_batch *b) {
   CU(cudaMemsetAsync(b->d_head[1], 0, S * 2 * b->cfg.fsc * sizeof(float), b->st));
   CU(cudaMemset2DAsync(b->pb.sub, (size_t)b->pb.sub_rows * 32 * sizeof(float), 0, 576 * sizeof(float), S * b->cfg.channels, b->st));
   CU(cudaStreamSynchronize(b->st));
-  std::fill(b->pending.begin(), b->pending.end(), 0u);
+  std::fill(b->pending.begin(), b->pending.end(), 0u); std::fill(b->fed.begin(), b->fed.end(), (uint8_t)0);
   std::fill(b->out_len.begin(), b->out_len.end(), 0u);
   std::fill(b->frame_count.begin(), b->frame_count.end(), 0u);
   std::fill(b->byte_count.begin(), b->byte_count.end(), 0u);
@@ -1159,7 +1166,7 @@ int mp3b_batch_clone(const mp3b_batch *src, mp3b_batch **out) {
   b->head_sel = src->head_sel; b->cfg.iso = src->cfg.iso; b->cfg.ms_scale = src->cfg.ms_scale; b->cfg.iso_delay = src->cfg.iso_delay;
   if (b->cfg.iso >= 2 && ensure_iso2(b) != MP3B_OK) { free_batch(b); return MP3B_ERR_CUDA; }
   if (src->pb.tc_b && mp3b_batch_set_matrixing(b, 1) != MP3B_OK) { free_batch(b); return MP3B_ERR_CUDA; }
-  b->pending = src->pending; b->frame_count = src->frame_count; b->byte_count = src->byte_count; b->frame_sizes = src->frame_sizes;
+  b->pending = src->pending; b->fed = src->fed; b->frame_count = src->frame_count; b->byte_count = src->byte_count; b->frame_sizes = src->frame_sizes;
   b->trace = src->trace;
   *out = b;
   return MP3B_OK;
@@ -1182,7 +1189,7 @@ int mp3b_batch_reset_stream(mp3b_batch *b, int stream) {
   CU(cudaMemsetAsync(b->d_head[1] + s * fsc2, 0, fsc2 * sizeof(float), b->st));
   CU(cudaMemset2DAsync(b->pb.sub + s * ch * (size_t)b->pb.sub_rows * 32, (size_t)b->pb.sub_rows * 32 * sizeof(float), 0, 576 * sizeof(float), ch, b->st));
   CU(cudaStreamSynchronize(b->st));
-  b->pending[s] = 0; b->out_len[s] = 0; b->frame_count[s] = 0; b->byte_count[s] = 0; b->frame_sizes[s].clear();
+  b->pending[s] = 0; b->fed[s] = 0; b->out_len[s] = 0; b->frame_count[s] = 0; b->byte_count[s] = 0; b->frame_sizes[s].clear();
   return MP3B_OK;
 }
 // Opt-in ISO mode (iso_mode.cuh).  Only on fresh sessions: the two modes do not share reservoir semantics.

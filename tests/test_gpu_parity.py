@@ -898,10 +898,27 @@ def test_iso_level3_window_switching(mp3):
                 b2.set_iso_mode(3)
                 assert b2.encode([pcm, pcm], flush=True) == [out, out]
                 b2.close()
+                # the delayed granule is flushed: every input sample is inside the coded frames (one extra frame when the last
+                # frame is more than half full or exactly full), flush() stays idempotent, an unfed session flushes to nothing
+                n_s = len(pcm) // ch
+                assert b.frame_count(0) == -(-(n_s + 576) // 1152), (n_s, b.frame_count(0))
+                hi = min(n_s, len(dec[0]) - lag) - 8              # (the decoder itself keeps its last 500-odd samples of delay back)
+                if hi > n_s - 500:                                  # part of the last granule of the input is visible in the decoder's output
+                    tail_in, tail_out = xin[n_s - 570:hi], dec[0][n_s - 570 + lag:hi + lag]
+                    assert np.sum((tail_in - tail_out) ** 2) < 0.5 * np.sum(tail_in ** 2) + 1e-6, "the end of the input is missing from the decoded stream"
+                    res["tail_checked"] = True
+                s = mp3.MP3Encoder(_opts(mp3, **o)).newSession()
+                s.set_iso_mode(3)
+                assert s.flush() == b"" and len(s.encode(pcm[:1152 * ch])) == 0
+                first = s.flush()
+                assert len(first) > 0 and s.flush() == b"" and s.encodedFrameCount == 2
+                s.close()
             b.close()
         t3 = res[3]["types"][:, 0]
         report[name] = dict(snr_long_only=round(res[2]["snr"], 2), snr_switching=round(res[3]["snr"], 2), short=int((t3 == 2).sum()), start=int((t3 == 1).sum()),
                             stop=int((t3 == 3).sum()), granules=len(t3))
+        if name == "castanets":
+            assert res.get("tail_checked")
         if name == "steady":
             assert (t3 == 0).all()
         else:
