@@ -699,6 +699,22 @@ def test_iso_mode_bitstream_roundtrip(mp3):
                     assert g["table_select"] == list(gg["table_select"][k]) and g["count1table"] == gg["count1table_select"][k]
                     assert all(t not in (4, 14) for t in g["table_select"]) and g["part23"] <= gg["max_bits"][k]
                     k += 1
+            # the decisions against their numpy restatement (tests/isocount.py): partition, regions, table selection, count1 table
+            # and bit count of every granule-channel; and the gain is the smallest whose count fits the budget
+            import isocount
+            sri = {44100: 0, 48000: 1, 32000: 2}[o["sample_rate"]]
+            sides = [g for f in frames for g in f["gc"]]
+            step_k = max(1, len(sides) // 150)
+            for k in range(0, len(sides), step_k):
+                c = isocount.count(np.abs(got[k]), sri)
+                g = sides[k]
+                assert c["bits"] == g["part23"] and c["big_values"] == g["big_values"] and c["count1table"] == g["count1table"], (name, k, c, g)
+                assert c["table_select"] == g["table_select"] and (c["region0"], c["region1"]) == (g["region0"], g["region1"]), (name, k, c, g)
+                G = int(gg["gain_used"][k])
+                if G > 0:
+                    inv1 = np.float32(2.0) ** np.float32((180.0 - 3.0 * (G - 1 - 210.0)) / 16.0)
+                    lower = np.minimum(np.floor((mag[k] * inv1).astype(np.float32) + np.float32(0.4054)), 8206).astype(np.int64)
+                    assert isocount.count(lower, sri)["bits"] > min(int(gg["max_bits"][k]), 4095), (name, k, "one gain step lower would have fitted too")
             if name == "c2":
                 assert ix.max() > 15, "the case is meant to exercise the linbits escapes"
             if name in ("c1", "c3"):                           # (white noise at 320 kbps has no run of |ix| <= 1 to put in count1)
@@ -809,8 +825,12 @@ def test_iso_level2_psy_and_scalefactors(mp3):
                 inv = (np.float32(2.0) ** ((180.0 - 3.0 * (gg["gain_used"].astype(np.float64) - 210.0)) / 16.0)).astype(np.float32)
                 want = np.minimum(np.floor(((mag * amp).astype(np.float32) * inv[:, None]).astype(np.float32) + np.float32(0.4054)), 8206).astype(np.int32)
                 assert np.array_equal(np.abs(got), want), "%s: quantizer law with scalefactors" % name
+                import isocount
                 for k, g in enumerate(g for f in frames for g in f["gc"]):
                     assert g["part23"] == gg["part23_length"][k] <= gg["max_bits"][k]
+                    if k % 9 == 0:                                        # bit count and table choice against the numpy restatement
+                        c = isocount.count(np.abs(got[k]), sfi)
+                        assert c["bits"] + info[k]["part2"] == g["part23"] and c["table_select"] == g["table_select"] and c["big_values"] == g["big_values"], (name, k, c, g)
                 # psychoacoustic record against the numpy model
                 psy = b.trace_array(0, "psy")
                 fr = b.trace_frames(0)
@@ -874,6 +894,14 @@ def test_iso_level3_window_switching(mp3):
             frames, ix, info = isoparse.decode_stream(out)
             assert np.array_equal(ix, b.trace_array(0, "ix")), "%s level %d: parsed ix differs from the coded ix" % (name, level)
             gg = b.trace_gc(0)
+            import isocount
+            sri = {44100: 0, 48000: 1, 32000: 2}[o["sample_rate"]]
+            got_ix = b.trace_array(0, "ix")
+            for k, g in enumerate(g for f in frames for g in f["gc"]):
+                if k % 5 == 0 or g["ws"]:                                   # every window-switched granule, a sample of the others
+                    c = isocount.count(np.abs(got_ix[k]), sri, ws=bool(g["ws"]))
+                    assert c["bits"] + info[k]["part2"] == g["part23"] and c["big_values"] == g["big_values"] and c["count1table"] == g["count1table"], (name, level, k, c, g)
+                    assert c["table_select"][:len(g["table_select"])] == g["table_select"] and (not g["ws"] or c["table_select"][2] == 0), (name, level, k, c, g)
             types = np.array([g["block_type"] if g["ws"] else 0 for f in frames for g in f["gc"]]).reshape(-1, ch)
             assert np.array_equal(types.reshape(-1), gg["block_type"])
             dec, ok, bad = avdecode.decode_unit_scale(out)
