@@ -984,7 +984,7 @@ int mp3b_batch_stream_device(const mp3b_batch *b, int stream) {
 int mp3b_session_create(const mp3b_options *opts, int device, mp3b_session **out) {
   if (!out) return fail(MP3B_ERR_BAD_ARG, "null out");
   mp3b_batch *b = nullptr;
-  int rc = create_batch(opts, 1, device, 256, &b);
+  int rc = create_batch(opts, 1, device, 1024, &b);                  // 1024 frames (27 s at 44.1 kHz) per pass: ~45 MB of device memory per session
   if (rc) return rc;
   mp3b_session *s = new mp3b_session(); s->b = b; *out = s;
   return MP3B_OK;

@@ -131,7 +131,10 @@ public struct EncoderSession {
   public var encodedByteCount: UInt32 { mp3b_session_byte_count(box.handle) }     // SRC:264
 
   /// Opt-in ISO mode (include/mp3b200.h); call before the first encode(samples:).
-  public mutating func setISOMode(_ on: Bool) { makeUnique(); precondition(mp3b_session_set_iso_mode(box.handle, on ? 1 : 0) == 0) }
+  /// Extension (not in the reference; default 0 = the reference's bytes): 1 = ISO quantizer / table selection / count1 / real
+  /// main_data_begin, 2 = + psychoacoustic model and scalefactor outer loop, 3 = + window switching.  Fresh sessions only.
+  public mutating func setISOMode(_ level: Int32) { makeUnique(); precondition(mp3b_session_set_iso_mode(box.handle, level) == 0, String(cString: mp3b_last_error())) }
+  public mutating func setISOMode(_ on: Bool) { setISOMode(on ? 1 : 0) }
 
   private func collect(_ call: (UnsafeMutablePointer<UInt8>?, Int, UnsafeMutablePointer<Int>) -> Int32, bound: Int) -> Data {
     var out = Data(count: bound)

@@ -46,6 +46,16 @@ def _pair(b, lut, linbits):
     return x, y
 
 
+def crc16(data):
+    """CRC-16 of ISO 11172-3 2.4.3.1: polynomial 0x8005, start value 0xFFFF, most significant bit first."""
+    crc = 0xFFFF
+    for byte in data:
+        crc ^= byte << 8
+        for _ in range(8):
+            crc = ((crc << 1) ^ 0x8005) & 0xFFFF if crc & 0x8000 else (crc << 1) & 0xFFFF
+    return crc
+
+
 def decode_stream(stream):
     """-> (frames, ix [n_gc][576], info per gc: bits used by big_values / count1, count1 quadruples)."""
     luts, linbits, quad, _ = tables()
@@ -54,6 +64,9 @@ def decode_stream(stream):
     starts = np.concatenate([[0], np.cumsum([len(f["slot"]) for f in frames])])
     out, info = [], []
     for n, f in enumerate(frames):
+        if f["protection"] == 0:                               # ISO CRC: header bytes 2-3 and the side info (the reference: the 4 header bytes)
+            h = f["header"]
+            assert (h[4] << 8 | h[5]) == crc16(h[2:4] + h[6:]), "frame %d: CRC mismatch" % n
         begin = int(starts[n]) - f["mdb"]
         assert begin >= 0, "frame %d: main_data_begin %d points before the start of the stream" % (n, f["mdb"])
         b = Bits(cat, begin * 8)

@@ -5,7 +5,8 @@
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total --format=csv; nproc; free -g | head -2
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python -m pytest tests -m gpu -x -q -s 2>&1 | tee gpurun_out/pytest_gpu_full.txt | tail -15
+grep -h "^\.*ISO mode:\|^\.*ISO level\|^\.*tensor-core matrixing" gpurun_out/pytest_gpu_full.txt | sed 's/^\.*//' > gpurun_out/quality_report.txt
 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo bench rc=$?
 tail -c 1500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo ref rc=$?
@@ -28,7 +29,8 @@ MP3B_MATRIXING=1 python tools/stage_times.py 4096 1.671837 1 > gpurun_out/plain3
 MP3B_MATRIXING=1 ncu --set full --clock-control none --import-source on -k "$TCK" -s 2 -c 1 -o gpurun_out/prof_tc python tools/stage_times.py 4096 1.671837 1 > gpurun_out/ncu3.log 2>&1
 echo ncu3 rc=$?
 python tools/iso_bench.py 1024 10 3 > gpurun_out/iso_bench.json 2> gpurun_out/iso_bench.err; echo iso rc=$?
-ncu --set full --clock-control none --import-source on -k "regex:k_(psy|outer|pack_iso)" -s 3 -c 3 -o gpurun_out/prof_iso python tools/iso_bench.py 256 10 1 > gpurun_out/ncu4.log 2>&1
+# (sections only, no source import: gpurun copies back at most 64 MiB and the two reports above take 38)
+ncu --section SpeedOfLight --section LaunchStats --section Occupancy --section WarpStateStats --clock-control none -k "regex:k_(psy|outer|iso_blocktype)" -s 0 -c 2 -o gpurun_out/prof_iso python tools/iso_bench.py 256 10 1 > gpurun_out/ncu4.log 2>&1
 echo ncu4 rc=$?
 fi
 ls -la gpurun_out | tail -12
