@@ -345,7 +345,8 @@ int create_batch(const mp3b_options *opts, int n_streams, int device, int frames
   const size_t stage_bytes = S * (size_t)Fc * cfg.fsc * sizeof(float);
   if (stage_bytes <= ((size_t)64 << 20)) {
     b->stage_stride = (size_t)Fc * cfg.fsc;
-    const size_t out_stride = round_up<size_t>((size_t)(Fc + 2) * b->max_frame_bytes, 16), total = S * out_stride;
+    // (output for calls of up to four passes: growing the pinned download buffer inside a call costs more than the call)
+    const size_t out_stride = round_up<size_t>((size_t)(4 * Fc + 2) * b->max_frame_bytes, 16), total = S * out_stride;
     bool ok = cudaMalloc((void **)&b->d_stage[0], stage_bytes) == cudaSuccess && cudaMalloc((void **)&b->d_stage[1], stage_bytes) == cudaSuccess &&
               cudaMalloc((void **)&b->pb.out, total) == cudaSuccess;
     if (ok) { b->out_cap_bytes = total; b->pb.out_stride = out_stride; }
