@@ -868,6 +868,8 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
   __shared__ int sh_state[8];
   __shared__ float sh_pe[32 * 4];                            // ISO mode level 2: perceptual entropy per gc
   __shared__ uint16_t sh_bpg[32 * 4];                        // the budget each gc was given
+  __shared__ int16_t sh_mds[32];                             // fast path: main-data bytes of the frame (padding included), -1: final frame
+  __shared__ uint32_t sh_ser[32][2];                         // fast path: what the serial loop leaves per frame: huff | avail << 16, W before
   const int s = blockIdx.x, lane = threadIdx.x;
   const StreamPlan plan = pb.plan[s];
   StreamState &st = pb.state[s];
@@ -903,6 +905,110 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
       if (cfg.iso >= 2) for (int i = lane; i < cnt * ngc; i += 32) sh_pe[i] = pb.gc_psy[(g0s + i) * 24 + 22];
     }
     __syncwarp();
+    if (!cfg.iso) {
+      // (2) fast path (the reference-compatible mode).  One warp runs the serial chain at its own issue latency — every instruction
+      // in the loop costs the stream about six cycles per frame — so the loop keeps only what truly depends on the reservoir:
+      // budget, curve look-up (lane j = gc j), bit total, reservoir, FIFO cursors.  Padding / slot sizes come before it as a
+      // parallel prefix (lane = frame), the emission records and counters after it, again lane = frame.
+      const int ngc_shift = ch == 1 ? 1 : 2;
+      int pad_l = 0, mds_l = 0;
+      {  // (2a) shouldPad SRC:456-463 for 32 frames at once: rem < sample_rate, so the accumulator wraps at most once per frame and
+         // padding = floor(cum / sr) - floor(cum_prev / sr) with cum the running sum of the remainders on top of the carried one
+        const int bri = lane < cnt ? sh_bri[lane] : 0;
+        int cum = lane < cnt ? cfg.frame_rem[bri] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, cum, d); if (lane >= d) cum += t; }
+        cum += pad_rem;
+        const int q = cum / cfg.sample_rate;
+        int qp = __shfl_up_sync(0xffffffffu, q, 1);
+        if (lane == 0) qp = 0;
+        pad_l = q - qp;
+        mds_l = cfg.frame_base[bri] + pad_l - cfg.header_bytes;       // SRC:497
+        pad_rem = __shfl_sync(0xffffffffu, cum - q * cfg.sample_rate, cnt - 1);
+        if (lane < cnt) sh_mds[lane] = (int16_t)mds_l;
+      }
+      __syncwarp();
+      const int prev_slot0 = prev_slot;
+      const uint32_t R0 = R;
+#pragma unroll 2
+      for (int l = 0; l < cnt; ++l) {
+        const int mds = sh_mds[l];
+        const bool is_final = (plan.flags & 1) && base + l == nf - 1;
+        const int res_bits = is_final ? 0 : avail * 8;               // SRC:500
+        const int bpg = (mds * 8 + (res_bits * 9) / 10) >> ngc_shift;  // SRC:647-650
+        int total;
+        {
+          const int j = lane & (ngc - 1);
+          const uint32_t meta = sh_meta[l * ngc + j];
+          const int g0 = (int)(meta & 255u), n = (int)((meta >> 8) & 255u), restart = (int)((meta >> 16) & 1u);
+          const uint16_t *cb = sh_bits + (l * ngc + j) * kMaxEntries;
+          int gain = g0, chosen = n - 1, gain_out = g0, gain_used = g0, iters = n, bits = -1;
+          for (int e = 0; e < n; ++e) {                              // quantizeToFitBudget SRC:745-776
+            gain_used = gain;
+            if (e == 0 && restart) { gain = max(gain - 40, 0); continue; }
+            const int be = cb[e];
+            if (be <= bpg) { chosen = e; gain_out = gain; iters = e + 1; bits = be; break; }
+            int next = min(gain + 4, 255);
+            if (next >= 255 || e == kMaxEntries - 1) { chosen = e; gain_out = next; iters = e + 1; bits = be; break; }
+            if (e == n - 1) { chosen = e; gain_out = next; err |= 1; bits = be; break; }   // curve ended early: engine bug
+            gain = next;
+          }
+          if (bits < 0) bits = cb[chosen];
+          if (lane < ngc)
+            *reinterpret_cast<uint32_t *>(sh_sel[l * ngc + j]) = (uint32_t)chosen | (uint32_t)gain_out << 8 | (uint32_t)gain_used << 16 | (uint32_t)iters << 24;
+          total = bits;
+        }
+        total += __shfl_xor_sync(0xffffffffu, total, 1);
+        if (ngc == 4) total += __shfl_xor_sync(0xffffffffu, total, 2);
+        const int huff = (total + 7) >> 3;                           // padToByte SRC:729
+        if (lane < 2) sh_ser[l][lane] = lane == 0 ? ((uint32_t)huff | (uint32_t)avail << 16) : W;
+        W += (uint32_t)huff;                                         // appendHuffmanData SRC:511
+        if (W > pb.md_stride) { err |= 2; W = (uint32_t)pb.md_stride; }
+        const int a = avail + mds - huff;                            // updateReservoir SRC:565, 2125-2128
+        avail = a < 0 ? 0 : a > 511 ? 511 : a;
+      }
+      __syncwarp();
+      {  // (2b) lane = frame: FIFO read cursor, emission of the buffered frame (SRC:548-556, fillSlot 2110-2121), counters
+        const uint32_t huff = lane < cnt ? (sh_ser[lane][0] & 0xFFFFu) : 0u, avail_l = lane < cnt ? (sh_ser[lane][0] >> 16) : 0u;
+        const uint32_t w_before = lane < cnt ? sh_ser[lane][1] : 0u;
+        const uint32_t w_after = min(w_before + huff, (uint32_t)pb.md_stride);
+        int pslot = __shfl_up_sync(0xffffffffu, mds_l, 1);           // the frame emitted while frame l is encoded is frame l - 1
+        if (lane == 0) pslot = prev_slot0;
+        // R_l = min(R_{l-1} + slot_{l-1}, W_l): a serial recurrence, but over 32 lanes of registers, not in the loop above
+        uint32_t r_before = R0;
+        {
+          uint32_t r = R0;
+          for (int k = 0; k < cnt; ++k) {
+            const int ps = __shfl_sync(0xffffffffu, pslot, k);
+            const uint32_t wa = __shfl_sync(0xffffffffu, w_after, k);
+            if (lane == k) r_before = r;
+            if (ps >= 0) r = min(r + (uint32_t)ps, wa);
+          }
+          R = r;
+        }
+        const bool emits = lane < cnt && pslot >= 0;
+        const uint32_t sz = emits ? (uint32_t)cfg.header_bytes + (uint32_t)pslot : 0u;
+        uint32_t pre = sz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, pre, d); if (lane >= d) pre += t; }
+        const uint32_t sum_sz = __shfl_sync(0xffffffffu, pre, 31), n_em = (uint32_t)__popc(__ballot_sync(0xffffffffu, emits));
+        if (lane < cnt) {
+          const bool is_final = (plan.flags & 1) && base + lane == nf - 1;
+          ScanFrame o;
+          o.padding = pad_l; o.is_final = is_final; o.huff = (int)huff;
+          o.mdb = is_final ? 0 : (int)min(w_before - r_before, 511u);                    // SRC:499, 2099-2101
+          o.res_bits = is_final ? 0 : (int)avail_l * 8;
+          o.bpg = (mds_l * 8 + (o.res_bits * 9) / 10) >> ngc_shift;
+          o.w_off = w_before;
+          o.e_take = emits ? min((uint32_t)pslot, w_after - r_before) : 0xFFFFFFFFu;
+          o.e_src = emits ? r_before : 0u; o.e_out = emits ? out_pos + pre - sz : 0u;
+          sh_fr[lane] = o;
+          for (int j = 0; j < ngc; ++j) sh_bpg[lane * ngc + j] = (uint16_t)min(o.bpg, 65535);
+        }
+        out_pos += sum_sz; total_bytes += sum_sz; frame_count += n_em; n_emit += n_em;
+        prev_slot = __shfl_sync(0xffffffffu, mds_l, cnt - 1);
+      }
+    } else
     {  // (2) the serial chain, SRC:475-568.  Every lane carries the scalar recurrences (padding, reservoir, cursors)
        // redundantly, lane j < ngc additionally walks the curve of gc j: the per-frame critical path is the reservoir
        // update plus one curve look-up plus two shuffles instead of four look-ups in sequence.
