@@ -88,8 +88,14 @@ __device__ __forceinline__ double drsqrt_fast(double d) {
 }
 
 // [OD3] |x|^0.75 = (float)(sqrt(d) * sqrt(sqrt(d))) in IEEE double, a >= 1e-10f; evaluated as d * (d^1/2)^-1/2.
-__device__ __forceinline__ float pow34(float a) {
-  const double d = (double)a;
+// exact widening of a POSITIVE NORMAL float with integer operations: the conversion instruction (F2F) runs on the XU pipe, one
+// warp instruction per 8 cycles per scheduler, which MUFU.RSQ64H and the quantizer's F2I already keep busy
+__device__ __forceinline__ double widen_normal(float a) {
+  const uint32_t b = __float_as_uint(a);
+  return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+template <bool NORMAL = true> __device__ __forceinline__ float pow34(float a) {
+  const double d = NORMAL ? widen_normal(a) : (double)a;
   const double r = __dmul_rn(d, drsqrt_fast(d));                   // d^1/2
   return __double2float_rn(__dmul_rn(d, drsqrt_fast(r)));          // d * d^-1/4
 }
@@ -106,6 +112,10 @@ __device__ __forceinline__ float pow34_reference(float a) {      // the same wit
 // Huffman tables indexed by (ux, uy) (tab::kLen31s, tab::kTab31, row stride 32) save the increment, shift and clamp per value;
 // q != 0 <=> u != 0.
 __device__ __forceinline__ int quant30(float mag, float inv2) { return min(__float2int_rd(__fmul_rn(mag, inv2)), 30); }
+// the same index without the conversion instruction (XU pipe): 2^23 + floor(min(t, 30.5)) by an addition that rounds down; the
+// index of a pair is ((mx << 5) + my) & 1023 on the bit patterns (2^23 as a float is 0x4B000000: nothing of it survives the mask)
+__device__ __forceinline__ uint32_t quant30m(float mag, float inv2) { return __float_as_uint(__fadd_rd(fminf(__fmul_rn(mag, inv2), 30.5f), 8388608.0f)); }
+__device__ __forceinline__ int pair_index(float mx, float my, float inv2) { return (int)(((quant30m(mx, inv2) << 5) + quant30m(my, inv2)) & 1023u); }
 
 // a / d correctly rounded for d = 9 and d = 3 (r = RN(1 / d)): quotient estimate, exact residual, one correction.
 // tools/check_div.c compares it with the IEEE division for all 2^32 floats (signed zeros and denormals included).
@@ -119,14 +129,21 @@ __device__ __forceinline__ float div_exact(float a, float d, float r) {
 #include "iso_mode.cuh"   // opt-in ISO mode: quantizer, partition, table selection (needs the warp helpers above)
 namespace mp3b {
 
+// x / 192 as (x / 3) / 64: the division by 64 is exact unless the quotient is subnormal (then the IEEE division)
+__device__ __forceinline__ float div192(float x) {
+  return x >= 1e-30f ? __fmul_rn(div_exact(x, 3.0f, 1.0f / 3.0f), 0.015625f) : __fdiv_rn(x, 192.0f);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // K0: pre-pass.  One warp per frame: frame energy (SRC:477), stereo decision (SRC:2140-2162), granule energies
 // (SRC:673), transient thirds -> block type + subblock_gain (SRC:1944-1968).
 
-__device__ __forceinline__ void transient_decide(const float e3[3], int &bt, int sbg[3]) {
+// ALL_SBG = false: subblock_gain only where it is coded (window-switched granules, SRC:586-624); long granules get 0
+template <bool ALL_SBG = true> __device__ __forceinline__ void transient_decide(const float e3[3], int &bt, int sbg[3]) {
   float mx = fmaxf(e3[0], fmaxf(e3[1], e3[2])), mn = fminf(e3[0], fminf(e3[1], e3[2]));
   float ratio = __fdiv_rn(mx, fmaxf(mn, 0.0001f));
   if (ratio > 6.0f) bt = (e3[0] == mx) ? 1 : 2; else bt = 0;
+  if (!ALL_SBG && bt == 0) { sbg[0] = sbg[1] = sbg[2] = 0; return; }
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     float normalized = fminf(fmaxf(__fdiv_rn(e3[i], fmaxf(mx, 0.0001f)), 0.0f), 1.0f);
@@ -284,7 +301,7 @@ constexpr int kLook = 15;                         // 480 samples of look-back = 
 
 __device__ __forceinline__ int gain_from_peak(float peak) {      // computeGlobalGain SRC:989-1006
   if (!(peak > 0.0f)) return 210;
-  float ratio = __fdiv_rn(pow34(peak), 15.0f);
+  float ratio = __fdiv_rn(pow34<false>(peak), 15.0f);
   if (ratio <= 0.0f) return 210;
   double r = (double)ratio;
   // 210 + Int(4*log2(r)): Int() truncates toward zero.  i = largest index with 2^((i-210)/4) <= r.
@@ -573,7 +590,9 @@ __device__ __forceinline__ int lo_bits_of(const Config &cfg, int bri) {
 constexpr int kGranulePerWarp = 1;   // 4 measured slower (6.0 vs 5.7 ms): one granule-channel per warp keeps the tail short
 // TRACE: also leave the MDCT spectrum behind.  PRE: no k_prepass ran (CBR, not joint stereo, no trace: nothing but the block
 // type is needed from the PCM) — the warp reads its granule's 576 samples itself and decides the block type (SRC:1944-1968).
-template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256, 4) k_granule(Config cfg, PassBuffers pb) {
+// CH: the channel count as a compile-time constant (0 = cfg.channels) — the product variant's 18 PCM loads then carry their
+// strides as immediates instead of computing 18 addresses.
+template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_bounds__(256, 4) k_granule(Config cfg, PassBuffers pb) {
   __shared__ __align__(16) uint8_t len31[ISO ? 16 : 31 * 32];   // table-15 code length of a pair + its sign bits (SRC:828-853), indexed by quant30
   __shared__ __align__(16) uint8_t iso_len[ISO ? (kHuffEntries + 15) / 16 * 16 : 16];   // ISO mode: all Huffman length tables
   __shared__ uint8_t iso_c[ISO ? 8 : 1][ISO ? 288 : 1];
@@ -581,7 +600,7 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
   __shared__ uint8_t s_swid[ISO ? 192 : 1];
   __shared__ __align__(8) float smg[8][576];
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ch = cfg.channels, chs = ch - 1;         // channels = 1 or 2: / ch is >> chs
+  const int ch = CH ? CH : cfg.channels, chs = ch - 1;   // channels = 1 or 2: / ch is >> chs
   // a warp walks kGranulePerWarp granule-channels: the table staging below and the CTA start-up are paid once for all
   for (int rep = 0; rep < kGranulePerWarp; ++rep) {
   const int gci = (blockIdx.y * kGranulePerWarp + rep) * 8 + warp;
@@ -635,9 +654,9 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
         float a = 0.0f;
 #pragma unroll
         for (int jj = 0; jj < 6; ++jj) a = __fmaf_rn(pc[6 * th + jj], pc[6 * th + jj], a);
-        e3[th] = __fdiv_rn(lane_tree(a), 192.0f);
+        e3[th] = div192(lane_tree(a));
       }
-      transient_decide(e3, bt, sbg);
+      transient_decide<false>(e3, bt, sbg);      // the trace plane, which shows subblock_gain of every granule, runs k_prepass
       if (lane == 0) pb.gc_bt[gslot] = (uint16_t)(bt | sbg[0] << 2 | sbg[1] << 5 | sbg[2] << 8);
     } else if (ISO) {
       if (cfg.iso >= 3) bt = pb.gc_bt[gslot] & 3;                 // level 3: ISO block type 0 / 1 start / 2 short / 3 stop from k_iso_blocktype
@@ -782,7 +801,7 @@ template <bool TRACE, bool PRE, bool ISO> __global__ void __launch_bounds__(256,
     int total = 0, last = 0;
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
-      const int idx = quant30(mx[j], inv2) * 32 + quant30(my[j], inv2);
+      const int idx = pair_index(mx[j], my[j], inv2);
       total += len31[idx];
       if (idx) last = lane + 32 * j + 1;
     }
@@ -1228,7 +1247,7 @@ template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta, 
     for (int j = 0; j < 9; ++j) {
       const int p = 9 * lane + j;
       const float2 v = cur.v[j];
-      const int qx = quant30(fabsf(v.x), inv), qy = quant30(fabsf(v.y), inv);     // (u, not q: non-zero exactly when q is)
+      const int qx = quant30(fabsf(v.x), inv), qy = quant30(fabsf(v.y), inv);     // (u, not q: non-zero exactly when q is; the conversion-free form of k_granule measured slower here: 12.5 vs 12.3 ms)
       if (TRACE) { const int ax = (qx + 1) >> 1, ay = (qy + 1) >> 1; trix[2 * p] = v.x < 0.0f ? -ax : ax; trix[2 * p + 1] = v.y < 0.0f ? -ay : ay; }
       const uint32_t t15 = tab31[qx * 32 + qy];
       uint32_t code = t15 & 255u; int l = (int)(t15 >> 8);
@@ -1786,7 +1805,7 @@ int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st, bool
   dim3 grid(cfg.n_streams, (pb.max_frames * 2 * cfg.channels + 8 * kGranulePerWarp - 1) / (8 * kGranulePerWarp));
   if (cfg.iso) { if (pb.spec) k_granule<true, false, true><<<grid, 256, 0, st>>>(cfg, pb); else k_granule<false, false, true><<<grid, 256, 0, st>>>(cfg, pb); }
   else if (pb.spec) k_granule<true, false, false><<<grid, 256, 0, st>>>(cfg, pb);
-  else if (fused_prepass) k_granule<false, true, false><<<grid, 256, 0, st>>>(cfg, pb);
+  else if (fused_prepass) { if (cfg.channels == 2) k_granule<false, true, false, 2><<<grid, 256, 0, st>>>(cfg, pb); else k_granule<false, true, false, 1><<<grid, 256, 0, st>>>(cfg, pb); }
   else k_granule<false, false, false><<<grid, 256, 0, st>>>(cfg, pb);
   return check(1);
 }
