@@ -70,6 +70,18 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int m = 16; m >= 1; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
   return v;
 }
+// lane_tree of two values for the price of one and a half: the upper half-warp reduces b while the lower one reduces a (the
+// same additions as the butterfly performs in those lanes), then both results are broadcast.
+__device__ __forceinline__ void lane_tree_pair(float &a, float &b, int lane) {
+  const bool up = lane & 16;
+  float keep = up ? b : a;
+  keep = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, up ? a : b, 16));
+#pragma unroll
+  for (int m = 8; m >= 1; m >>= 1) keep = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, keep, m));
+  a = __shfl_sync(0xffffffffu, keep, 0); b = __shfl_sync(0xffffffffu, keep, 16);
+}
+// maximum of non-negative floats: their bit patterns order like unsigned integers (one REDUX instead of five shuffles and maxima)
+__device__ __forceinline__ float warp_max_nonneg(float v) { return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v))); }
 __device__ __forceinline__ int warp_max_i(int v) { return __reduce_max_sync(0xffffffffu, v); }   // REDUX: one instruction
 __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
@@ -306,8 +318,11 @@ __device__ __forceinline__ int gain_from_peak(float peak) {      // computeGloba
   double r = (double)ratio;
   // 210 + Int(4*log2(r)): Int() truncates toward zero.  i = largest index with 2^((i-210)/4) <= r.
   if (r < c_gain_thr[0]) return 0;
-  int lo = 0, hi = 255;
-  while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (c_gain_thr[mid] <= r) lo = mid; else hi = mid - 1; }
+  // start from the hardware logarithm (any estimate would do) and walk to the largest index whose threshold is <= r: zero or
+  // one step instead of the eight of a bisection
+  int lo = min(max(__float2int_rd(__fmaf_rn(__log2f(ratio), 4.0f, 210.0f)), 0), 255);
+  while (lo < 255 && c_gain_thr[lo + 1] <= r) ++lo;
+  while (lo > 0 && c_gain_thr[lo] > r) --lo;
   int gain = lo;                                                   // floor
   if (r < 1.0 && c_gain_thr[lo] != r) gain = lo + 1;               // negative values truncate upwards
   return gain > 255 ? 255 : gain;
@@ -616,6 +631,9 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
 #pragma unroll
     for (int k = 0; k < 36; ++k) v[k] = __ldg(prev + k * 32);
   }
+  // (requested here, not where they are used: after the barrier below their latency would stand in front of everything)
+  const int n_gc = (int)pb.plan[s].n_frames * 2 * ch;
+  const int bri_f = pb.frame_br[(size_t)s * pb.Fc + min(gci >> (chs + 1), pb.Fc - 1)];
   float pc[PRE ? 18 : 1];                            // PRE: sample 32 k + lane of the granule-channel
   if (PRE) {
     const PcmView pv = pcm_view(cfg, pb, s);
@@ -639,10 +657,9 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
     else if (threadIdx.x < 31 * 32 / 4) reinterpret_cast<uint32_t *>(len31)[threadIdx.x] = reinterpret_cast<const uint32_t *>(tab::kLen31s)[threadIdx.x];
     __syncthreads();
   }
-  if (gci >= (int)pb.plan[s].n_frames * 2 * ch) return;
+  if (gci >= n_gc) return;
   const size_t gslot = (size_t)s * pb.GC + gci;
-  const int f = gci >> (chs + 1);
-  const int lo_bits = lo_bits_of(cfg, pb.frame_br[(size_t)s * pb.Fc + f]);
+  const int lo_bits = lo_bits_of(cfg, bri_f);
   int bt_gc = 0;
   {
     int bt;
@@ -654,8 +671,12 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
         float a = 0.0f;
 #pragma unroll
         for (int jj = 0; jj < 6; ++jj) a = __fmaf_rn(pc[6 * th + jj], pc[6 * th + jj], a);
-        e3[th] = div192(lane_tree(a));
+        e3[th] = a;
       }
+      lane_tree_pair(e3[0], e3[1], lane);
+      e3[2] = lane_tree(e3[2]);
+#pragma unroll
+      for (int th = 0; th < 3; ++th) e3[th] = div192(e3[th]);
       transient_decide<false>(e3, bt, sbg);      // the trace plane, which shows subblock_gain of every granule, runs k_prepass
       if (lane == 0) pb.gc_bt[gslot] = (uint16_t)(bt | sbg[0] << 2 | sbg[1] << 5 | sbg[2] << 8);
     } else if (ISO) {
@@ -742,8 +763,9 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
       smag[i] = __uint_as_float(__float_as_uint(mag) | (__float_as_uint(x[j]) & 0x80000000u));   // sign of x on mag > 0 (a -0 line quantizes to 0 either way: no sign bit is coded)
       smg[warp][i] = mag;
     }
-    peak = warp_max(peak);
-    const float low = lane_tree(plo), high = lane_tree(phi);
+    peak = warp_max_nonneg(peak);
+    float low = plo, high = phi;
+    lane_tree_pair(low, high, lane);
     // every lane holds the same peak and energies: all of them derive g0 / preflag (no broadcast, no read-back)
     meta = (uint32_t)gain_from_peak(peak) | (uint32_t)(high > __fmul_rn(low, 1.5f) ? 1 : 0) << 17;
     __syncwarp();
