@@ -108,8 +108,23 @@ __device__ __forceinline__ double widen_normal(float a) {
 }
 template <bool NORMAL = true> __device__ __forceinline__ float pow34(float a) {
   const double d = NORMAL ? widen_normal(a) : (double)a;
+#if MP3B_POW34_V1
   const double r = __dmul_rn(d, drsqrt_fast(d));                   // d^1/2
   return __double2float_rn(__dmul_rn(d, drsqrt_fast(r)));          // d * d^-1/4
+#else
+  // d * d^-1/4 with ONE Newton step: seed q0 = y * y^-1/2 from two reciprocal-square-root approximations (y ~ d^-1/2, so
+  // q0 ~ d^-1/4 to about 2^-21), then the third-order step for the inverse fourth root, e = 1 - d q0^4,
+  // q = q0 (1 + e / 4 + 5 e^2 / 32): 8 FP64 instructions instead of 12 — the same exhaustive proof (mp3b_selftest)
+  double y, z;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(z) : "d"(y));
+  const double q0 = __dmul_rn(y, z);
+  const double q2 = __dmul_rn(q0, q0);
+  const double e = __fma_rn(-d, __dmul_rn(q2, q2), 1.0);
+  const double p = __fma_rn(e, 0.15625, 0.25);
+  const double q = __fma_rn(p, __dmul_rn(q0, e), q0);
+  return __double2float_rn(__dmul_rn(d, q));
+#endif
 }
 __device__ __forceinline__ float pow34_reference(float a) {      // the same with the library's IEEE square root
   double d = (double)a;
@@ -623,13 +638,18 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
   // the subband array (row 18 (g + 1) + t = step t of granule g; rows 0..17 = last granule of the previous pass).
   // They are requested before anything else — their addresses need nothing from memory — so that the frame count, the
   // block type and the bitrate index arrive under their latency instead of in front of it.
+  // The last rows are requested after the block-type decision: the MDCT needs them ~600 instructions later, and until then
+  // their registers hold the PCM samples of the decision (all 54 loads in flight at once spill).
+  constexpr int kEarlyRows = PRE ? 22 : 36;
   float v[36];
+  const float *prev_late;
   {
     const int gcl = min(gci, pb.GC - 1);             // the grid is rounded up to whole CTAs: stay inside the array
     const int g = gcl >> chs, c = gcl & chs;
     const float *prev = pb.sub + ((size_t)(s * ch + c) * pb.sub_rows + 18 * g) * 32 + lane;
 #pragma unroll
-    for (int k = 0; k < 36; ++k) v[k] = __ldg(prev + k * 32);
+    for (int k = 0; k < kEarlyRows; ++k) v[k] = __ldg(prev + k * 32);
+    prev_late = prev;
   }
   // (requested here, not where they are used: after the barrier below their latency would stand in front of everything)
   const int n_gc = (int)pb.plan[s].n_frames * 2 * ch;
@@ -684,6 +704,8 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
       else { bt = 0; if (lane == 0) pb.gc_bt[gslot] = 0; }        // levels 1, 2: long blocks only
     } else bt = pb.gc_bt[gslot] & 3;
     bt_gc = bt;
+#pragma unroll
+    for (int k = kEarlyRows; k < 36; ++k) v[k] = __ldg(prev_late + k * 32);
     float *X = smg[warp];
     const int sb = lane;
     const bool flip = sb & 1;
