@@ -143,6 +143,12 @@ __device__ __forceinline__ int quant30(float mag, float inv2) { return min(__flo
 // index of a pair is ((mx << 5) + my) & 1023 on the bit patterns (2^23 as a float is 0x4B000000: nothing of it survives the mask)
 __device__ __forceinline__ uint32_t quant30m(float mag, float inv2) { return __float_as_uint(__fadd_rd(fminf(__fmul_rn(mag, inv2), 30.5f), 8388608.0f)); }
 __device__ __forceinline__ int pair_index(float mx, float my, float inv2) { return (int)(((quant30m(mx, inv2) << 5) + quant30m(my, inv2)) & 1023u); }
+// ... with both products in one packed multiply (the same IEEE product per half)
+__device__ __forceinline__ int pair_index2(float2 m, float inv2) {
+  const float2 t = __fmul2_rn(m, make_float2(inv2, inv2));
+  const uint32_t ux = __float_as_uint(__fadd_rd(fminf(t.x, 30.5f), 8388608.0f)), uy = __float_as_uint(__fadd_rd(fminf(t.y, 30.5f), 8388608.0f));
+  return (int)(((ux << 5) + uy) & 1023u);
+}
 
 // a / d correctly rounded for d = 9 and d = 3 (r = RN(1 / d)): quotient estimate, exact residual, one correction.
 // tools/check_div.c compares it with the IEEE division for all 2^32 floats (signed zeros and denormals included).
@@ -793,8 +799,9 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
     __syncwarp();
   }
   float mx[9], my[9];
+  float2 mxy[9];
 #pragma unroll
-  for (int j = 0; j < 9; ++j) { float2 v = reinterpret_cast<const float2 *>(smg[warp])[lane + 32 * j]; mx[j] = v.x; my[j] = v.y; }
+  for (int j = 0; j < 9; ++j) { mxy[j] = reinterpret_cast<const float2 *>(smg[warp])[lane + 32 * j]; mx[j] = mxy[j].x; my[j] = mxy[j].y; }
   uint16_t *bits_out = pb.gc_bits + gslot * kMaxEntries, *bv_out = pb.gc_bv + gslot * kMaxEntries;
   if (ISO && cfg.iso >= 2) { __syncwarp(); continue; }   // level 2: k_outer (iso_psy.cuh) takes it from the magnitudes
   if (ISO) {
@@ -845,7 +852,7 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
     int total = 0, last = 0;
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
-      const int idx = pair_index(mx[j], my[j], inv2);
+      const int idx = pair_index2(mxy[j], inv2);
       total += len31[idx];
       if (idx) last = lane + 32 * j + 1;
     }
