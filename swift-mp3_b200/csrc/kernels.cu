@@ -1266,6 +1266,14 @@ __global__ void __launch_bounds__(32) k_scan(Config cfg, PassBuffers pb) {
 // bytes are written once.  Nothing in the frame loop waits for another warp (the previous layout — a warp per
 // granule-channel, a CTA walking four frames — paid three block barriers per frame: mono 1.14 -> 0.97 ms, stereo 1.62 -> 1.60).
 constexpr int kPackFramesPerCta = 4;
+__device__ __forceinline__ void put_bits64(uint32_t *buf, uint32_t pos, unsigned long long v, int len) {   // len in 1...64, MSB first
+  const unsigned long long top = v << (64 - len);
+  const uint32_t w = pos >> 5, off = pos & 31;
+  const uint32_t a = (uint32_t)(top >> (32 + off)), b = (uint32_t)(top >> off), c = off ? (uint32_t)(top << (32 - off)) : 0u;
+  if (a) atomicOr(&buf[w], a);
+  if (b) atomicOr(&buf[w + 1], b);
+  if (c) atomicOr(&buf[w + 2], c);
+}
 struct PackGc { float2 v[9]; uint32_t sel, bitoff; };
 __device__ __forceinline__ void pack_load(const PassBuffers &pb, size_t gslot, int lane, PackGc &g) {
   const float2 *sm2 = reinterpret_cast<const float2 *>(pb.smag + gslot * 576) + 9 * lane;
@@ -1273,7 +1281,7 @@ __device__ __forceinline__ void pack_load(const PassBuffers &pb, size_t gslot, i
   for (int j = 0; j < 9; ++j) g.v[j] = __ldg(sm2 + j);
   g.sel = pb.gc_sel[gslot]; g.bitoff = pb.gc_bitoff[gslot];
 }
-template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta, TRACE ? 4 : 10) k_pack(Config cfg, PassBuffers pb) {   // TRACE: also leave ix behind
+template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta, TRACE ? 4 : 8) k_pack(Config cfg, PassBuffers pb) {   // TRACE: also leave ix behind
   __shared__ uint32_t bufs[kPackFramesPerCta][548];
   __shared__ __align__(16) uint16_t tab31[31 * 32];   // code | length << 8, indexed by quant30
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1304,23 +1312,22 @@ template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta, 
       uint32_t code = t15 & 255u; int l = (int)(t15 >> 8);
       if (qx) { code = code << 1 | __float_as_uint(v.x) >> 31; ++l; }   // SRC:1729-1736 (the magnitude carries the line's sign)
       if (qy) { code = code << 1 | __float_as_uint(v.y) >> 31; ++l; }
-      if (p >= bv) l = 0;
+      if (p >= bv) { l = 0; code = 0; }
       val[j] = code; len[j] = l; mine += l;
     }
     int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
     uint32_t pos = cur.bitoff + (uint32_t)(incl - mine);
+    // a lane's nine codes are consecutive in the stream: they are concatenated in registers (a code is at most 13 + 2 bits, four
+    // of them fit 64) and leave as three pieces instead of nine — each piece costs a dozen instructions and up to three atomics
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      if (len[j]) {
-        uint32_t w = pos >> 5, off = pos & 31;
-        unsigned long long v64 = (unsigned long long)val[j] << (64 - len[j] - off);
-        atomicOr(&buf[w], (uint32_t)(v64 >> 32));
-        uint32_t lo = (uint32_t)v64;
-        if (lo) atomicOr(&buf[w + 1], lo);
-        pos += len[j];
-      }
+    for (int j0 = 0; j0 < 9; j0 += 4) {
+      unsigned long long acc = 0; int al = 0;
+#pragma unroll
+      for (int j = j0; j < (j0 + 4 < 9 ? j0 + 4 : 9); ++j) { acc = acc << len[j] | val[j]; al += len[j]; }
+      if (al) put_bits64(buf, pos, acc, al);
+      pos += al;
     }
     if (g + 1 < ngc) pack_load(pb, gslot + 1, lane, cur);   // (holding the next one's magnitudes during the coding above costs more in occupancy than it hides: measured)
   }
@@ -1338,14 +1345,6 @@ template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta, 
 // big_values pairs with the region's table (+ linbits escapes, + sign bits), count1 quadruples with table A or B.  One warp per
 // frame; lane L codes pairs 9L...9L+8 and quadruples 5L...5L+4, bit positions from warp prefix sums.  The choices (regions,
 // table_select, count1table_select, big_values) go into the frame record for k_frames' side info.
-__device__ __forceinline__ void put_bits64(uint32_t *buf, uint32_t pos, unsigned long long v, int len) {   // len in 1...64, MSB first
-  const unsigned long long top = v << (64 - len);
-  const uint32_t w = pos >> 5, off = pos & 31;
-  const uint32_t a = (uint32_t)(top >> (32 + off)), b = (uint32_t)(top >> off), c = off ? (uint32_t)(top << (32 - off)) : 0u;
-  if (a) atomicOr(&buf[w], a);
-  if (b) atomicOr(&buf[w + 1], b);
-  if (c) atomicOr(&buf[w + 2], c);
-}
 template <bool TRACE> __global__ void __launch_bounds__(32 * kPackFramesPerCta) k_pack_iso(Config cfg, PassBuffers pb) {
   __shared__ uint32_t bufs[kPackFramesPerCta][552];
   __shared__ uint32_t s_huff[kHuffEntries];
