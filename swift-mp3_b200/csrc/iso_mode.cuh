@@ -66,7 +66,7 @@ struct IsoChoice {            // everything the side info and the bit packer nee
 // s_len: the concatenated length tables in shared memory; s_c: 288 bytes of warp scratch; sfb: cumulative band ends (21).
 // ws: the granule is window-switched (block type start / short / stop): the side info then has two regions only, region 0 = the
 // first 36 lines (ISO 11172-3 2.4.2.7: region0_count 7 resp. 8 and region1_count 13 are implied), two table_selects.
-__device__ __forceinline__ IsoChoice iso_evaluate(const int qx[9], const int qy[9], int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb, bool ws = false) {
+__device__ __noinline__ IsoChoice iso_evaluate(const int qx[9], const int qy[9], int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb, bool ws = false) {
   IsoChoice ch;
   int top = 0, big = 0;
 #pragma unroll

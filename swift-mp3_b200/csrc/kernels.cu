@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(kFbThreads, 3) k_filterbank(Config cfg, PassBu
         auto matrixing = [&](auto Mc) {
           constexpr int PFM = decltype(Mc)::value;
           const float4 *mrow = reinterpret_cast<const float4 *>(sM + (32 * H) * 32 + kg * 16);
-#pragma unroll 2
+#pragma unroll
           for (int a = 0; a < 4; ++a) {
             static_for<0, 8>([&](auto bc) {
               constexpr int b = decltype(bc)::value;
@@ -628,18 +628,19 @@ constexpr int kGranulePerWarp = 1;   // 4 measured slower (6.0 vs 5.7 ms): one g
 // type is needed from the PCM) — the warp reads its granule's 576 samples itself and decides the block type (SRC:1944-1968).
 // CH: the channel count as a compile-time constant (0 = cfg.channels) — the product variant's 18 PCM loads then carry their
 // strides as immediates instead of computing 18 addresses.
-template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_bounds__(256, 4) k_granule(Config cfg, PassBuffers pb) {
+constexpr int kGrWarps = 8;                      // warps (= granule-channels) per CTA
+template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_bounds__(32 * kGrWarps, 32 / kGrWarps) k_granule(Config cfg, PassBuffers pb) {
   __shared__ __align__(16) uint8_t len31[ISO ? 16 : 31 * 32];   // table-15 code length of a pair + its sign bits (SRC:828-853), indexed by quant30
   __shared__ __align__(16) uint8_t iso_len[ISO ? (kHuffEntries + 15) / 16 * 16 : 16];   // ISO mode: all Huffman length tables
-  __shared__ uint8_t iso_c[ISO ? 8 : 1][ISO ? 288 : 1];
+  __shared__ uint8_t iso_c[ISO ? kGrWarps : 1][ISO ? 288 : 1];
   __shared__ uint16_t s_spos[ISO ? 192 : 1];                    // ISO short blocks: line order by scalefactor band and window
   __shared__ uint8_t s_swid[ISO ? 192 : 1];
-  __shared__ __align__(8) float smg[8][576];
+  __shared__ __align__(8) float smg[kGrWarps][576];
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ch = CH ? CH : cfg.channels, chs = ch - 1;   // channels = 1 or 2: / ch is >> chs
   // a warp walks kGranulePerWarp granule-channels: the table staging below and the CTA start-up are paid once for all
   for (int rep = 0; rep < kGranulePerWarp; ++rep) {
-  const int gci = (blockIdx.y * kGranulePerWarp + rep) * 8 + warp;
+  const int gci = (blockIdx.y * kGranulePerWarp + rep) * kGrWarps + warp;
   // ---- MDCT (SRC:1512-1565): lane = subband; the 36 time samples are the previous and the current granule's rows of
   // the subband array (row 18 (g + 1) + t = step t of granule g; rows 0..17 = last granule of the previous pass).
   // They are requested before anything else — their addresses need nothing from memory — so that the frame count, the
@@ -677,10 +678,10 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
   }
   if (rep == 0) {
     if (ISO) {
-      for (int i = threadIdx.x; i < kHuffEntries; i += 256) iso_len[i] = kHuffLenFlat[i];
-      if (threadIdx.x < 192) { s_spos[threadIdx.x] = c_short_pos[cfg.sfb_index][threadIdx.x]; s_swid[threadIdx.x] = c_short_width[cfg.sfb_index][threadIdx.x]; }
+      for (int i = threadIdx.x; i < kHuffEntries; i += 32 * kGrWarps) iso_len[i] = kHuffLenFlat[i];
+      for (int i = threadIdx.x; i < 192; i += 32 * kGrWarps) { s_spos[i] = c_short_pos[cfg.sfb_index][i]; s_swid[i] = c_short_width[cfg.sfb_index][i]; }
     }
-    else if (threadIdx.x < 31 * 32 / 4) reinterpret_cast<uint32_t *>(len31)[threadIdx.x] = reinterpret_cast<const uint32_t *>(tab::kLen31s)[threadIdx.x];
+    else for (int i = threadIdx.x; i < 31 * 32 / 4; i += 32 * kGrWarps) reinterpret_cast<uint32_t *>(len31)[i] = reinterpret_cast<const uint32_t *>(tab::kLen31s)[i];
     __syncthreads();
   }
   if (gci >= n_gc) return;
@@ -1852,11 +1853,11 @@ int launch_spectrum(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
 }
 int launch_curve(const Config &cfg, const PassBuffers &pb, cudaStream_t st, bool fused_prepass) {
   if (pb.max_frames <= 0) return 0;
-  dim3 grid(cfg.n_streams, (pb.max_frames * 2 * cfg.channels + 8 * kGranulePerWarp - 1) / (8 * kGranulePerWarp));
-  if (cfg.iso) { if (pb.spec) k_granule<true, false, true><<<grid, 256, 0, st>>>(cfg, pb); else k_granule<false, false, true><<<grid, 256, 0, st>>>(cfg, pb); }
-  else if (pb.spec) k_granule<true, false, false><<<grid, 256, 0, st>>>(cfg, pb);
-  else if (fused_prepass) { if (cfg.channels == 2) k_granule<false, true, false, 2><<<grid, 256, 0, st>>>(cfg, pb); else k_granule<false, true, false, 1><<<grid, 256, 0, st>>>(cfg, pb); }
-  else k_granule<false, false, false><<<grid, 256, 0, st>>>(cfg, pb);
+  dim3 grid(cfg.n_streams, (pb.max_frames * 2 * cfg.channels + kGrWarps * kGranulePerWarp - 1) / (kGrWarps * kGranulePerWarp));
+  if (cfg.iso) { if (pb.spec) k_granule<true, false, true><<<grid, 32 * kGrWarps, 0, st>>>(cfg, pb); else k_granule<false, false, true><<<grid, 32 * kGrWarps, 0, st>>>(cfg, pb); }
+  else if (pb.spec) k_granule<true, false, false><<<grid, 32 * kGrWarps, 0, st>>>(cfg, pb);
+  else if (fused_prepass) { if (cfg.channels == 2) k_granule<false, true, false, 2><<<grid, 32 * kGrWarps, 0, st>>>(cfg, pb); else k_granule<false, true, false, 1><<<grid, 32 * kGrWarps, 0, st>>>(cfg, pb); }
+  else k_granule<false, false, false><<<grid, 32 * kGrWarps, 0, st>>>(cfg, pb);
   return check(1);
 }
 int launch_blocktype(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
