@@ -66,7 +66,7 @@ struct IsoChoice {            // everything the side info and the bit packer nee
 // s_len: the concatenated length tables in shared memory; s_c: 288 bytes of warp scratch; sfb: cumulative band ends (21).
 // ws: the granule is window-switched (block type start / short / stop): the side info then has two regions only, region 0 = the
 // first 36 lines (ISO 11172-3 2.4.2.7: region0_count 7 resp. 8 and region1_count 13 are implied), two table_selects.
-__device__ __noinline__ IsoChoice iso_evaluate(const int qx[9], const int qy[9], int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb, bool ws = false) {
+__device__ __forceinline__ IsoChoice iso_evaluate_core(const int qx[9], const int qy[9], int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb, bool ws) {
   IsoChoice ch;
   int top = 0, big = 0;
 #pragma unroll
@@ -155,6 +155,22 @@ __device__ __noinline__ IsoChoice iso_evaluate(const int qx[9], const int qy[9],
   ch.c1sel = cb < ca;
   ch.bits = bits + min(ca, cb);
   return ch;
+}
+// ONE copy of the evaluation in the library, called from every search site: inlined into each of them (bisections, galloping
+// searches, the curve — nine sites in k_outer), the kernels were 350 KB of straight-line code and their warps spent most of the
+// time between two instructions waiting for instruction fetch (ncu: 35 of 40 cycles).
+__device__ __noinline__ IsoChoice iso_evaluate(const int qx[9], const int qy[9], int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb, bool ws = false) {
+  return iso_evaluate_core(qx, qy, lane, s_len, s_c, sfb, ws);
+}
+// The search form: quantize the warp's 288 pairs of (amplified) magnitudes m[lane + 32 j] at gain G and count.  Returns
+// min(bits, 65535) | big_values << 16 — one register, and the magnitudes stay in shared memory instead of 18 registers per lane.
+__device__ __noinline__ uint32_t iso_eval_gain(int G, const float2 *m, int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb, bool ws) {
+  const float inv = c_inv_step_iso[G];
+  int qx[9], qy[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) { const float2 v = m[lane + 32 * j]; qx[j] = iso_quant(v.x, inv); qy[j] = iso_quant(v.y, inv); }
+  const IsoChoice c = iso_evaluate_core(qx, qy, lane, s_len, s_c, sfb, ws);
+  return (uint32_t)min(c.bits, 65535) | (uint32_t)c.bv << 16;
 }
 
 

@@ -189,21 +189,33 @@ __constant__ uint8_t c_slen1[16] = {0, 0, 0, 0, 3, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4,
 __constant__ uint8_t c_slen2[16] = {0, 1, 2, 3, 0, 1, 2, 3, 1, 2, 3, 1, 2, 3, 2, 3};
 
 // K4 in ISO mode level 2 (north_star stage 4): the outer loop.  One warp per granule-channel.
-__global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuffers pb) {
+__global__ void __launch_bounds__(32 * kOuterWarps, 8) k_outer(Config cfg, PassBuffers pb) {
+  // The kernel is a chain of searches, each step one call of the shared evaluation function: latency-bound, so it wants resident
+  // warps, i.e. few registers — everything per-line lives in shared memory (amplified magnitudes, |xr|, band of a pair), the
+  // magnitudes themselves are re-read from HBM / L2 whenever the scalefactors change (at most eight times).
   __shared__ __align__(16) uint8_t s_len[(kHuffEntries + 15) / 16 * 16];
   __shared__ uint8_t s_c[kOuterWarps][288];
+  __shared__ uint8_t s_bnd[288];                                  // long scalefactor band of pair p
   __shared__ float s_val[kOuterWarps][288];
+  __shared__ __align__(8) float2 s_mag[kOuterWarps][288];         // magnitudes |xr|^0.75 amplified by the current scalefactors
+  __shared__ __align__(8) float2 s_ax[kOuterWarps][288];          // |xr| on the decoder's scale
   __shared__ int s_sf[kOuterWarps][2][24];                        // current and best scalefactors
   __shared__ float s_p43[256];                                    // ix^(4/3) for the values nearly all lines quantize to
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int *sfb = c_sfb_cum[cfg.sfb_index];
   for (int i = threadIdx.x; i < kHuffEntries; i += 32 * kOuterWarps) s_len[i] = kHuffLenFlat[i];
   for (int i = threadIdx.x; i < 256; i += 32 * kOuterWarps) s_p43[i] = pow43_fast((float)i);
+  for (int p = threadIdx.x; p < 288; p += 32 * kOuterWarps) {
+    int b = 0;
+#pragma unroll
+    for (int i = 0; i < 21; ++i) b += sfb[i] <= 2 * p;
+    s_bnd[p] = (uint8_t)b;
+  }
   __syncthreads();
   const int ch = cfg.channels, chs = ch - 1;
   const int gci = blockIdx.y * kOuterWarps + warp;
   if (gci >= (int)pb.plan[s].n_frames * 2 * ch) return;
   const size_t gslot = (size_t)s * pb.GC + gci;
-  const int *sfb = c_sfb_cum[cfg.sfb_index];
   const int bt = pb.gc_bt[gslot] & 3;                            // level 3: 1 start, 2 short, 3 stop
   const bool ws = bt != 0;
   const int f = gci >> (chs + 1);
@@ -211,45 +223,36 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
   const int lo_bits = min(lo_bits_of(cfg, bri), 4095);
   const int mds1 = cfg.frame_base[bri] + 1 - cfg.header_bytes;
   const int hi_bits = min(4095, (mds1 * 8 + min(511, mds1) * 8) >> cfg.channels);
-  // pairs p = lane + 32 j: magnitudes |xr|^0.75 (k_granule left them behind), |xr| on the decoder's scale, band of the pair
-  float mx[9], my[9], ax[9], ay[9];
-  int bnd[9];
-  {
-    const float2 *sm2 = reinterpret_cast<const float2 *>(pb.smag + gslot * 576);
+  // pairs p = lane + 32 j: magnitudes |xr|^0.75 (k_granule left them behind), |xr| on the decoder's scale
+  const float2 *sm2 = reinterpret_cast<const float2 *>(pb.smag + gslot * 576);
+  float2 *s_m = s_mag[warp], *s_a = s_ax[warp];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      const float2 v = __ldg(sm2 + lane + 32 * j);
-      mx[j] = fabsf(v.x); my[j] = fabsf(v.y);
-      ax[j] = 32768.0f * pow43_fast(mx[j]); ay[j] = 32768.0f * pow43_fast(my[j]);
-      int b = 0;
-#pragma unroll
-      for (int i = 0; i < 21; ++i) b += sfb[i] <= 2 * (lane + 32 * j);
-      bnd[j] = b;
-    }
+  for (int j = 0; j < 9; ++j) {
+    const float2 v = __ldg(sm2 + lane + 32 * j);
+    const float ax = 32768.0f * pow43_fast(fabsf(v.x)), ay = 32768.0f * pow43_fast(fabsf(v.y));
+    s_a[lane + 32 * j] = make_float2(ax, ay);
+    s_val[warp][lane + 32 * j] = ax * ax + ay * ay;
   }
   // band sums of a per-pair quantity: lane b adds up the pairs of band b
   const int p_lo = lane == 0 ? 0 : lane < 22 ? sfb[lane - 1] >> 1 : 288, p_hi = lane < 21 ? sfb[lane] >> 1 : 288;
   auto band_sum = [&]() { float a = 0.0f; for (int p = p_lo; p < p_hi; ++p) a += s_val[warp][p]; return a; };
-#pragma unroll
-  for (int j = 0; j < 9; ++j) s_val[warp][lane + 32 * j] = ax[j] * ax[j] + ay[j] * ay[j];
   __syncwarp();
   const float xmin = lane < 22 ? pb.gc_psy[gslot * 24 + lane] * band_sum() : 0.0f;
   __syncwarp();
   int *sf = s_sf[warp][0], *best = s_sf[warp][1];
   if (lane < 24) { sf[lane] = 0; best[lane] = 0; }
   __syncwarp();
-  float a34[9];
+  // the amplified magnitudes of the current scalefactors (a lane reads back only what it wrote)
   auto load_amp = [&](const int *q) {
 #pragma unroll
-    for (int j = 0; j < 9; ++j) a34[j] = c_amp34[q[bnd[j]]];
+    for (int j = 0; j < 9; ++j) {
+      const float2 v = __ldg(sm2 + lane + 32 * j);
+      const float a34 = c_amp34[q[s_bnd[lane + 32 * j]]];
+      s_m[lane + 32 * j] = make_float2(__fmul_rn(fabsf(v.x), a34), __fmul_rn(fabsf(v.y), a34));
+    }
   };
-  auto eval = [&](int G) {
-    const float inv = c_inv_step_iso[G];
-    int qx[9], qy[9];
-#pragma unroll
-    for (int j = 0; j < 9; ++j) { qx[j] = iso_quant(__fmul_rn(mx[j], a34[j]), inv); qy[j] = iso_quant(__fmul_rn(my[j], a34[j]), inv); }
-    return iso_evaluate(qx, qy, lane, s_len, s_c[warp], sfb, ws);
-  };
+  auto eval = [&](int G) { return iso_eval_gain(G, s_m, lane, s_len, s_c[warp], sfb, ws); };   // min(bits, 65535) | big_values << 16
+  auto bits_of = [](uint32_t c) { return (int)(c & 0xFFFFu); };
   auto part2_of = [&](const int *q, int &sfc) {                  // cheapest scalefac_compress that holds the scalefactors
     int m1 = 0, m2 = 0;
     for (int i = 0; i < 11; ++i) m1 = max(m1, q[i]);
@@ -265,13 +268,13 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
   // previous outer iteration's gain: amplifying bands only adds bits), search_down downwards from a gain known to fit (the curve
   // starts below the outer loop's gain: its budget is larger), and only the very first search bisects the whole range.
   auto bisect = [&](int lo, int hi, int budget) {                  // invariant: gains < lo do not fit, hi fits
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (eval(mid).bits <= budget) hi = mid; else lo = mid + 1; }
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (bits_of(eval(mid)) <= budget) hi = mid; else lo = mid + 1; }
     return hi;
   };
   auto search_up = [&](int from, int budget) {
     int lo = from, hi = kIsoGainMax;
     for (int stp = 1; lo + stp < hi; stp <<= 1) {
-      if (eval(lo + stp - 1).bits <= budget) { hi = lo + stp - 1; break; }
+      if (bits_of(eval(lo + stp - 1)) <= budget) { hi = lo + stp - 1; break; }
       lo = lo + stp;
     }
     return bisect(lo, hi, budget);
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
   auto search_down = [&](int fits, int budget) {
     int hi = fits, lo = 0;
     for (int stp = 1; hi - stp > 0; stp <<= 1) {
-      if (eval(hi - stp).bits > budget) { lo = hi - stp + 1; break; }
+      if (bits_of(eval(hi - stp)) > budget) { lo = hi - stp + 1; break; }
       hi = hi - stp;
     }
     return bisect(lo, hi, budget);
@@ -296,10 +299,11 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
     const float inv = c_inv_step_iso[G], step = c_step_iso[G];
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
-      const int qx = iso_quant(__fmul_rn(mx[j], a34[j]), inv), qy = iso_quant(__fmul_rn(my[j], a34[j]), inv);
-      const float back = step * c_ampinv[sf[bnd[j]]];
+      const float2 m = s_m[lane + 32 * j], a = s_a[lane + 32 * j];
+      const int qx = iso_quant(m.x, inv), qy = iso_quant(m.y, inv);
+      const float back = step * c_ampinv[sf[s_bnd[lane + 32 * j]]];
       const float px = qx < 256 ? s_p43[qx] : pow43_fast((float)qx), py = qy < 256 ? s_p43[qy] : pow43_fast((float)qy);
-      const float dx = ax[j] - px * back, dy = ay[j] - py * back;
+      const float dx = a.x - px * back, dy = a.y - py * back;
       s_val[warp][lane + 32 * j] = dx * dx + dy * dy;
     }
     __syncwarp();
@@ -330,15 +334,15 @@ __global__ void __launch_bounds__(32 * kOuterWarps) k_outer(Config cfg, PassBuff
   int n = 0, g_last = g_first, fitted = 0;
   for (int e = 0; e < kMaxEntries - 1 && !fitted; ++e) {
     const int Ge = min(g_first + e, kIsoGainMax);
-    const IsoChoice c = eval(Ge);
-    if (lane == 0) { bits_out[e] = (uint16_t)min(c.bits + part2, 65535); bv_out[e] = (uint16_t)c.bv; }
+    const uint32_t c = eval(Ge);
+    if (lane == 0) { bits_out[e] = (uint16_t)min(bits_of(c) + part2, 65535); bv_out[e] = (uint16_t)(c >> 16); }
     n = e + 1; g_last = Ge;
-    fitted = c.bits + part2 <= lo_bits || Ge == kIsoGainMax;
+    fitted = bits_of(c) + part2 <= lo_bits || Ge == kIsoGainMax;
   }
   if (!fitted) {
     const int Gl = search_up(min(g_first + kMaxEntries - 1, kIsoGainMax), max(lo_bits - part2, 0));
-    const IsoChoice c = eval(Gl);
-    if (lane == 0) { bits_out[kMaxEntries - 1] = (uint16_t)min(c.bits + part2, 65535); bv_out[kMaxEntries - 1] = (uint16_t)c.bv; }
+    const uint32_t c = eval(Gl);
+    if (lane == 0) { bits_out[kMaxEntries - 1] = (uint16_t)min(bits_of(c) + part2, 65535); bv_out[kMaxEntries - 1] = (uint16_t)(c >> 16); }
     n = kMaxEntries; g_last = Gl;
   }
   if (lane == 0) pb.gc_meta[gslot] = (uint32_t)g_first | (uint32_t)n << 9 | (uint32_t)g_last << 14;

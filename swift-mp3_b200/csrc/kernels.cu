@@ -817,29 +817,25 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
     const int lo_fit = min(lo_bits, 4095);
     const int *sfb = c_sfb_cum[cfg.sfb_index];
     const bool ws = bt_gc != 0;
-    auto eval = [&](int G) {
-      const float inv = c_inv_step_iso[G];
-      int qx[9], qy[9];
-#pragma unroll
-      for (int j = 0; j < 9; ++j) { qx[j] = iso_quant(mx[j], inv); qy[j] = iso_quant(my[j], inv); }
-      return iso_evaluate(qx, qy, lane, iso_len, iso_c[warp], sfb, ws);
-    };
+    // the magnitudes are read from the warp's tile (pair p = lines 2 p, 2 p + 1 as one float2) by the shared evaluation function
+    const float2 *mt = reinterpret_cast<const float2 *>(smg[warp]);
+    auto eval = [&](int G) { return iso_eval_gain(G, mt, lane, iso_len, iso_c[warp], sfb, ws); };   // bits | big_values << 16
     int lo = 0, hi = kIsoGainMax;                     // invariant: the count at `hi` fits (at kIsoGainMax every line quantizes to 0)
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (eval(mid).bits <= hi_bits) hi = mid; else lo = mid + 1; }
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)(eval(mid) & 0xFFFFu) <= hi_bits) hi = mid; else lo = mid + 1; }
     const int g_first = hi;
     int n = 0, g_last = g_first, fitted = 0;
     for (int e = 0; e < kMaxEntries - 1 && !fitted; ++e) {
       const int G = min(g_first + e, kIsoGainMax);
-      const IsoChoice c = eval(G);
-      if (lane == 0) { bits_out[e] = (uint16_t)min(c.bits, 65535); bv_out[e] = (uint16_t)c.bv; }
+      const uint32_t c = eval(G);
+      if (lane == 0) { bits_out[e] = (uint16_t)(c & 0xFFFFu); bv_out[e] = (uint16_t)(c >> 16); }
       n = e + 1; g_last = G;
-      fitted = c.bits <= lo_fit || G == kIsoGainMax;
+      fitted = (int)(c & 0xFFFFu) <= lo_fit || G == kIsoGainMax;
     }
     if (!fitted) {
       lo = min(g_first + kMaxEntries - 1, kIsoGainMax); hi = kIsoGainMax;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (eval(mid).bits <= lo_fit) hi = mid; else lo = mid + 1; }
-      const IsoChoice c = eval(hi);
-      if (lane == 0) { bits_out[kMaxEntries - 1] = (uint16_t)min(c.bits, 65535); bv_out[kMaxEntries - 1] = (uint16_t)c.bv; }
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)(eval(mid) & 0xFFFFu) <= lo_fit) hi = mid; else lo = mid + 1; }
+      const uint32_t c = eval(hi);
+      if (lane == 0) { bits_out[kMaxEntries - 1] = (uint16_t)(c & 0xFFFFu); bv_out[kMaxEntries - 1] = (uint16_t)(c >> 16); }
       n = kMaxEntries; g_last = hi;
     }
     if (lane == 0) pb.gc_meta[gslot] = (uint32_t)g_first | (uint32_t)n << 9 | (uint32_t)g_last << 14;   // 9 + 5 + 9 bits
