@@ -66,15 +66,19 @@ struct IsoChoice {            // everything the side info and the bit packer nee
 // s_len: the concatenated length tables in shared memory; s_c: 288 bytes of warp scratch; sfb: cumulative band ends (21).
 // ws: the granule is window-switched (block type start / short / stop): the side info then has two regions only, region 0 = the
 // first 36 lines (ISO 11172-3 2.4.2.7: region0_count 7 resp. 8 and region1_count 13 are implied), two table_selects.
-__device__ __forceinline__ IsoChoice iso_evaluate_core(const int qx[9], const int qy[9], int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb, bool ws) {
+// Q: q(j, x, y) delivers the quantized pair lane + 32 j — from registers (U = 9: fully unrolled, the bit packer's single call) or from
+// the warp's scratch in shared memory (U = 3: the search function, whose code has to stay small enough for the instruction cache:
+// fully unrolled it is 36 KB that every one of ~40 calls per granule-channel streams through).
+template <int U, class Q> __device__ __forceinline__ IsoChoice iso_evaluate_core(Q q, int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb, bool ws) {
   IsoChoice ch;
   int top = 0, big = 0;
-#pragma unroll
+#pragma unroll U
   for (int j = 0; j < 9; ++j) {
     const int p = lane + 32 * j;
-    if (qx[j] | qy[j]) top = p + 1;
-    if (qx[j] > 1 || qy[j] > 1) big = p + 1;
-    s_c[p] = (uint8_t)((qx[j] & 1) << 1 | (qy[j] & 1));            // only read for pairs of the count1 region (values 0 / 1)
+    int qx, qy; q(j, qx, qy);
+    if (qx | qy) top = p + 1;
+    if (qx > 1 || qy > 1) big = p + 1;
+    s_c[p] = (uint8_t)((qx & 1) << 1 | (qy & 1));                  // only read for pairs of the count1 region (values 0 / 1)
   }
   top = warp_max_i(top); big = warp_max_i(big);
   ch.c1 = (top - big) >> 1;                                        // quadruples of |value| <= 1 from the top down
@@ -90,9 +94,10 @@ __device__ __forceinline__ IsoChoice iso_evaluate_core(const int qx[9], const in
   ch.a1 = sfb[k0 - 1]; ch.a2 = k0 + k1 - 1 < 21 ? sfb[k0 + k1 - 1] : 576;
   if (ws) { ch.r0 = 0; ch.r1 = 0; ch.a1 = 36; ch.a2 = 576; }
   int m0 = 0, m1 = 0, m2 = 0;
-#pragma unroll
+#pragma unroll U
   for (int j = 0; j < 9; ++j) {
-    const int p = lane + 32 * j, m = max(qx[j], qy[j]);
+    int qx, qy; q(j, qx, qy);
+    const int p = lane + 32 * j, m = max(qx, qy);
     if (p < ch.bv) { if (2 * p < ch.a1) m0 = max(m0, m); else if (2 * p < ch.a2) m1 = max(m1, m); else m2 = max(m2, m); }
   }
   m0 = warp_max_i(m0); m1 = warp_max_i(m1); m2 = warp_max_i(m2);
@@ -107,14 +112,15 @@ __device__ __forceinline__ IsoChoice iso_evaluate_core(const int qx[9], const in
   // at most 19 bits); values >= 15 per region (10-bit fields) for the linbits; sign bits; count1 bits with table A and with table B
   unsigned long long acc[3] = {0ull, 0ull, 0ull};
   uint32_t n15 = 0, misc = 0;                                       // misc: signs of big values (<= 576) | count1 A bits << 10 (<= 1440) | count1 B bits << 21 (<= 1152)
-#pragma unroll
+#pragma unroll U
   for (int j = 0; j < 9; ++j) {
     const int p = lane + 32 * j;
     if (p < ch.bv) {
+      int qx, qy; q(j, qx, qy);
       const int r = (2 * p >= ch.a1) + (2 * p >= ch.a2);
-      const int cx = min(qx[j], 15), cy = min(qy[j], 15);
-      n15 += (uint32_t)((qx[j] >= 15) + (qy[j] >= 15)) << (10 * r);
-      misc += (uint32_t)((qx[j] != 0) + (qy[j] != 0));
+      const int cx = min(qx, 15), cy = min(qy, 15);
+      n15 += (uint32_t)((qx >= 15) + (qy >= 15)) << (10 * r);
+      misc += (uint32_t)((qx != 0) + (qy != 0));
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const uint32_t dk = r == 0 ? d[0][k] : r == 1 ? d[1][k] : d[2][k];
@@ -124,11 +130,12 @@ __device__ __forceinline__ IsoChoice iso_evaluate_core(const int qx[9], const in
     }
   }
   __syncwarp();
-#pragma unroll
+#pragma unroll U
   for (int j = 0; j < 9; ++j) {
     const int p = lane + 32 * j;
     if (p >= ch.bv && p < ch.bv + 2 * ch.c1 && !((p - ch.bv) & 1)) {
-      const int idx = ((qx[j] & 1) << 3) | ((qy[j] & 1) << 2) | s_c[p + 1];
+      int qx, qy; q(j, qx, qy);
+      const int idx = ((qx & 1) << 3) | ((qy & 1) << 2) | s_c[p + 1];
       const int sg = __popc(idx);
       misc += (uint32_t)(quad_len_a(idx) + sg) << 10 | (uint32_t)(4 + sg) << 21;
     }
@@ -160,16 +167,18 @@ __device__ __forceinline__ IsoChoice iso_evaluate_core(const int qx[9], const in
 // searches, the curve — nine sites in k_outer), the kernels were 350 KB of straight-line code and their warps spent most of the
 // time between two instructions waiting for instruction fetch (ncu: 35 of 40 cycles).
 __device__ __noinline__ IsoChoice iso_evaluate(const int qx[9], const int qy[9], int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb, bool ws = false) {
-  return iso_evaluate_core(qx, qy, lane, s_len, s_c, sfb, ws);
+  return iso_evaluate_core<9>([&](int j, int &x, int &y) { x = qx[j]; y = qy[j]; }, lane, s_len, s_c, sfb, ws);
 }
 // The search form: quantize the warp's 288 pairs of (amplified) magnitudes m[lane + 32 j] at gain G and count.  Returns
-// min(bits, 65535) | big_values << 16 — one register, and the magnitudes stay in shared memory instead of 18 registers per lane.
-__device__ __noinline__ uint32_t iso_eval_gain(int G, const float2 *m, int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb, bool ws) {
+// min(bits, 65535) | big_values << 16 — one register; the magnitudes and the quantized values (sq: 288 words of scratch per warp,
+// a lane reads back only what it wrote) stay in shared memory.
+// U: unrolling of the pair loops — 3 for k_outer (~40 calls per granule-channel: the code has to stay in the instruction cache), 9 for
+// k_granule's level-1 search (fewer calls, more resident warps: the unrolled form measured 6 % faster there).
+template <int U> __device__ __noinline__ uint32_t iso_eval_gain(int G, const float2 *m, uint32_t *sq, int lane, const uint8_t *s_len, uint8_t *s_c, const int *sfb, bool ws) {
   const float inv = c_inv_step_iso[G];
-  int qx[9], qy[9];
-#pragma unroll
-  for (int j = 0; j < 9; ++j) { const float2 v = m[lane + 32 * j]; qx[j] = iso_quant(v.x, inv); qy[j] = iso_quant(v.y, inv); }
-  const IsoChoice c = iso_evaluate_core(qx, qy, lane, s_len, s_c, sfb, ws);
+#pragma unroll U
+  for (int j = 0; j < 9; ++j) { const float2 v = m[lane + 32 * j]; sq[lane + 32 * j] = (uint32_t)iso_quant(v.x, inv) | (uint32_t)iso_quant(v.y, inv) << 16; }
+  const IsoChoice c = iso_evaluate_core<U>([&](int j, int &x, int &y) { const uint32_t w = sq[lane + 32 * j]; x = (int)(w & 0xFFFFu); y = (int)(w >> 16); }, lane, s_len, s_c, sfb, ws);
   return (uint32_t)min(c.bits, 65535) | (uint32_t)c.bv << 16;
 }
 

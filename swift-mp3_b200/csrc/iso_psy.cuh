@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(32 * kOuterWarps, 8) k_outer(Config cfg, PassB
       s_m[lane + 32 * j] = make_float2(__fmul_rn(fabsf(v.x), a34), __fmul_rn(fabsf(v.y), a34));
     }
   };
-  auto eval = [&](int G) { return iso_eval_gain(G, s_m, lane, s_len, s_c[warp], sfb, ws); };   // min(bits, 65535) | big_values << 16
+  auto eval = [&](int G) { return iso_eval_gain<3>(G, s_m, reinterpret_cast<uint32_t *>(s_val[warp]), lane, s_len, s_c[warp], sfb, ws); };   // (s_val is free during the searches)   // min(bits, 65535) | big_values << 16
   auto bits_of = [](uint32_t c) { return (int)(c & 0xFFFFu); };
   auto part2_of = [&](const int *q, int &sfc) {                  // cheapest scalefac_compress that holds the scalefactors
     int m1 = 0, m2 = 0;

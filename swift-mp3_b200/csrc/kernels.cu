@@ -633,6 +633,7 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
   __shared__ __align__(16) uint8_t len31[ISO ? 16 : 31 * 32];   // table-15 code length of a pair + its sign bits (SRC:828-853), indexed by quant30
   __shared__ __align__(16) uint8_t iso_len[ISO ? (kHuffEntries + 15) / 16 * 16 : 16];   // ISO mode: all Huffman length tables
   __shared__ uint8_t iso_c[ISO ? kGrWarps : 1][ISO ? 288 : 1];
+  __shared__ uint32_t iso_q[ISO ? kGrWarps : 1][ISO ? 288 : 1];   // ISO mode: the quantized pairs of the gain being evaluated
   __shared__ uint16_t s_spos[ISO ? 192 : 1];                    // ISO short blocks: line order by scalefactor band and window
   __shared__ uint8_t s_swid[ISO ? 192 : 1];
   __shared__ __align__(8) float smg[kGrWarps][576];
@@ -819,7 +820,7 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
     const bool ws = bt_gc != 0;
     // the magnitudes are read from the warp's tile (pair p = lines 2 p, 2 p + 1 as one float2) by the shared evaluation function
     const float2 *mt = reinterpret_cast<const float2 *>(smg[warp]);
-    auto eval = [&](int G) { return iso_eval_gain(G, mt, lane, iso_len, iso_c[warp], sfb, ws); };   // bits | big_values << 16
+    auto eval = [&](int G) { return iso_eval_gain<9>(G, mt, iso_q[warp], lane, iso_len, iso_c[warp], sfb, ws); };   // bits | big_values << 16
     int lo = 0, hi = kIsoGainMax;                     // invariant: the count at `hi` fits (at kIsoGainMax every line quantizes to 0)
     while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)(eval(mid) & 0xFFFFu) <= hi_bits) hi = mid; else lo = mid + 1; }
     const int g_first = hi;
