@@ -628,7 +628,7 @@ constexpr int kGranulePerWarp = 1;   // 4 measured slower (6.0 vs 5.7 ms): one g
 // type is needed from the PCM) — the warp reads its granule's 576 samples itself and decides the block type (SRC:1944-1968).
 // CH: the channel count as a compile-time constant (0 = cfg.channels) — the product variant's 18 PCM loads then carry their
 // strides as immediates instead of computing 18 addresses.
-constexpr int kGrWarps = 8;                      // warps (= granule-channels) per CTA
+constexpr int kGrWarps = 8;                      // warps (= granule-channels) per CTA (4 and 16 measured slower: 39.4 / 41.4 vs 38.4 ms)
 template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_bounds__(32 * kGrWarps, 32 / kGrWarps) k_granule(Config cfg, PassBuffers pb) {
   __shared__ __align__(16) uint8_t len31[ISO ? 16 : 31 * 32];   // table-15 code length of a pair + its sign bits (SRC:828-853), indexed by quant30
   __shared__ __align__(16) uint8_t iso_len[ISO ? (kHuffEntries + 15) / 16 * 16 : 16];   // ISO mode: all Huffman length tables
@@ -644,10 +644,10 @@ template <bool TRACE, bool PRE, bool ISO, int CH = 0> __global__ void __launch_b
   const int gci = (blockIdx.y * kGranulePerWarp + rep) * kGrWarps + warp;
   // ---- MDCT (SRC:1512-1565): lane = subband; the 36 time samples are the previous and the current granule's rows of
   // the subband array (row 18 (g + 1) + t = step t of granule g; rows 0..17 = last granule of the previous pass).
-  // They are requested before anything else — their addresses need nothing from memory — so that the frame count, the
-  // block type and the bitrate index arrive under their latency instead of in front of it.
-  // The last rows are requested after the block-type decision: the MDCT needs them ~600 instructions later, and until then
-  // their registers hold the PCM samples of the decision (all 54 loads in flight at once spill).
+  // The first rows are requested before anything else — their addresses need nothing from memory —, the frame count and the
+  // bitrate index right behind them.  On the fused path the last 14 rows are requested after the block-type decision: the
+  // MDCT needs them ~400 instructions later, and until then their registers hold the PCM samples of the decision (all 54
+  // loads in flight at once spill, and a spill store of a loaded value holds up every load behind it).
   constexpr int kEarlyRows = PRE ? 22 : 36;
   float v[36];
   const float *prev_late;
