@@ -20,6 +20,7 @@
 namespace mp3b {
 
 constexpr int kPsyWarps = 4;
+constexpr int kPsySmemBytes = kPsyWarps * 1280 * 8;
 constexpr int kGainMaxIso = 319;                   // = kIsoGainMax
 __constant__ float c_step_iso[kGainMaxIso + 1];    // 2^((G - 210) / 4): the decoder's step
 __constant__ float c_amp34[16];                    // 2^(0.375 sf): what a scalefactor does to |xr|^0.75 (scalefac_scale = 0)
@@ -39,6 +40,10 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(
 
 // In-place radix-4 decimation-in-frequency FFT of N = 4^k points by one warp; tw[j] = exp(-2 pi i j / 1024).  X[k] ends up at
 // the base-4 digit reversal of k.
+// Element i lives at x[fpad(i)]: one element of padding after every four.  The last two passes (butterfly spans 4 and 1) touch
+// elements 16 resp. 4 apart per lane — unpadded that is 4 of the 32 banks (four times the shared-memory wavefronts needed),
+// padded a half-warp covers all of them.  (The array base must be a multiple of 4 elements.)
+__device__ __forceinline__ int fpad(int i) { return i + (i >> 2); }
 template <int N> __device__ __forceinline__ void warp_fft4(float2 *x, const float2 *tw, int lane) {
 #pragma unroll 1
   for (int L = N; L >= 4; L >>= 2) {
@@ -46,13 +51,14 @@ template <int N> __device__ __forceinline__ void warp_fft4(float2 *x, const floa
 #pragma unroll 2
     for (int t = lane; t < N / 4; t += 32) {
       const int pos = t & (q - 1), i0 = ((t - pos) << 2) + pos;
-      const float2 a = x[i0], b = x[i0 + q], c = x[i0 + 2 * q], d = x[i0 + 3 * q];
+      const int ja = fpad(i0), jb = fpad(i0 + q), jc = fpad(i0 + 2 * q), jd = fpad(i0 + 3 * q);
+      const float2 a = x[ja], b = x[jb], c = x[jc], d = x[jd];
       const float2 apc = make_float2(a.x + c.x, a.y + c.y), amc = make_float2(a.x - c.x, a.y - c.y);
       const float2 bpd = make_float2(b.x + d.x, b.y + d.y), bmd = make_float2(b.x - d.x, b.y - d.y);
-      x[i0] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
-      x[i0 + q] = cmul(make_float2(amc.x + bmd.y, amc.y - bmd.x), tw[pos * ts]);
-      x[i0 + 2 * q] = cmul(make_float2(apc.x - bpd.x, apc.y - bpd.y), tw[2 * pos * ts]);
-      x[i0 + 3 * q] = cmul(make_float2(amc.x - bmd.y, amc.y + bmd.x), tw[3 * pos * ts]);
+      x[ja] = make_float2(apc.x + bpd.x, apc.y + bpd.y);
+      x[jb] = cmul(make_float2(amc.x + bmd.y, amc.y - bmd.x), tw[pos * ts]);
+      x[jc] = cmul(make_float2(apc.x - bpd.x, apc.y - bpd.y), tw[2 * pos * ts]);
+      x[jd] = cmul(make_float2(amc.x - bmd.y, amc.y + bmd.x), tw[3 * pos * ts]);
     }
     __syncwarp();
   }
@@ -68,7 +74,7 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // K3 (north_star stage 3): one warp per granule-channel.  Output: gc_psy[gslot][0..21] = threshold / energy per long
 // scalefactor band, [22] = perceptual entropy, [23] = mean tonality (trace).
 __global__ void __launch_bounds__(32 * kPsyWarps) k_psy(Config cfg, PassBuffers pb) {
-  __shared__ __align__(16) float2 s_x[kPsyWarps][1024];
+  extern __shared__ __align__(16) float2 s_x_dyn[];               // [kPsyWarps][1280]: 1024 elements per warp, padded (fpad); dynamic: with it the CTA needs 52 KB
   __shared__ __align__(16) float2 s_tw[768];
   __shared__ float s_cw[kPsyWarps][132];
   __shared__ float s_part[kPsyWarps][3][kPsyMaxPart];
@@ -99,7 +105,7 @@ __global__ void __launch_bounds__(32 * kPsyWarps) k_psy(Config cfg, PassBuffers 
       v[i] = x * 32768.0f;
     }
   }
-  float2 *x = s_x[warp];
+  float2 *x = s_x_dyn + warp * 1280;
   // ---- unpredictability from three 256-point FFTs: windows start at 192, 384, 576 of the 1024
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
@@ -107,14 +113,14 @@ __global__ void __launch_bounds__(32 * kPsyWarps) k_psy(Config cfg, PassBuffers 
 #pragma unroll
     for (int w = 0; w < 3; ++w) {
       const int k = n - 192 - 192 * w;
-      if (k >= 0 && k < 256) x[256 * w + k] = make_float2(v[i] * T.hann256[k], 0.0f);
+      if (k >= 0 && k < 256) x[fpad(256 * w + k)] = make_float2(v[i] * T.hann256[k], 0.0f);
     }
   }
   __syncwarp();
-  warp_fft4<256>(x, s_tw, lane); warp_fft4<256>(x + 256, s_tw, lane); warp_fft4<256>(x + 512, s_tw, lane);
+  warp_fft4<256>(x, s_tw, lane); warp_fft4<256>(x + fpad(256), s_tw, lane); warp_fft4<256>(x + fpad(512), s_tw, lane);
   for (int j = lane; j <= 128; j += 32) {
     const int r = rev4_256(j & 255);
-    const float2 a0 = x[r], a1 = x[256 + r], a2 = x[512 + r];
+    const float2 a0 = x[fpad(r)], a1 = x[fpad(256 + r)], a2 = x[fpad(512 + r)];
     const float r0 = sqrtf(a0.x * a0.x + a0.y * a0.y), r1 = sqrtf(a1.x * a1.x + a1.y * a1.y), r2 = sqrtf(a2.x * a2.x + a2.y * a2.y);
     // unit vectors; e^(i (2 phi1 - phi0)) = u1^2 conj(u0)
     const float2 u0 = r0 > 0.0f ? make_float2(a0.x / r0, a0.y / r0) : make_float2(1.0f, 0.0f);
@@ -128,14 +134,14 @@ __global__ void __launch_bounds__(32 * kPsyWarps) k_psy(Config cfg, PassBuffers 
   __syncwarp();
   // ---- line energies from the 1024-point FFT
 #pragma unroll
-  for (int i = 0; i < 32; ++i) x[lane + 32 * i] = make_float2(v[i] * T.hann1024[lane + 32 * i], 0.0f);
+  for (int i = 0; i < 32; ++i) x[fpad(lane + 32 * i)] = make_float2(v[i] * T.hann1024[lane + 32 * i], 0.0f);
   __syncwarp();
   warp_fft4<1024>(x, s_tw, lane);
   float e[16], cw[16];
 #pragma unroll
   for (int t = 0; t < 16; ++t) {
     const int k = lane + 32 * t;
-    const float2 a = x[rev4_1024(k)];
+    const float2 a = x[fpad(rev4_1024(k))];
     e[t] = a.x * a.x + a.y * a.y;
     cw[t] = e[t] * (k < 206 ? s_cw[warp][(k + 2) >> 2] : 0.4f);
   }

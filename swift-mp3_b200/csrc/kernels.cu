@@ -1866,7 +1866,10 @@ int launch_blocktype(const Config &cfg, const PassBuffers &pb, cudaStream_t st) 
 int launch_psy(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
   if (pb.max_frames <= 0) return 0;
   dim3 grid(cfg.n_streams, (pb.max_frames * 2 * cfg.channels + kPsyWarps - 1) / kPsyWarps);
-  k_psy<<<grid, 32 * kPsyWarps, 0, st>>>(cfg, pb);
+  static bool psy_attr[64];
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 64 && !psy_attr[dev]) { cudaFuncSetAttribute(k_psy, cudaFuncAttributeMaxDynamicSharedMemorySize, kPsySmemBytes); psy_attr[dev] = true; }
+  k_psy<<<grid, 32 * kPsyWarps, kPsySmemBytes, st>>>(cfg, pb);
   return check(1);
 }
 int launch_outer(const Config &cfg, const PassBuffers &pb, cudaStream_t st) {
