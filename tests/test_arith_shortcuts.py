@@ -96,3 +96,23 @@ def test_lane_tree_pair_gives_the_butterflys_bits():
         ra, rb = _butterfly(a), _butterfly(b)
         assert len(set(ra.view(np.uint32))) == 1 and len(set(rb.view(np.uint32))) == 1     # every lane ends with the same bits
         assert keep[0].view(np.uint32) == ra[0].view(np.uint32) and keep[16].view(np.uint32) == rb[0].view(np.uint32)
+
+
+def test_pow34_newton_step_truncation_error():
+    """|x|^0.75 = d * q with q = q0 (1 + e / 4 + 5 e^2 / 32), e = 1 - d q0^4: in exact arithmetic, a seed q0 within 2^-19 of
+    d^-1/4 (the device's two rsqrt approximations give about 2^-21) leaves a relative error below 2^-52 — what remains on the
+    device is the rounding of its eight FP64 operations, and whether that ever reaches the float is what mp3b_selftest decides
+    exhaustively."""
+    from decimal import Decimal, getcontext
+    getcontext().prec = 60
+    rng = np.random.default_rng(6)
+    worst = Decimal(0)
+    for _ in range(1500):
+        d = Decimal(float(np.float32(np.exp(rng.uniform(np.log(1e-10), np.log(1e10))))))
+        true_q = 1 / d.sqrt().sqrt()
+        for rel in (Decimal(2) ** -19, -(Decimal(2) ** -19), Decimal(float(rng.uniform(-1, 1))) * Decimal(2) ** -21):
+            q0 = true_q * (1 + rel)
+            e = 1 - d * q0 ** 4
+            q = q0 * (1 + e / 4 + 5 * e * e / 32)
+            worst = max(worst, abs(q / true_q - 1))
+    assert worst < Decimal(2) ** -52, worst
